@@ -1,0 +1,256 @@
+"""ORACLE (test infrastructure, not product code): ctypes view of oracle/_build/liborc.so.
+
+Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference leg may import this.
+All values are canonical BabyBear u32; matrices are column-major numpy uint32 arrays of shape (width, height).
+"""
+import ctypes as C
+import os
+import subprocess
+import numpy as np
+
+_DIR = os.path.dirname(os.path.abspath(__file__))
+_SO = os.path.join(_DIR, "_build", "liborc.so")
+P = 2013265921
+GENERATOR = 31
+
+
+def build(force=False):
+    srcs = [os.path.join(_DIR, f) for f in ("ntt.c", "poseidon2.c", "air.c", "prove.c", "oracle.h", "bb31.h")]
+    if force or not os.path.exists(_SO) or any(os.path.getmtime(s) > os.path.getmtime(_SO) for s in srcs):
+        subprocess.check_call(["make", "-C", _DIR, "-s"])
+    return _SO
+
+
+class Span(C.Structure):
+    _fields_ = [("off", C.c_uint32), ("len", C.c_uint32)]
+
+
+class OriginalAir(C.Structure):
+    _fields_ = [("width", C.c_int32), ("height", C.c_int32), ("buffer", C.c_void_p), ("row_block_size", C.c_int32)]
+
+
+class Subst(C.Structure):
+    _fields_ = [("air_index", C.c_int32), ("col", C.c_int32), ("row", C.c_int32), ("apc_col", C.c_int32)]
+
+
+class DerivedSpec(C.Structure):
+    _fields_ = [("col_base", C.c_uint64), ("span", Span)]
+
+
+class Interaction(C.Structure):
+    _fields_ = [("bus_id", C.c_uint32), ("num_args", C.c_uint32), ("args_index_off", C.c_uint32)]
+
+
+class SegmentProof(C.Structure):
+    _fields_ = [("trace_root", C.c_uint32 * 8), ("quotient_root", C.c_uint32 * 8), ("alpha", C.c_uint32 * 4),
+                ("n_fri_layers", C.c_uint32), ("fri_roots", (C.c_uint32 * 8) * 32), ("fri_betas", (C.c_uint32 * 4) * 32),
+                ("final_poly", (C.c_uint32 * 4) * 8), ("final_len", C.c_uint32)]
+
+    def as_dict(self):
+        n = self.n_fri_layers
+        return {
+            "trace_root": list(self.trace_root), "quotient_root": list(self.quotient_root), "alpha": list(self.alpha),
+            "n_fri_layers": int(n), "fri_roots": [list(self.fri_roots[i]) for i in range(n)],
+            "fri_betas": [list(self.fri_betas[i]) for i in range(n)],
+            "final_poly": [list(self.final_poly[i]) for i in range(self.final_len)], "final_len": int(self.final_len),
+        }
+
+
+_lib = None
+
+
+def lib():
+    global _lib
+    if _lib is None:
+        build()
+        _lib = C.CDLL(_SO)
+        _lib.orc_eval_expr.restype = C.c_uint32
+        _lib.orc_challenger_sample.restype = C.c_uint32
+        _lib.orc_num_threads.restype = C.c_int
+    return _lib
+
+
+def _p(a):
+    return a.ctypes.data_as(C.c_void_p)
+
+
+def _u32(a):
+    return np.ascontiguousarray(a, dtype=np.uint32)
+
+
+def num_threads():
+    return lib().orc_num_threads()
+
+
+def dft_naive(coeffs, shift=1):
+    a = _u32(coeffs)
+    out = np.empty_like(a)
+    lib().orc_dft_naive(_p(a), _p(out), C.c_uint(a.size.bit_length() - 1), C.c_uint32(shift))
+    return out
+
+
+def ntt(a):
+    a = _u32(a).copy()
+    lib().orc_ntt(_p(a), C.c_uint(a.size.bit_length() - 1))
+    return a
+
+
+def intt(a):
+    a = _u32(a).copy()
+    lib().orc_intt(_p(a), C.c_uint(a.size.bit_length() - 1))
+    return a
+
+
+def lde_batch(trace, log_blowup=1, shift=GENERATOR):
+    """trace: (width, n) column-major -> (width, n << log_blowup), rows bit-reversed."""
+    t = _u32(trace)
+    w, n = t.shape
+    out = np.empty((w, n << log_blowup), dtype=np.uint32)
+    lib().orc_lde_batch(_p(t), C.c_uint(n.bit_length() - 1), C.c_size_t(w), C.c_uint(log_blowup), C.c_uint32(shift), _p(out))
+    return out
+
+
+def poseidon2_permute(state):
+    s = _u32(state).copy()
+    assert s.size == 16
+    lib().orc_poseidon2_permute(_p(s))
+    return s
+
+
+def hash_row(row):
+    r = _u32(row)
+    d = np.empty(8, dtype=np.uint32)
+    lib().orc_hash_row(_p(r), C.c_size_t(r.size), _p(d))
+    return d
+
+
+def compress(l, r):
+    l, r = _u32(l), _u32(r)
+    d = np.empty(8, dtype=np.uint32)
+    lib().orc_compress(_p(l), _p(r), _p(d))
+    return d
+
+
+def merkle_commit(mats):
+    """mats: list of (width_i, h) column-major arrays of equal height -> list of digest layers [(h,8),(h/2,8),...,(1,8)]."""
+    mats = [_u32(m) for m in mats]
+    h = mats[0].shape[1]
+    log_h = h.bit_length() - 1
+    ptrs = (C.c_void_p * len(mats))(*[m.ctypes.data for m in mats])
+    widths = (C.c_size_t * len(mats))(*[m.shape[0] for m in mats])
+    flat = np.empty((2 * h - 1, 8), dtype=np.uint32)
+    lib().orc_merkle_commit(ptrs, widths, C.c_size_t(len(mats)), C.c_uint(log_h), _p(flat))
+    layers, off, n = [], 0, h
+    while n >= 1:
+        layers.append(flat[off:off + n])
+        off += n
+        n >>= 1
+    return layers
+
+
+def compile_spans(spans):
+    arr = (Span * max(1, len(spans)))()
+    for i, (o, l) in enumerate(spans):
+        arr[i].off, arr[i].len = o, l
+    return arr
+
+
+def eval_expr(bc, mat_flat, r):
+    bc = _u32(bc)
+    m = _u32(mat_flat)
+    return lib().orc_eval_expr(_p(bc), C.c_uint32(bc.size), _p(m), C.c_size_t(r))
+
+
+def constraint_fold(bc, spans, mat, alpha):
+    bc, m, al = _u32(bc), _u32(mat), _u32(alpha)
+    w, h = m.shape
+    out = np.empty((4, h), dtype=np.uint32)
+    lib().orc_constraint_fold(_p(bc), compile_spans(spans), C.c_size_t(len(spans)), _p(m), C.c_size_t(h), _p(al), _p(out))
+    return out
+
+
+def quotient(bc, spans, lde, log_n, alpha, shift=GENERATOR):
+    bc, m, al = _u32(bc), _u32(lde), _u32(alpha)
+    n = 1 << log_n
+    out = np.empty((2, 4, n), dtype=np.uint32)
+    lib().orc_quotient(_p(bc), compile_spans(spans), C.c_size_t(len(spans)), _p(m), C.c_uint(log_n), C.c_uint(1),
+                       C.c_uint32(shift), _p(al), _p(out))
+    return out
+
+
+def fri_fold(f, shift, beta):
+    """f: (len, 4) ext elements, bit-reversed over shift*<w_len> -> (len/2, 4)."""
+    f, b = _u32(f), _u32(beta)
+    n = f.shape[0]
+    out = np.empty((n // 2, 4), dtype=np.uint32)
+    lib().orc_fri_fold(_p(f), C.c_uint(n.bit_length() - 1), C.c_uint32(shift), _p(b), _p(out))
+    return out
+
+
+class Challenger:
+    class _S(C.Structure):
+        _fields_ = [("sponge", C.c_uint32 * 16), ("in_buf", C.c_uint32 * 8), ("n_in", C.c_int),
+                    ("out_buf", C.c_uint32 * 8), ("n_out", C.c_int)]
+
+    def __init__(self):
+        self.s = Challenger._S()
+        lib().orc_challenger_init(C.byref(self.s))
+
+    def observe(self, vals):
+        v = _u32(vals)
+        lib().orc_challenger_observe(C.byref(self.s), _p(v), C.c_size_t(v.size))
+
+    def sample(self):
+        return int(lib().orc_challenger_sample(C.byref(self.s)))
+
+    def sample_ext(self):
+        return [self.sample() for _ in range(4)]
+
+
+def apc_tracegen(H, width, airs, subs, num_calls):
+    """airs: list of (col-major array (w,h), row_block_size); subs: list of (air_index, col, row, apc_col)."""
+    out = np.full((width, H), 0xDEADBEEF % P, dtype=np.uint32)
+    keep = [_u32(a) for a, _ in airs]
+    A = (OriginalAir * len(airs))()
+    for i, (a, rbs) in enumerate(airs):
+        A[i].width, A[i].height, A[i].buffer, A[i].row_block_size = keep[i].shape[0], keep[i].shape[1], keep[i].ctypes.data, rbs
+    S = (Subst * max(1, len(subs)))()
+    for i, s in enumerate(subs):
+        S[i].air_index, S[i].col, S[i].row, S[i].apc_col = s
+    lib().orc_apc_tracegen(_p(out), C.c_size_t(H), A, S, C.c_size_t(len(subs)), C.c_int(num_calls))
+    return out
+
+
+def apc_apply_derived(out, num_calls, specs, bc):
+    """specs: list of (col_index, off, len); in-place on `out` (width, H)."""
+    H = out.shape[1]
+    D = (DerivedSpec * max(1, len(specs)))()
+    for i, (c, o, l) in enumerate(specs):
+        D[i].col_base, D[i].span.off, D[i].span.len = c * H, o, l
+    bc = _u32(bc)
+    lib().orc_apc_apply_derived_expr(_p(out), C.c_size_t(H), C.c_int(num_calls), D, C.c_size_t(len(specs)), _p(bc))
+    return out
+
+
+def apc_apply_bus(out, num_calls, bc, interactions, arg_spans, var=(3, 1 << 18), tuple2=(7, 256, 2048), bitwise=6):
+    bc = _u32(bc)
+    I = (Interaction * max(1, len(interactions)))()
+    for i, (b, n, o) in enumerate(interactions):
+        I[i].bus_id, I[i].num_args, I[i].args_index_off = b, n, o
+    var_hist = np.zeros(var[1], dtype=np.uint32)
+    t_hist = np.zeros(tuple2[1] * tuple2[2], dtype=np.uint32)
+    b_hist = np.zeros(1 << 17, dtype=np.uint32)
+    lib().orc_apc_apply_bus(_p(_u32(out)), C.c_int(num_calls), _p(bc), I, C.c_size_t(len(interactions)), compile_spans(arg_spans),
+                            C.c_uint32(var[0]), _p(var_hist), C.c_size_t(var[1]), C.c_uint32(tuple2[0]), _p(t_hist),
+                            C.c_uint32(tuple2[1]), C.c_uint32(tuple2[2]), C.c_uint32(bitwise), _p(b_hist))
+    return var_hist, t_hist, b_hist
+
+
+def prove_segment(trace, bc, spans):
+    t, bc = _u32(trace), _u32(bc)
+    w, n = t.shape
+    proof = SegmentProof()
+    st = (C.c_double * 8)()
+    lib().orc_prove_segment(_p(t), C.c_uint(n.bit_length() - 1), C.c_size_t(w), _p(bc), compile_spans(spans),
+                            C.c_size_t(len(spans)), C.byref(proof), st)
+    return proof.as_dict(), list(st)[:6]
