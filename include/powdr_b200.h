@@ -1,0 +1,140 @@
+/*
+ * powdr_b200 -- C ABI of the B200-native STARK proving hot path for powdr autoprecompile (APC) chips over BabyBear.
+ *
+ * Conventions (copied from the reference's only in-tree FFI, /root/reference/openvm/src/cuda_abi.rs:8-64):
+ *   - every entry point returns int: 0 = ok, a positive cudaError_t, or a negative PB_ERR_* code; nothing aborts;
+ *   - device buffers are raw pointers + explicit sizes, allocated and owned by the caller;
+ *   - kernels are enqueued on the context's stream and NOT synchronised (except where a host result is returned);
+ *   - matrices are COLUMN-MAJOR (element (row r, col c) at c*height + r) -- DeviceMatrix<BabyBear>
+ *     (/root/reference/openvm/cuda/src/apc_tracegen.cu:13,36);
+ *   - field elements in device/host data buffers are u32 in MONTGOMERY form (R = 2^32), the in-memory form of
+ *     p3_baby_bear::BabyBear / the device Fp.  Scalars passed by value in arguments (shift, alpha, beta, constants)
+ *     are CANONICAL u32 in [0,p), like `PushConst` operands (/root/reference/openvm/src/powdr_extension/trace_generator/cuda/mod.rs:57-58).
+ *
+ * Reference interfaces each group replaces are cited per function; the Rust-side bindings are in INTEGRATION.md.
+ */
+#ifndef POWDR_B200_H
+#define POWDR_B200_H
+#include <stddef.h>
+#include <stdint.h>
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define PB_ERR_INVALID_ARG (-1)
+#define PB_ERR_UNSUPPORTED (-2)
+#define PB_ERR_STACK_DEPTH (-3)   /* expression needs more than 16 stack slots (STACK_CAPACITY, expr_eval.cuh:22) */
+#define PB_ERR_BAD_BYTECODE (-4)
+#define PB_ERR_NO_DEVICE (-5)
+
+#define PB_BABYBEAR_P 2013265921u
+#define PB_DIGEST_WORDS 8
+
+typedef struct pb_ctx pb_ctx_t;   /* device + stream + twiddle/constant caches + scratch */
+typedef struct pb_air pb_air_t;   /* compiled constraint program of one APC AIR */
+
+/* ---- context -------------------------------------------------------------------------------------------------
+ * Replaces the implicit "default stream + global device state" of the reference launchers (apc_tracegen.cu:139-145).
+ * `cuda_stream` is a cudaStream_t (NULL = default stream). */
+int pb_ctx_create(pb_ctx_t** out, int device, void* cuda_stream);
+int pb_ctx_destroy(pb_ctx_t* ctx);
+int pb_ctx_synchronize(pb_ctx_t* ctx);
+/* Poseidon2 instantiation as data (canonical values): 8x16 external round constants (4 initial then 4 terminal),
+ * 13 internal, 16-entry internal diagonal V (matrix 1 + diag(V)).  Default = include/pb_poseidon2_constants.h. */
+int pb_ctx_set_poseidon2(pb_ctx_t* ctx, const uint32_t rc_ext[8][16], const uint32_t rc_int[13], const uint32_t diag_m1[16]);
+
+/* pinned host memory + representation helpers */
+int pb_host_alloc(void** out, size_t bytes);
+int pb_host_free(void* p);
+int pb_device_alloc(void** out, size_t bytes);
+int pb_device_free(void* p);
+/* stream-ordered copies, the MemCopyH2D::to_device / to_host of openvm-cuda-common (use-sites cuda/mod.rs:331-355) */
+int pb_copy_h2d(pb_ctx_t* ctx, void* d_dst, const void* h_src, size_t bytes);
+int pb_copy_d2h(pb_ctx_t* ctx, void* h_dst, const void* d_src, size_t bytes);   /* synchronises the stream */
+int pb_memset_zero(pb_ctx_t* ctx, void* d_dst, size_t bytes);                    /* DeviceBuffer::fill_zero */
+int pb_to_monty(pb_ctx_t* ctx, uint32_t* d_buf, size_t n);     /* in place, canonical -> Montgomery */
+int pb_from_monty(pb_ctx_t* ctx, uint32_t* d_buf, size_t n);   /* in place, Montgomery -> canonical */
+
+/* ---- stage 1: coset LDE (replaces the backend's main_trace_commit LDE) -------------------------
+ * d_trace: width columns of 2^log_n evaluations over the subgroup H, natural row order.
+ * d_lde:   width columns of 2^(log_n+log_blowup) evaluations over shift*H', rows BIT-REVERSED. */
+int pb_lde_batch(pb_ctx_t* ctx, const uint32_t* d_trace, size_t log_n, size_t width, uint32_t log_blowup, uint32_t shift,
+                 uint32_t* d_lde);
+
+/* ---- stage 2: constraint evaluation / quotient (replaces quotient_poly_compute over PowdrAir::eval,
+ *      /root/reference/openvm/src/powdr_extension/chip.rs:94-130) --------------------------------------------------
+ * Bytecode = the reference stack machine (/root/reference/openvm/cuda/src/expr_eval.cuh:12-20) with the PUSH_APC operand
+ * being the COLUMN INDEX (height independent) and PUSH_CONST a canonical u32. */
+typedef struct { uint32_t off; uint32_t len; } pb_expr_span_t;   /* == ExprSpan, cuda_abi.rs:162-169 */
+int pb_air_compile(pb_ctx_t* ctx, const uint32_t* bytecode, size_t n_words, const pb_expr_span_t* constraints,
+                   size_t n_constraints, uint32_t width, pb_air_t** out);
+int pb_air_free(pb_air_t* air);
+/* d_quotient: [2 chunks][4 limbs][2^log_n], chunk = parity of the natural LDE index (= top bit of the bit-reversed row),
+ * rows inside a chunk in bit-reversed order.  log_blowup must be 1 (constraint degree <= 3, openvm/src/lib.rs:97-101). */
+int pb_quotient(pb_ctx_t* ctx, const pb_air_t* air, const uint32_t* d_lde, size_t log_n, uint32_t log_blowup, uint32_t shift,
+                const uint32_t alpha[4], uint32_t* d_quotient);
+/* raw alpha-fold of all constraints on every row of any column-major matrix: d_out [4][height] */
+int pb_constraint_fold(pb_ctx_t* ctx, const pb_air_t* air, const uint32_t* d_mat, size_t height, const uint32_t alpha[4],
+                       uint32_t* d_out);
+
+/* ---- stage 3a: Poseidon2 Merkle tree (replaces MerkleTreeMmcs::commit of the backend) -------------
+ * d_mats[i]: column-major, height 2^log_height, width widths[i]; leaf r = sponge(row r of mat 0 || row r of mat 1 ...).
+ * d_digest_layers: (2^(log_height+1) - 1) * 8 words, node-major: 2^log_height leaves, then each parent layer, root last.
+ * root_out (host, canonical, may be NULL): synchronises the stream when given. */
+int pb_merkle_commit(pb_ctx_t* ctx, const uint32_t* const* d_mats, const size_t* widths, size_t n_mats, size_t log_height,
+                     uint32_t* d_digest_layers, uint32_t root_out[8]);
+/* same tree over ONE row-major matrix of width 8 (a FRI layer: row j = the fold pair (f[2j], f[2j+1])) */
+int pb_merkle_commit_rows8(pb_ctx_t* ctx, const uint32_t* d_rows, size_t log_height, uint32_t* d_digest_layers, uint32_t root_out[8]);
+/* n independent permutations of [n][16] states, in place (tests, micro-benchmarks) */
+int pb_poseidon2_permute(pb_ctx_t* ctx, uint32_t* d_states, size_t n, int reps);
+
+/* ---- stage 3b: FRI fold (replaces the commit-phase fold of pcs_opening) -----------------------------
+ * d_in: 2^log_len Ext4 elements [len][4], bit-reversed evaluations over shift*<w_len>; d_out: [len/2][4]. */
+int pb_fri_fold(pb_ctx_t* ctx, const uint32_t* d_in, size_t log_len, uint32_t shift, const uint32_t beta[4], uint32_t* d_out);
+
+/* ---- whole segment: the metric's unit of work ------------------------------------------------------------------------
+ * Replaces engine.prove(pk, ProvingContext{common_main}) for one APC chip behind sdk.app_prover(exe)?.prove(stdin)
+ * (/root/reference/openvm-riscv/src/lib.rs:327-332; AirProvingContext built at
+ * /root/reference/openvm/src/powdr_extension/trace_generator/cuda/mod.rs:415-419): main trace commit (LDE + Merkle),
+ * quotient, quotient commit, FRI commit phase.  Transcript documented in DESIGN.md. */
+typedef struct {
+    uint32_t trace_root[8];
+    uint32_t quotient_root[8];
+    uint32_t alpha[4];
+    uint32_t n_fri_layers;
+    uint32_t fri_roots[32][8];
+    uint32_t fri_betas[32][4];
+    uint32_t final_poly[8][4];
+    uint32_t final_len;
+} pb_segment_proof_t;               /* all values canonical */
+#define PB_TRACE_ON_DEVICE 1u       /* `trace` is a device pointer (value-only timing); else host memory, copied in */
+int pb_prove_segment(pb_ctx_t* ctx, const pb_air_t* air, const uint32_t* trace, size_t log_n, size_t width, uint32_t flags,
+                     pb_segment_proof_t* proof);
+/* per-stage device milliseconds of the last pb_prove_segment: [h2d, lde, merkle, quotient, qlde, qmerkle, fri, total] */
+int pb_last_stage_ms(pb_ctx_t* ctx, float ms[8]);
+/* kernels launched by this context since creation (bench.py's gpu_launches) */
+uint64_t pb_launch_count(pb_ctx_t* ctx);
+/* CUDA-event timing of the dominant kernel (Poseidon2 leaf hashing of column-major matrices) since the last call:
+ * number of launches (first 16 kept), summed device ms and summed algorithmic bytes (4*h*w in + 32*h out). Synchronises. */
+int pb_leaf_kernel_profile(pb_ctx_t* ctx, int* n_launches, double* total_ms, double* total_bytes);
+
+/* ---- stage 0: drop-in replacements with the reference's exact symbols and layouts (cuda_abi.rs:8-64) ------------------- */
+typedef struct { int width; int height; const uint32_t* buffer; int row_block_size; } OriginalAir;   /* cuda_abi.rs:66-73 */
+typedef struct { int air_index; int col; int row; int apc_col; } Subst;                               /* cuda_abi.rs:75-86 */
+typedef struct { uint32_t off; uint32_t len; } ExprSpan;                                               /* cuda_abi.rs:162-169 */
+typedef struct { uint64_t col_base; ExprSpan span; } DerivedExprSpec;                                  /* cuda_abi.rs:88-95 */
+typedef struct { uint32_t bus_id; uint32_t num_args; uint32_t args_index_off; } DevInteraction;        /* cuda_abi.rs:150-160 */
+int _apc_tracegen(uint32_t* d_output, size_t output_height, const OriginalAir* d_original_airs, const Subst* d_subs,
+                  size_t n_subs, int num_apc_calls);
+int _apc_apply_derived_expr(uint32_t* d_output, size_t output_height, int num_apc_calls, const DerivedExprSpec* d_specs,
+                            size_t n_cols, const uint32_t* d_bytecode);
+int _apc_apply_bus(const uint32_t* d_output, int num_apc_calls, const uint32_t* d_bytecode, size_t bytecode_len,
+                   const DevInteraction* d_interactions, size_t n_interactions, const ExprSpan* d_arg_spans, size_t n_arg_spans,
+                   uint32_t var_range_bus_id, uint32_t* d_var_hist, size_t var_num_bins,
+                   uint32_t tuple2_bus_id, uint32_t* d_tuple2_hist, uint32_t tuple2_sz0, uint32_t tuple2_sz1,
+                   uint32_t bitwise_bus_id, uint32_t* d_bitwise_hist);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

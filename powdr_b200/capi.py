@@ -1,0 +1,271 @@
+"""ctypes binding of include/powdr_b200.h -- the Python stand-in for the Rust `extern "C"` block + safe wrappers of
+/root/reference/openvm/src/cuda_abi.rs:8-64,97-135,174-223.  Raises if the CUDA library is missing: no CPU fallback."""
+import ctypes as C
+import os
+
+import numpy as np
+
+P = 2013265921
+R_MOD_P = (1 << 32) % P
+R_INV_MOD_P = pow(1 << 32, -1, P)
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "_lib", "libpowdr_b200.so")
+
+EXPORTS = [
+    "pb_ctx_create", "pb_ctx_destroy", "pb_ctx_synchronize", "pb_ctx_set_poseidon2", "pb_host_alloc", "pb_host_free",
+    "pb_device_alloc", "pb_device_free", "pb_copy_h2d", "pb_copy_d2h", "pb_memset_zero", "pb_to_monty", "pb_from_monty",
+    "pb_lde_batch", "pb_air_compile", "pb_air_free", "pb_quotient", "pb_constraint_fold", "pb_merkle_commit",
+    "pb_merkle_commit_rows8", "pb_poseidon2_permute", "pb_fri_fold", "pb_prove_segment", "pb_last_stage_ms",
+    "pb_launch_count", "pb_leaf_kernel_profile", "_apc_tracegen", "_apc_apply_derived_expr", "_apc_apply_bus",
+]
+
+
+class LibraryMissing(RuntimeError):
+    pass
+
+
+class PbError(RuntimeError):
+    def __init__(self, code, where):
+        super().__init__("%s failed with code %d (%s)" % (where, code, "cudaError_t" if code > 0 else "PB_ERR"))
+        self.code = code
+
+
+class Span(C.Structure):
+    _fields_ = [("off", C.c_uint32), ("len", C.c_uint32)]
+
+
+class OriginalAir(C.Structure):
+    _fields_ = [("width", C.c_int), ("height", C.c_int), ("buffer", C.c_void_p), ("row_block_size", C.c_int)]
+
+
+class Subst(C.Structure):
+    _fields_ = [("air_index", C.c_int), ("col", C.c_int), ("row", C.c_int), ("apc_col", C.c_int)]
+
+
+class DerivedExprSpec(C.Structure):
+    _fields_ = [("col_base", C.c_uint64), ("span", Span)]
+
+
+class DevInteraction(C.Structure):
+    _fields_ = [("bus_id", C.c_uint32), ("num_args", C.c_uint32), ("args_index_off", C.c_uint32)]
+
+
+class SegmentProof(C.Structure):
+    _fields_ = [("trace_root", C.c_uint32 * 8), ("quotient_root", C.c_uint32 * 8), ("alpha", C.c_uint32 * 4),
+                ("n_fri_layers", C.c_uint32), ("fri_roots", (C.c_uint32 * 8) * 32), ("fri_betas", (C.c_uint32 * 4) * 32),
+                ("final_poly", (C.c_uint32 * 4) * 8), ("final_len", C.c_uint32)]
+
+    def as_dict(self):
+        n = self.n_fri_layers
+        return {
+            "trace_root": list(self.trace_root), "quotient_root": list(self.quotient_root), "alpha": list(self.alpha),
+            "n_fri_layers": int(n), "fri_roots": [list(self.fri_roots[i]) for i in range(n)],
+            "fri_betas": [list(self.fri_betas[i]) for i in range(n)],
+            "final_poly": [list(self.final_poly[i]) for i in range(self.final_len)], "final_len": int(self.final_len),
+        }
+
+
+_lib = None
+
+
+def load_library(path=None):
+    """dlopen the in-tree sm_100a library; never falls back to anything else."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    path = path or LIB_PATH
+    if not os.path.exists(path):
+        raise LibraryMissing("%s not built: run `python -m powdr_b200.build` (nvcc, sm_100a)" % path)
+    lib = C.CDLL(path)
+    for name in EXPORTS:
+        if not hasattr(lib, name):
+            raise LibraryMissing("symbol %s missing from %s" % (name, path))
+        getattr(lib, name).restype = C.c_int
+    lib.pb_launch_count.restype = C.c_uint64
+    _lib = lib
+    return lib
+
+
+def _chk(code, where):
+    if code != 0:
+        raise PbError(code, where)
+
+
+def _u32(a):
+    return np.ascontiguousarray(a, dtype=np.uint32)
+
+
+class DeviceBuffer:
+    """Caller-owned device memory (DeviceBuffer<T> of openvm-cuda-common)."""
+
+    def __init__(self, ctx, nbytes):
+        self.ctx, self.nbytes = ctx, int(nbytes)
+        p = C.c_void_p()
+        _chk(ctx.lib.pb_device_alloc(C.byref(p), C.c_size_t(max(4, self.nbytes))), "pb_device_alloc")
+        self.ptr = p.value
+
+    def free(self):
+        if self.ptr:
+            self.ctx.lib.pb_device_free(C.c_void_p(self.ptr))
+            self.ptr = None
+
+    def __del__(self):
+        try:
+            self.free()
+        except Exception:
+            pass
+
+    def upload(self, arr):
+        a = np.ascontiguousarray(arr)
+        assert a.nbytes <= self.nbytes
+        _chk(self.ctx.lib.pb_copy_h2d(self.ctx.h, C.c_void_p(self.ptr), a.ctypes.data_as(C.c_void_p), C.c_size_t(a.nbytes)), "pb_copy_h2d")
+        self.ctx.synchronize()
+        return self
+
+    def download(self, shape, dtype=np.uint32):
+        out = np.empty(shape, dtype=dtype)
+        assert out.nbytes <= self.nbytes
+        _chk(self.ctx.lib.pb_copy_d2h(self.ctx.h, out.ctypes.data_as(C.c_void_p), C.c_void_p(self.ptr), C.c_size_t(out.nbytes)), "pb_copy_d2h")
+        return out
+
+    def zero(self):
+        _chk(self.ctx.lib.pb_memset_zero(self.ctx.h, C.c_void_p(self.ptr), C.c_size_t(self.nbytes)), "pb_memset_zero")
+        return self
+
+
+class Air:
+    def __init__(self, ctx, bytecode, spans, width):
+        self.ctx, self.width, self.n_constraints = ctx, width, len(spans)
+        bc = _u32(bytecode)
+        sp = (Span * max(1, len(spans)))()
+        for i, (o, l) in enumerate(spans):
+            sp[i].off, sp[i].len = o, l
+        h = C.c_void_p()
+        _chk(ctx.lib.pb_air_compile(ctx.h, bc.ctypes.data_as(C.c_void_p), C.c_size_t(bc.size), sp, C.c_size_t(len(spans)),
+                                    C.c_uint32(width), C.byref(h)), "pb_air_compile")
+        self.h = h
+
+    def free(self):
+        if self.h:
+            self.ctx.lib.pb_air_free(self.h)
+            self.h = None
+
+
+class Context:
+    """pb_ctx_t: one per GPU / stream."""
+
+    def __init__(self, device=0, stream=None):
+        self.lib = load_library()
+        h = C.c_void_p()
+        _chk(self.lib.pb_ctx_create(C.byref(h), C.c_int(device), C.c_void_p(stream or 0)), "pb_ctx_create")
+        self.h = h
+        self.device = device
+
+    def close(self):
+        if self.h:
+            self.lib.pb_ctx_destroy(self.h)
+            self.h = None
+
+    def synchronize(self):
+        _chk(self.lib.pb_ctx_synchronize(self.h), "pb_ctx_synchronize")
+
+    # ---- memory ----
+    def alloc(self, nbytes):
+        return DeviceBuffer(self, nbytes)
+
+    def to_device(self, arr, monty=True):
+        """numpy (canonical) -> device buffer (Montgomery unless monty=False); conversion done on the host."""
+        a = _u32(arr)
+        if monty:
+            a = ((a.astype(np.uint64) * np.uint64(R_MOD_P)) % np.uint64(P)).astype(np.uint32)
+        return DeviceBuffer(self, a.nbytes).upload(a)
+
+    def to_host(self, buf, shape, monty=True):
+        raw = buf.download(shape)
+        if monty:
+            raw = ((raw.astype(np.uint64) * np.uint64(R_INV_MOD_P)) % np.uint64(P)).astype(np.uint32)
+        return raw
+
+    # ---- stages ----
+    def air(self, bytecode, spans, width):
+        return Air(self, bytecode, spans, width)
+
+    def lde_batch(self, d_trace_ptr, log_n, width, d_lde_ptr, log_blowup=1, shift=31):
+        _chk(self.lib.pb_lde_batch(self.h, C.c_void_p(d_trace_ptr), C.c_size_t(log_n), C.c_size_t(width), C.c_uint32(log_blowup),
+                                   C.c_uint32(shift), C.c_void_p(d_lde_ptr)), "pb_lde_batch")
+
+    def quotient(self, air, d_lde_ptr, log_n, alpha, d_q_ptr, log_blowup=1, shift=31):
+        al = (C.c_uint32 * 4)(*[int(x) for x in alpha])
+        _chk(self.lib.pb_quotient(self.h, air.h, C.c_void_p(d_lde_ptr), C.c_size_t(log_n), C.c_uint32(log_blowup), C.c_uint32(shift),
+                                  al, C.c_void_p(d_q_ptr)), "pb_quotient")
+
+    def constraint_fold(self, air, d_mat_ptr, height, alpha, d_out_ptr):
+        al = (C.c_uint32 * 4)(*[int(x) for x in alpha])
+        _chk(self.lib.pb_constraint_fold(self.h, air.h, C.c_void_p(d_mat_ptr), C.c_size_t(height), al, C.c_void_p(d_out_ptr)),
+             "pb_constraint_fold")
+
+    def merkle_commit(self, mat_ptrs, widths, log_h, d_layers_ptr, want_root=True):
+        n = len(mat_ptrs)
+        ptrs = (C.c_void_p * n)(*mat_ptrs)
+        ws = (C.c_size_t * n)(*widths)
+        root = (C.c_uint32 * 8)()
+        _chk(self.lib.pb_merkle_commit(self.h, ptrs, ws, C.c_size_t(n), C.c_size_t(log_h), C.c_void_p(d_layers_ptr),
+                                       root if want_root else None), "pb_merkle_commit")
+        return list(root) if want_root else None
+
+    def merkle_commit_rows8(self, d_rows_ptr, log_h, d_layers_ptr, want_root=True):
+        root = (C.c_uint32 * 8)()
+        _chk(self.lib.pb_merkle_commit_rows8(self.h, C.c_void_p(d_rows_ptr), C.c_size_t(log_h), C.c_void_p(d_layers_ptr),
+                                             root if want_root else None), "pb_merkle_commit_rows8")
+        return list(root) if want_root else None
+
+    def poseidon2_permute(self, d_states_ptr, n, reps=1):
+        _chk(self.lib.pb_poseidon2_permute(self.h, C.c_void_p(d_states_ptr), C.c_size_t(n), C.c_int(reps)), "pb_poseidon2_permute")
+
+    def fri_fold(self, d_in_ptr, log_len, shift, beta, d_out_ptr):
+        b = (C.c_uint32 * 4)(*[int(x) for x in beta])
+        _chk(self.lib.pb_fri_fold(self.h, C.c_void_p(d_in_ptr), C.c_size_t(log_len), C.c_uint32(shift), b, C.c_void_p(d_out_ptr)),
+             "pb_fri_fold")
+
+    def prove_segment(self, air, trace_ptr, log_n, width, on_device=False):
+        proof = SegmentProof()
+        _chk(self.lib.pb_prove_segment(self.h, air.h, C.c_void_p(trace_ptr), C.c_size_t(log_n), C.c_size_t(width),
+                                       C.c_uint32(1 if on_device else 0), C.byref(proof)), "pb_prove_segment")
+        return proof.as_dict()
+
+    def last_stage_ms(self):
+        ms = (C.c_float * 8)()
+        _chk(self.lib.pb_last_stage_ms(self.h, ms), "pb_last_stage_ms")
+        return dict(zip(["h2d", "lde", "merkle", "quotient", "qlde", "qmerkle", "fri", "total"], [float(x) for x in ms]))
+
+    def launch_count(self):
+        return int(self.lib.pb_launch_count(self.h))
+
+    def leaf_kernel_profile(self):
+        n, ms, by = C.c_int(), C.c_double(), C.c_double()
+        _chk(self.lib.pb_leaf_kernel_profile(self.h, C.byref(n), C.byref(ms), C.byref(by)), "pb_leaf_kernel_profile")
+        return n.value, ms.value, by.value
+
+    def host_alloc(self, nbytes):
+        p = C.c_void_p()
+        _chk(self.lib.pb_host_alloc(C.byref(p), C.c_size_t(nbytes)), "pb_host_alloc")
+        return p.value
+
+    def host_free(self, ptr):
+        self.lib.pb_host_free(C.c_void_p(ptr))
+
+    # ---- stage 0 (reference symbols) ----
+    def apc_tracegen(self, d_out_ptr, H, d_airs_ptr, d_subs_ptr, n_subs, num_calls):
+        _chk(self.lib._apc_tracegen(C.c_void_p(d_out_ptr), C.c_size_t(H), C.c_void_p(d_airs_ptr), C.c_void_p(d_subs_ptr),
+                                    C.c_size_t(n_subs), C.c_int(num_calls)), "_apc_tracegen")
+
+    def apc_apply_derived_expr(self, d_out_ptr, H, num_calls, d_specs_ptr, n_cols, d_bc_ptr):
+        _chk(self.lib._apc_apply_derived_expr(C.c_void_p(d_out_ptr), C.c_size_t(H), C.c_int(num_calls), C.c_void_p(d_specs_ptr),
+                                              C.c_size_t(n_cols), C.c_void_p(d_bc_ptr)), "_apc_apply_derived_expr")
+
+    def apc_apply_bus(self, d_out_ptr, num_calls, d_bc_ptr, bc_len, d_ints_ptr, n_ints, d_spans_ptr, n_spans, var_bus, d_var, var_bins,
+                      t2_bus, d_t2, sz0, sz1, bw_bus, d_bw):
+        _chk(self.lib._apc_apply_bus(C.c_void_p(d_out_ptr), C.c_int(num_calls), C.c_void_p(d_bc_ptr), C.c_size_t(bc_len),
+                                     C.c_void_p(d_ints_ptr), C.c_size_t(n_ints), C.c_void_p(d_spans_ptr), C.c_size_t(n_spans),
+                                     C.c_uint32(var_bus), C.c_void_p(d_var), C.c_size_t(var_bins), C.c_uint32(t2_bus), C.c_void_p(d_t2),
+                                     C.c_uint32(sz0), C.c_uint32(sz1), C.c_uint32(bw_bus), C.c_void_p(d_bw)), "_apc_apply_bus")

@@ -1,0 +1,760 @@
+// C ABI + host orchestration of the powdr_b200 hot path (include/powdr_b200.h).  Single translation unit: the kernels
+// live in the .cuh files included below.  Host code here plays the role of the reference's Rust host side
+// (bytecode packing ~ emit_expr, /root/reference/openvm/src/powdr_extension/trace_generator/cuda/mod.rs:49-81;
+// launch wrappers ~ /root/reference/openvm/src/cuda_abi.rs:97-135,174-223; stage order ~ engine.prove behind
+// /root/reference/openvm-riscv/src/lib.rs:327-332).  No CPU fallback exists: every entry point needs a CUDA device.
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <string.h>
+#include <algorithm>
+#include <unordered_map>
+#include <vector>
+
+#include "../../include/pb_poseidon2_constants.h"
+#include "../../include/powdr_b200.h"
+#include "air.cuh"
+#include "bb31.cuh"
+#include "fri.cuh"
+#include "ntt.cuh"
+#include "poseidon2.cuh"
+#include "tracegen.cuh"
+
+#define CK(x)                                  \
+    do {                                       \
+        cudaError_t e__ = (x);                 \
+        if (e__ != cudaSuccess) return (int)e__; \
+    } while (0)
+#define LAUNCHED(ctx) ((ctx)->launches++)
+
+namespace {
+
+// ---------------- host-side field helpers (Montgomery, same bb:: code as the device) ----------------
+inline uint32_t h_to_m(uint32_t c) { return bb::to_monty(c % bb::P); }
+inline uint32_t h_from_m(uint32_t m) { return bb::from_monty(m); }
+inline uint32_t h_root_of_unity_m(int log_n) { return bb::pow(h_to_m(bb::GEN), (uint64_t)(bb::P - 1) >> log_n); }
+inline bb::E4 h_e4_from_canon(const uint32_t v[4]) { bb::E4 r; for (int i = 0; i < 4; i++) r.c[i] = h_to_m(v[i]); return r; }
+
+struct P2Host {   // Montgomery constants for the host-side transcript permutation
+    uint32_t rc_ext[8][16], rc_int[13], diag[16];
+};
+
+void host_external_linear(uint32_t s[16]) {
+    static const uint32_t M4[4][4] = {{2, 3, 1, 1}, {1, 2, 3, 1}, {1, 1, 2, 3}, {3, 1, 1, 2}};
+    for (int c = 0; c < 16; c += 4) {
+        uint32_t y[4];
+        for (int i = 0; i < 4; i++) {
+            uint32_t acc = 0;
+            for (int j = 0; j < 4; j++)
+                for (uint32_t k = 0; k < M4[i][j]; k++) acc = bb::add(acc, s[c + j]);
+            y[i] = acc;
+        }
+        for (int i = 0; i < 4; i++) s[c + i] = y[i];
+    }
+    uint32_t q[4] = {0, 0, 0, 0};
+    for (int i = 0; i < 16; i++) q[i & 3] = bb::add(q[i & 3], s[i]);
+    for (int i = 0; i < 16; i++) s[i] = bb::add(s[i], q[i & 3]);
+}
+inline uint32_t host_sbox(uint32_t x) {
+    uint32_t x2 = bb::mul(x, x), x3 = bb::mul(x2, x), x4 = bb::mul(x2, x2);
+    return bb::mul(x3, x4);
+}
+void host_permute(uint32_t s[16], const P2Host& k) {
+    host_external_linear(s);
+    for (int r = 0; r < 4; r++) {
+        for (int i = 0; i < 16; i++) s[i] = host_sbox(bb::add(s[i], k.rc_ext[r][i]));
+        host_external_linear(s);
+    }
+    for (int r = 0; r < 13; r++) {
+        s[0] = host_sbox(bb::add(s[0], k.rc_int[r]));
+        uint32_t sum = 0;
+        for (int i = 0; i < 16; i++) sum = bb::add(sum, s[i]);
+        for (int i = 0; i < 16; i++) s[i] = bb::add(sum, bb::mul(s[i], k.diag[i]));
+    }
+    for (int r = 4; r < 8; r++) {
+        for (int i = 0; i < 16; i++) s[i] = host_sbox(bb::add(s[i], k.rc_ext[r][i]));
+        host_external_linear(s);
+    }
+}
+
+// DuplexChallenger<BabyBear, Perm16, 16, 8> on Montgomery values
+struct Challenger {
+    const P2Host* k;
+    uint32_t sponge[16] = {0};
+    uint32_t in_buf[8];
+    int n_in = 0;
+    uint32_t out_buf[8];
+    int n_out = 0;
+    void duplexing() {
+        for (int i = 0; i < n_in; i++) sponge[i] = in_buf[i];
+        n_in = 0;
+        host_permute(sponge, *k);
+        memcpy(out_buf, sponge, 32);
+        n_out = 8;
+    }
+    void observe(const uint32_t* v, int n) {
+        for (int i = 0; i < n; i++) {
+            n_out = 0;
+            in_buf[n_in++] = v[i];
+            if (n_in == 8) duplexing();
+        }
+    }
+    uint32_t sample() {
+        if (n_in > 0 || n_out == 0) duplexing();
+        return out_buf[--n_out];
+    }
+    bb::E4 sample_ext() { bb::E4 r; for (int i = 0; i < 4; i++) r.c[i] = sample(); return r; }
+};
+
+struct TwiddleSet {
+    int n, log_blowup;
+    uint32_t shift;      // canonical
+    uint32_t ninv;       // Montgomery 1/N
+    uint32_t* d_inv;     // [2^n]           tw_inv[2^u + k] = w_{2^(u+1)}^{-k}
+    uint32_t* d_fwd;     // [cosets][2^n]   tw_fwd[c][2^u + k] = S_c^(2^(n-1-u)) * w_{2^(u+1)}^{k},  S_c = shift * w_{N 2^b}^c
+};
+
+template <typename T>
+struct DevBuf {
+    T* p = nullptr;
+    size_t cap = 0;
+    int ensure(size_t n) {
+        if (n <= cap) return 0;
+        if (p) cudaFree(p);
+        p = nullptr;
+        cap = 0;
+        cudaError_t e = cudaMalloc((void**)&p, n * sizeof(T));
+        if (e != cudaSuccess) return (int)e;
+        cap = n;
+        return 0;
+    }
+    void release() { if (p) cudaFree(p); p = nullptr; cap = 0; }
+};
+
+__global__ void to_monty_kernel(uint32_t* a, size_t n) {
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) a[i] = bb::to_monty(a[i]);
+}
+__global__ void from_monty_kernel(uint32_t* a, size_t n) {
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) a[i] = bb::from_monty(a[i]);
+}
+
+}  // namespace
+
+struct pb_air {
+    uint32_t width = 0, n_constraints = 0;
+    uint32_t* d_code = nullptr;
+    air::Span* d_spans = nullptr;
+    uint32_t* d_pool = nullptr;
+    uint32_t* d_alpha_pows = nullptr;   // [C][4]
+    size_t n_code = 0, n_pool = 0;
+};
+
+struct pb_ctx {
+    int device = 0;
+    cudaStream_t stream = nullptr;
+    uint64_t launches = 0;
+    P2Host p2;
+    std::vector<TwiddleSet> tws;
+    uint32_t* d_fold_tab = nullptr;   // w_L^{-bitrev(j)}, j < L/2, Montgomery
+    int fold_tab_log_len = 0;
+    DevBuf<uint32_t> tmp, tmp2;       // LDE intermediates (L2-sized)
+    DevBuf<const uint32_t*> coltab;
+    // pb_prove_segment workspace
+    DevBuf<uint32_t> ws_trace, ws_lde, ws_layers, ws_q, ws_qnat, ws_qlde, ws_f0, ws_f1;
+    cudaEvent_t ev[8] = {nullptr};
+    float stage_ms[8] = {0};
+    // live timing of the dominant kernel (Poseidon2 leaf hashing over column-major matrices): event pairs on the stream
+    static constexpr int KPROF = 16;
+    cudaEvent_t kp_a[KPROF] = {nullptr}, kp_b[KPROF] = {nullptr};
+    double kp_bytes[KPROF] = {0};
+    int kp_n = 0;
+};
+
+namespace {
+
+int upload_p2(pb_ctx* ctx, const uint32_t rc_ext[8][16], const uint32_t rc_int[13], const uint32_t diag[16]) {
+    p2::Consts c;
+    for (int r = 0; r < 8; r++)
+        for (int i = 0; i < 16; i++) {
+            uint32_t m = h_to_m(rc_ext[r][i]);
+            ctx->p2.rc_ext[r][i] = m;
+            c.rc_ext_mp[r][i] = m - bb::P;
+        }
+    for (int r = 0; r < 13; r++) {
+        uint32_t m = h_to_m(rc_int[r]);
+        ctx->p2.rc_int[r] = m;
+        c.rc_int_mp[r] = m - bb::P;
+    }
+    for (int i = 0; i < 16; i++) ctx->p2.diag[i] = c.diag[i] = h_to_m(diag[i]);
+    CK(cudaMemcpyToSymbolAsync(p2::c_p2, &c, sizeof c, 0, cudaMemcpyHostToDevice, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    return 0;
+}
+
+int get_twiddles(pb_ctx* ctx, int n, int log_blowup, uint32_t shift, const TwiddleSet** out) {
+    for (auto& t : ctx->tws)
+        if (t.n == n && t.log_blowup == log_blowup && t.shift == shift) { *out = &t; return 0; }
+    const size_t N = (size_t)1 << n;
+    const int cosets = 1 << log_blowup;
+    std::vector<uint32_t> inv(N), fwd(N * cosets);
+    inv[0] = 0;
+    for (int u = 0; u < n; u++) {
+        uint32_t w = bb::inv(h_root_of_unity_m(u + 1)), x = bb::R1;
+        for (size_t k = 0; k < ((size_t)1 << u); k++) { inv[((size_t)1 << u) + k] = x; x = bb::mul(x, w); }
+    }
+    const uint32_t shift_m = h_to_m(shift);
+    const uint32_t w_ext = h_root_of_unity_m(n + log_blowup);
+    for (int c = 0; c < cosets; c++) {
+        uint32_t sc = bb::mul(shift_m, bb::pow(w_ext, (uint64_t)c));
+        uint32_t* f = fwd.data() + (size_t)c * N;
+        f[0] = 0;
+        // factor for stage u is S_c^(2^(n-1-u)): walk u from n-1 down, squaring
+        uint32_t fac = sc;
+        for (int u = n - 1; u >= 0; u--) {
+            uint32_t w = h_root_of_unity_m(u + 1), x = fac;
+            for (size_t k = 0; k < ((size_t)1 << u); k++) { f[((size_t)1 << u) + k] = x; x = bb::mul(x, w); }
+            fac = bb::mul(fac, fac);
+        }
+    }
+    TwiddleSet t;
+    t.n = n; t.log_blowup = log_blowup; t.shift = shift;
+    t.ninv = bb::inv(h_to_m((uint32_t)(N % bb::P)));
+    CK(cudaMalloc((void**)&t.d_inv, N * 4));
+    CK(cudaMalloc((void**)&t.d_fwd, N * cosets * 4));
+    CK(cudaMemcpyAsync(t.d_inv, inv.data(), N * 4, cudaMemcpyHostToDevice, ctx->stream));
+    CK(cudaMemcpyAsync(t.d_fwd, fwd.data(), N * cosets * 4, cudaMemcpyHostToDevice, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    if (ctx->tws.size() >= 12) {   // bounded cache
+        cudaFree(ctx->tws.front().d_inv);
+        cudaFree(ctx->tws.front().d_fwd);
+        ctx->tws.erase(ctx->tws.begin());
+    }
+    ctx->tws.push_back(t);
+    *out = &ctx->tws.back();
+    return 0;
+}
+
+int get_fold_table(pb_ctx* ctx, int log_len) {
+    if (ctx->d_fold_tab && ctx->fold_tab_log_len >= log_len) return 0;
+    if (ctx->d_fold_tab) { cudaFree(ctx->d_fold_tab); ctx->d_fold_tab = nullptr; }
+    const size_t half = (size_t)1 << (log_len - 1);
+    std::vector<uint32_t> nat(half), tab(half);
+    uint32_t w = bb::inv(h_root_of_unity_m(log_len)), x = bb::R1;
+    for (size_t k = 0; k < half; k++) { nat[k] = x; x = bb::mul(x, w); }
+    for (size_t j = 0; j < half; j++) {
+        uint32_t r = 0;
+        for (int b = 0; b < log_len - 1; b++) r |= ((j >> b) & 1u) << (log_len - 2 - b);
+        tab[j] = nat[r];
+    }
+    CK(cudaMalloc((void**)&ctx->d_fold_tab, half * 4));
+    CK(cudaMemcpyAsync(ctx->d_fold_tab, tab.data(), half * 4, cudaMemcpyHostToDevice, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    ctx->fold_tab_log_len = log_len;
+    return 0;
+}
+
+// Merkle layers above the leaves: node-major, layer k+1 follows layer k
+int merkle_upper(pb_ctx* ctx, uint32_t* d_layers, size_t log_h) {
+    size_t n = (size_t)1 << log_h;
+    uint32_t* prev = d_layers;
+    while (n > 1) {
+        size_t parents = n >> 1;
+        uint32_t* next = prev + 8 * n;
+        if (n <= 1024) {
+            p2::compress_tail_kernel<<<1, 512, 0, ctx->stream>>>(reinterpret_cast<uint4*>(prev), (uint32_t)n);
+            LAUNCHED(ctx);
+            break;
+        }
+        p2::compress_layer_kernel<<<(unsigned)((parents + 255) / 256), 256, 0, ctx->stream>>>(
+            reinterpret_cast<const uint4*>(prev), reinterpret_cast<uint4*>(next), parents);
+        LAUNCHED(ctx);
+        prev = next;
+        n = parents;
+    }
+    CK(cudaGetLastError());
+    return 0;
+}
+
+int read_root(pb_ctx* ctx, const uint32_t* d_layers, size_t log_h, uint32_t root_m[8]) {
+    const size_t root_off = 8 * (((size_t)2 << log_h) - 2);
+    CK(cudaMemcpyAsync(root_m, d_layers + root_off, 32, cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    return 0;
+}
+
+}  // namespace
+
+// =====================================================================================================================
+extern "C" {
+
+int pb_ctx_create(pb_ctx_t** out, int device, void* cuda_stream) {
+    if (!out) return PB_ERR_INVALID_ARG;
+    int count = 0;
+    if (cudaGetDeviceCount(&count) != cudaSuccess || count == 0) return PB_ERR_NO_DEVICE;
+    CK(cudaSetDevice(device));
+    pb_ctx* ctx = new pb_ctx();
+    ctx->device = device;
+    ctx->stream = (cudaStream_t)cuda_stream;
+    for (auto& e : ctx->ev) CK(cudaEventCreate(&e));
+    for (int i = 0; i < pb_ctx::KPROF; i++) { CK(cudaEventCreate(&ctx->kp_a[i])); CK(cudaEventCreate(&ctx->kp_b[i])); }
+    CK(cudaFuncSetAttribute(ntt::inv_hi_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 4 << ntt::LOG_TILE_HI_MAX));
+    CK(cudaFuncSetAttribute(ntt::fwd_hi_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 4 << ntt::LOG_TILE_HI_MAX));
+    CK(cudaFuncSetAttribute(ntt::lo_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 8 << ntt::LOG_TILE_LO));
+    int rc = upload_p2(ctx, PB_P2_RC_EXT, PB_P2_RC_INT, PB_P2_DIAG_M1);
+    if (rc) { delete ctx; return rc; }
+    *out = ctx;
+    return 0;
+}
+
+int pb_ctx_destroy(pb_ctx_t* ctx) {
+    if (!ctx) return 0;
+    cudaSetDevice(ctx->device);
+    cudaStreamSynchronize(ctx->stream);
+    for (auto& t : ctx->tws) { cudaFree(t.d_inv); cudaFree(t.d_fwd); }
+    if (ctx->d_fold_tab) cudaFree(ctx->d_fold_tab);
+    ctx->tmp.release(); ctx->tmp2.release(); ctx->coltab.release();
+    ctx->ws_trace.release(); ctx->ws_lde.release(); ctx->ws_layers.release(); ctx->ws_q.release();
+    ctx->ws_qnat.release(); ctx->ws_qlde.release(); ctx->ws_f0.release(); ctx->ws_f1.release();
+    for (auto& e : ctx->ev) if (e) cudaEventDestroy(e);
+    for (int i = 0; i < pb_ctx::KPROF; i++) { if (ctx->kp_a[i]) cudaEventDestroy(ctx->kp_a[i]); if (ctx->kp_b[i]) cudaEventDestroy(ctx->kp_b[i]); }
+    delete ctx;
+    return 0;
+}
+
+int pb_ctx_synchronize(pb_ctx_t* ctx) { CK(cudaStreamSynchronize(ctx->stream)); return 0; }
+
+int pb_ctx_set_poseidon2(pb_ctx_t* ctx, const uint32_t rc_ext[8][16], const uint32_t rc_int[13], const uint32_t diag_m1[16]) {
+    if (!ctx || !rc_ext || !rc_int || !diag_m1) return PB_ERR_INVALID_ARG;
+    return upload_p2(ctx, rc_ext, rc_int, diag_m1);
+}
+
+int pb_host_alloc(void** out, size_t bytes) { CK(cudaHostAlloc(out, bytes, cudaHostAllocDefault)); return 0; }
+int pb_host_free(void* p) { CK(cudaFreeHost(p)); return 0; }
+int pb_device_alloc(void** out, size_t bytes) { CK(cudaMalloc(out, bytes)); return 0; }
+int pb_device_free(void* p) { CK(cudaFree(p)); return 0; }
+
+int pb_copy_h2d(pb_ctx_t* ctx, void* d, const void* h, size_t bytes) {
+    CK(cudaMemcpyAsync(d, h, bytes, cudaMemcpyHostToDevice, ctx->stream));
+    return 0;
+}
+int pb_copy_d2h(pb_ctx_t* ctx, void* h, const void* d, size_t bytes) {
+    CK(cudaMemcpyAsync(h, d, bytes, cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    return 0;
+}
+int pb_memset_zero(pb_ctx_t* ctx, void* d, size_t bytes) {
+    CK(cudaMemsetAsync(d, 0, bytes, ctx->stream));
+    return 0;
+}
+
+int pb_to_monty(pb_ctx_t* ctx, uint32_t* d, size_t n) {
+    if (!n) return 0;
+    to_monty_kernel<<<(unsigned)((n + 255) / 256), 256, 0, ctx->stream>>>(d, n);
+    LAUNCHED(ctx);
+    CK(cudaGetLastError());
+    return 0;
+}
+int pb_from_monty(pb_ctx_t* ctx, uint32_t* d, size_t n) {
+    if (!n) return 0;
+    from_monty_kernel<<<(unsigned)((n + 255) / 256), 256, 0, ctx->stream>>>(d, n);
+    LAUNCHED(ctx);
+    CK(cudaGetLastError());
+    return 0;
+}
+
+// ---------------------------------------------------------------------------------------------------------------------
+int pb_lde_batch(pb_ctx_t* ctx, const uint32_t* d_trace, size_t log_n, size_t width, uint32_t log_blowup, uint32_t shift,
+                 uint32_t* d_lde) {
+    if (!ctx || !d_trace || !d_lde) return PB_ERR_INVALID_ARG;
+    if (log_n < 1 || log_n > 24 || log_blowup < 1 || log_blowup > 3 || shift == 0 || shift >= bb::P) return PB_ERR_UNSUPPORTED;
+    if (width == 0) return 0;
+    const int n = (int)log_n;
+    const size_t N = (size_t)1 << n;
+    const int cosets = 1 << log_blowup;
+    const TwiddleSet* tw;
+    int rc = get_twiddles(ctx, n, (int)log_blowup, shift, &tw);
+    if (rc) return rc;
+    const int n_lo = n <= 12 ? n : (n + 1) / 2;
+    const int n_hi = n - n_lo;
+    int log_lc = std::min(5, n_lo);
+    if (n_hi + log_lc > ntt::LOG_TILE_HI_MAX) log_lc = ntt::LOG_TILE_HI_MAX - n_hi;
+    const int log_tile_lo = std::min(ntt::LOG_TILE_LO, n);
+    // column batch sized so both intermediates (4N + 4N*cosets bytes per column) stay L2-resident (~48 MB)
+    size_t batch = std::max<size_t>(1, ((size_t)48 << 20) / (4 * N * (1 + cosets)));
+    batch = std::min<size_t>(std::min<size_t>(batch, width), 32768);
+    if (n_hi > 0) { rc = ctx->tmp.ensure(batch * N); if (rc) return rc; }
+    rc = ctx->tmp2.ensure(batch * N * cosets);
+    if (rc) return rc;
+    const size_t smem_hi = (size_t)4 << (n_hi + log_lc);
+    const size_t smem_lo = (size_t)8 << log_tile_lo;
+    for (size_t c0 = 0; c0 < width; c0 += batch) {
+        const unsigned nb = (unsigned)std::min(batch, width - c0);
+        const uint32_t* src = d_trace + c0 * N;
+        if (n_hi > 0) {
+            dim3 g1((unsigned)(1u << (n_lo - log_lc)), nb);
+            ntt::inv_hi_kernel<<<g1, ntt::K13_THREADS, smem_hi, ctx->stream>>>(src, N, ctx->tmp.p, n, n_lo, log_lc, tw->d_inv);
+            LAUNCHED(ctx);
+            src = ctx->tmp.p;
+        }
+        dim3 g2((unsigned)(N >> log_tile_lo), nb);
+        ntt::lo_kernel<<<g2, ntt::K2_THREADS, smem_lo, ctx->stream>>>(src, N, ctx->tmp2.p, n, n_lo, log_tile_lo, tw->d_inv, tw->d_fwd,
+                                                                      tw->ninv, cosets);
+        LAUNCHED(ctx);
+        dim3 g3((unsigned)(1u << (n_lo - log_lc)), nb, (unsigned)cosets);
+        ntt::fwd_hi_kernel<<<g3, ntt::K13_THREADS, smem_hi, ctx->stream>>>(ctx->tmp2.p, d_lde + c0 * N * cosets, N * cosets, n, n_lo,
+                                                                           log_lc, (int)log_blowup, tw->d_fwd);
+        LAUNCHED(ctx);
+    }
+    CK(cudaGetLastError());
+    return 0;
+}
+
+// ---------------------------------------------------------------------------------------------------------------------
+int pb_air_compile(pb_ctx_t* ctx, const uint32_t* bc, size_t n_words, const pb_expr_span_t* cons, size_t n_constraints,
+                   uint32_t width, pb_air_t** out) {
+    if (!ctx || !out || (!bc && n_words) || (!cons && n_constraints)) return PB_ERR_INVALID_ARG;
+    std::vector<uint32_t> code, pool;
+    std::vector<air::Span> spans;
+    std::unordered_map<uint32_t, uint32_t> pool_idx;
+    for (size_t k = 0; k < n_constraints; k++) {
+        const size_t off = cons[k].off, len = cons[k].len;
+        if (off + len > n_words) return PB_ERR_BAD_BYTECODE;
+        air::Span sp{(uint32_t)code.size(), 0};
+        int depth = 0;
+        for (size_t ip = off; ip < off + len;) {
+            const uint32_t op = bc[ip++];
+            if (op == air::OP_PUSH_APC || op == air::OP_PUSH_CONST) {
+                if (ip >= off + len) return PB_ERR_BAD_BYTECODE;
+                const uint32_t arg = bc[ip++];
+                if (++depth > air::STACK_CAPACITY) return PB_ERR_STACK_DEPTH;
+                if (op == air::OP_PUSH_APC) {
+                    if (arg >= width) return PB_ERR_BAD_BYTECODE;
+                    code.push_back((op << 28) | arg);
+                } else {
+                    auto it = pool_idx.find(arg % bb::P);
+                    uint32_t idx;
+                    if (it == pool_idx.end()) {
+                        idx = (uint32_t)pool.size();
+                        pool_idx[arg % bb::P] = idx;
+                        pool.push_back(h_to_m(arg));
+                    } else idx = it->second;
+                    code.push_back((op << 28) | idx);
+                }
+            } else if (op == air::OP_ADD || op == air::OP_SUB || op == air::OP_MUL) {
+                if (depth < 2) return PB_ERR_BAD_BYTECODE;
+                depth--;
+                code.push_back(op << 28);
+            } else if (op == air::OP_NEG || op == air::OP_INV_OR_ZERO) {
+                if (depth < 1) return PB_ERR_BAD_BYTECODE;
+                code.push_back(op << 28);
+            } else return PB_ERR_BAD_BYTECODE;
+        }
+        if (depth != 1) return PB_ERR_BAD_BYTECODE;
+        sp.len = (uint32_t)code.size() - sp.off;
+        spans.push_back(sp);
+    }
+    pb_air* a = new pb_air();
+    a->width = width;
+    a->n_constraints = (uint32_t)n_constraints;
+    a->n_code = code.size();
+    a->n_pool = pool.size();
+    CK(cudaMalloc((void**)&a->d_code, std::max<size_t>(1, code.size()) * 4));
+    CK(cudaMalloc((void**)&a->d_spans, std::max<size_t>(1, spans.size()) * sizeof(air::Span)));
+    CK(cudaMalloc((void**)&a->d_pool, std::max<size_t>(1, pool.size()) * 4));
+    CK(cudaMalloc((void**)&a->d_alpha_pows, std::max<size_t>(1, n_constraints) * 16));
+    CK(cudaMemcpyAsync(a->d_code, code.data(), code.size() * 4, cudaMemcpyHostToDevice, ctx->stream));
+    CK(cudaMemcpyAsync(a->d_spans, spans.data(), spans.size() * sizeof(air::Span), cudaMemcpyHostToDevice, ctx->stream));
+    CK(cudaMemcpyAsync(a->d_pool, pool.data(), pool.size() * 4, cudaMemcpyHostToDevice, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    *out = a;
+    return 0;
+}
+
+int pb_air_free(pb_air_t* a) {
+    if (!a) return 0;
+    cudaFree(a->d_code); cudaFree(a->d_spans); cudaFree(a->d_pool); cudaFree(a->d_alpha_pows);
+    delete a;
+    return 0;
+}
+
+static int upload_alpha_pows(pb_ctx* ctx, const pb_air* a, bb::E4 alpha) {
+    const size_t C = a->n_constraints;
+    std::vector<uint32_t> ap(4 * std::max<size_t>(1, C));
+    bb::E4 cur = {{bb::R1, 0, 0, 0}};
+    for (size_t k = C; k-- > 0;) {          // alpha_pows[k] = alpha^(C-1-k)
+        memcpy(&ap[4 * k], cur.c, 16);
+        cur = bb::e4_mul(cur, alpha);
+    }
+    CK(cudaMemcpyAsync(a->d_alpha_pows, ap.data(), 16 * C, cudaMemcpyHostToDevice, ctx->stream));
+    return 0;
+}
+
+int pb_quotient(pb_ctx_t* ctx, const pb_air_t* a, const uint32_t* d_lde, size_t log_n, uint32_t log_blowup, uint32_t shift,
+                const uint32_t alpha[4], uint32_t* d_q) {
+    if (!ctx || !a || !d_lde || !alpha || !d_q) return PB_ERR_INVALID_ARG;
+    if (log_blowup != 1 || log_n < 1 || log_n > 26) return PB_ERR_UNSUPPORTED;
+    int rc = upload_alpha_pows(ctx, a, h_e4_from_canon(alpha));
+    if (rc) return rc;
+    const uint32_t sn = bb::pow(h_to_m(shift), (uint64_t)1 << log_n);
+    const uint32_t zinv0 = bb::inv(bb::sub(sn, bb::R1)), zinv1 = bb::inv(bb::sub(bb::neg(sn), bb::R1));
+    const size_t m = (size_t)2 << log_n;
+    air::quotient_kernel<<<(unsigned)((m + air::THREADS - 1) / air::THREADS), air::THREADS, 0, ctx->stream>>>(
+        a->d_code, a->d_spans, a->n_constraints, a->d_pool, d_lde, (int)log_n, a->d_alpha_pows, zinv0, zinv1, d_q, 1);
+    LAUNCHED(ctx);
+    CK(cudaGetLastError());
+    return 0;
+}
+
+int pb_constraint_fold(pb_ctx_t* ctx, const pb_air_t* a, const uint32_t* d_mat, size_t height, const uint32_t alpha[4], uint32_t* d_out) {
+    if (!ctx || !a || !d_mat || !alpha || !d_out) return PB_ERR_INVALID_ARG;
+    if (!height) return 0;
+    int rc = upload_alpha_pows(ctx, a, h_e4_from_canon(alpha));
+    if (rc) return rc;
+    air::constraint_fold_kernel<<<(unsigned)((height + air::THREADS - 1) / air::THREADS), air::THREADS, 0, ctx->stream>>>(
+        a->d_code, a->d_spans, a->n_constraints, a->d_pool, d_mat, height, a->d_alpha_pows, d_out);
+    LAUNCHED(ctx);
+    CK(cudaGetLastError());
+    return 0;
+}
+
+// ---------------------------------------------------------------------------------------------------------------------
+int pb_merkle_commit(pb_ctx_t* ctx, const uint32_t* const* d_mats, const size_t* widths, size_t n_mats, size_t log_h,
+                     uint32_t* d_layers, uint32_t root_out[8]) {
+    if (!ctx || !d_mats || !widths || !n_mats || !d_layers) return PB_ERR_INVALID_ARG;
+    if (log_h > 30) return PB_ERR_UNSUPPORTED;
+    const size_t h = (size_t)1 << log_h;
+    std::vector<const uint32_t*> cols;
+    for (size_t i = 0; i < n_mats; i++)
+        for (size_t c = 0; c < widths[i]; c++) cols.push_back(d_mats[i] + c * h);
+    int rc = ctx->coltab.ensure(std::max<size_t>(1, cols.size()));
+    if (rc) return rc;
+    CK(cudaMemcpyAsync(ctx->coltab.p, cols.data(), cols.size() * sizeof(void*), cudaMemcpyHostToDevice, ctx->stream));
+    const int slot = ctx->kp_n < pb_ctx::KPROF ? ctx->kp_n : -1;
+    if (slot >= 0) CK(cudaEventRecord(ctx->kp_a[slot], ctx->stream));
+    p2::leaf_hash_cols_kernel<<<(unsigned)((h + 255) / 256), 256, 0, ctx->stream>>>(ctx->coltab.p, (uint32_t)cols.size(), h, d_layers);
+    LAUNCHED(ctx);
+    if (slot >= 0) {
+        CK(cudaEventRecord(ctx->kp_b[slot], ctx->stream));
+        ctx->kp_bytes[slot] = 4.0 * (double)h * (double)cols.size() + 32.0 * (double)h;   // algorithmic bytes: matrix in, digests out
+        ctx->kp_n++;
+    }
+    rc = merkle_upper(ctx, d_layers, log_h);
+    if (rc) return rc;
+    if (root_out) {
+        uint32_t r[8];
+        rc = read_root(ctx, d_layers, log_h, r);
+        if (rc) return rc;
+        for (int i = 0; i < 8; i++) root_out[i] = h_from_m(r[i]);
+    }
+    return 0;
+}
+
+int pb_merkle_commit_rows8(pb_ctx_t* ctx, const uint32_t* d_rows, size_t log_h, uint32_t* d_layers, uint32_t root_out[8]) {
+    if (!ctx || !d_rows || !d_layers) return PB_ERR_INVALID_ARG;
+    const size_t h = (size_t)1 << log_h;
+    p2::leaf_hash_rows8_kernel<<<(unsigned)((h + 255) / 256), 256, 0, ctx->stream>>>(reinterpret_cast<const uint4*>(d_rows), h, d_layers);
+    LAUNCHED(ctx);
+    int rc = merkle_upper(ctx, d_layers, log_h);
+    if (rc) return rc;
+    if (root_out) {
+        uint32_t r[8];
+        rc = read_root(ctx, d_layers, log_h, r);
+        if (rc) return rc;
+        for (int i = 0; i < 8; i++) root_out[i] = h_from_m(r[i]);
+    }
+    return 0;
+}
+
+int pb_poseidon2_permute(pb_ctx_t* ctx, uint32_t* d_states, size_t n, int reps) {
+    if (!ctx || !d_states) return PB_ERR_INVALID_ARG;
+    if (!n) return 0;
+    p2::permute_states_kernel<<<(unsigned)((n + 255) / 256), 256, 0, ctx->stream>>>(d_states, n, reps);
+    LAUNCHED(ctx);
+    CK(cudaGetLastError());
+    return 0;
+}
+
+// ---------------------------------------------------------------------------------------------------------------------
+static int fri_fold_m(pb_ctx* ctx, const uint32_t* d_in, size_t log_len, uint32_t shift_m, bb::E4 beta_m, uint32_t* d_out) {
+    int rc = get_fold_table(ctx, (int)log_len);
+    if (rc) return rc;
+    const size_t half = (size_t)1 << (log_len - 1);
+    const uint32_t two_inv = bb::inv(h_to_m(2));
+    const uint32_t c = bb::mul(two_inv, bb::inv(shift_m));          // (2*shift)^-1
+    bb::E4 beta_c = bb::e4_scale(beta_m, c);
+    // table prefix property: w_L^{-bitrev_{logL-1}(j)} for a shorter layer is the prefix of the longer layer's table
+    fri::fold_kernel<<<(unsigned)((half + 255) / 256), 256, 0, ctx->stream>>>(reinterpret_cast<const uint4*>(d_in),
+                                                                              reinterpret_cast<uint4*>(d_out), half, ctx->d_fold_tab,
+                                                                              beta_c, two_inv);
+    LAUNCHED(ctx);
+    CK(cudaGetLastError());
+    return 0;
+}
+
+int pb_fri_fold(pb_ctx_t* ctx, const uint32_t* d_in, size_t log_len, uint32_t shift, const uint32_t beta[4], uint32_t* d_out) {
+    if (!ctx || !d_in || !d_out || !beta) return PB_ERR_INVALID_ARG;
+    if (log_len < 1 || log_len > 27 || shift == 0 || shift >= bb::P) return PB_ERR_UNSUPPORTED;
+    return fri_fold_m(ctx, d_in, log_len, h_to_m(shift), h_e4_from_canon(beta), d_out);
+}
+
+// ---------------------------------------------------------------------------------------------------------------------
+int pb_prove_segment(pb_ctx_t* ctx, const pb_air_t* a, const uint32_t* trace, size_t log_n, size_t width, uint32_t flags,
+                     pb_segment_proof_t* proof) {
+    if (!ctx || !a || !trace || !proof) return PB_ERR_INVALID_ARG;
+    if (log_n < 1 || log_n > 24 || width == 0 || width != a->width) return PB_ERR_INVALID_ARG;
+    const uint32_t log_blowup = 1;
+    const size_t N = (size_t)1 << log_n, M = N << log_blowup;
+    const size_t log_m = log_n + log_blowup;
+    int rc;
+    memset(proof, 0, sizeof *proof);
+    cudaStream_t st = ctx->stream;
+#define RC(x) do { rc = (x); if (rc) return rc; } while (0)
+    CK(cudaEventRecord(ctx->ev[0], st));
+    const uint32_t* d_trace = trace;
+    if (!(flags & PB_TRACE_ON_DEVICE)) {
+        RC(ctx->ws_trace.ensure(width * N));
+        CK(cudaMemcpyAsync(ctx->ws_trace.p, trace, width * N * 4, cudaMemcpyHostToDevice, st));
+        d_trace = ctx->ws_trace.p;
+    }
+    RC(ctx->ws_lde.ensure(width * M));
+    RC(ctx->ws_layers.ensure(8 * (2 * M)));
+    RC(ctx->ws_q.ensure(8 * N));
+    RC(ctx->ws_qnat.ensure(8 * N));
+    RC(ctx->ws_qlde.ensure(8 * M));
+    RC(ctx->ws_f0.ensure(4 * M));
+    RC(ctx->ws_f1.ensure(4 * (M / 2)));
+    Challenger ch;
+    ch.k = &ctx->p2;
+    uint32_t root_m[8];
+
+    // main trace commit: LDE then Merkle
+    CK(cudaEventRecord(ctx->ev[1], st));
+    RC(pb_lde_batch(ctx, d_trace, log_n, width, log_blowup, bb::GEN, ctx->ws_lde.p));
+    CK(cudaEventRecord(ctx->ev[2], st));
+    const uint32_t* mats1[1] = {ctx->ws_lde.p};
+    RC(pb_merkle_commit(ctx, mats1, &width, 1, log_m, ctx->ws_layers.p, nullptr));
+    CK(cudaEventRecord(ctx->ev[3], st));
+    RC(read_root(ctx, ctx->ws_layers.p, log_m, root_m));
+    for (int i = 0; i < 8; i++) proof->trace_root[i] = h_from_m(root_m[i]);
+    ch.observe(root_m, 8);
+    bb::E4 alpha = ch.sample_ext();
+    for (int i = 0; i < 4; i++) proof->alpha[i] = h_from_m(alpha.c[i]);
+
+    // quotient
+    RC(pb_quotient(ctx, a, ctx->ws_lde.p, log_n, log_blowup, bb::GEN, proof->alpha, ctx->ws_q.p));
+    CK(cudaEventRecord(ctx->ev[4], st));
+
+    // quotient commit: chunk b = evals over g*w_{2N}^b*H (bit-reversed) -> natural -> LDE with shift g/s_b = w_{2N}^-b
+    {
+        const size_t tot = 8 * N;
+        ntt::bitrev_rows_kernel<<<(unsigned)((tot + 255) / 256), 256, 0, st>>>(ctx->ws_q.p, ctx->ws_qnat.p, (int)log_n, 8);
+        LAUNCHED(ctx);
+        const uint32_t w2n_inv = h_from_m(bb::inv(h_root_of_unity_m((int)log_n + 1)));
+        RC(pb_lde_batch(ctx, ctx->ws_qnat.p, log_n, 4, log_blowup, 1u, ctx->ws_qlde.p));
+        RC(pb_lde_batch(ctx, ctx->ws_qnat.p + 4 * N, log_n, 4, log_blowup, w2n_inv, ctx->ws_qlde.p + 4 * M));
+    }
+    CK(cudaEventRecord(ctx->ev[5], st));
+    const uint32_t* mats2[2] = {ctx->ws_qlde.p, ctx->ws_qlde.p + 4 * M};
+    const size_t w2[2] = {4, 4};
+    RC(pb_merkle_commit(ctx, mats2, w2, 2, log_m, ctx->ws_layers.p, nullptr));
+    CK(cudaEventRecord(ctx->ev[6], st));
+    RC(read_root(ctx, ctx->ws_layers.p, log_m, root_m));
+    for (int i = 0; i < 8; i++) proof->quotient_root[i] = h_from_m(root_m[i]);
+    ch.observe(root_m, 8);
+    bb::E4 gamma = ch.sample_ext();
+
+    // FRI commit phase on f = Q0 + gamma*Q1
+    fri::combine_chunks_kernel<<<(unsigned)((M + 255) / 256), 256, 0, st>>>(ctx->ws_qlde.p, M, gamma, reinterpret_cast<uint4*>(ctx->ws_f0.p));
+    LAUNCHED(ctx);
+    uint32_t* f = ctx->ws_f0.p;
+    uint32_t* g = ctx->ws_f1.p;
+    size_t log_len = log_m;
+    uint32_t shift_m = h_to_m(bb::GEN);
+    uint32_t layer = 0;
+    while (log_len > log_blowup) {
+        RC(pb_merkle_commit_rows8(ctx, f, log_len - 1, ctx->ws_layers.p, nullptr));
+        RC(read_root(ctx, ctx->ws_layers.p, log_len - 1, root_m));
+        for (int i = 0; i < 8; i++) proof->fri_roots[layer][i] = h_from_m(root_m[i]);
+        ch.observe(root_m, 8);
+        bb::E4 beta = ch.sample_ext();
+        for (int i = 0; i < 4; i++) proof->fri_betas[layer][i] = h_from_m(beta.c[i]);
+        RC(fri_fold_m(ctx, f, log_len, shift_m, beta, g));
+        std::swap(f, g);
+        shift_m = bb::mul(shift_m, shift_m);
+        log_len--;
+        layer++;
+    }
+    proof->n_fri_layers = layer;
+    proof->final_len = 1u << log_len;
+    uint32_t fin[8 * 4];
+    CK(cudaMemcpyAsync(fin, f, 16 * proof->final_len, cudaMemcpyDeviceToHost, st));
+    CK(cudaEventRecord(ctx->ev[7], st));
+    CK(cudaStreamSynchronize(st));
+    for (uint32_t i = 0; i < proof->final_len; i++)
+        for (int l = 0; l < 4; l++) proof->final_poly[i][l] = h_from_m(fin[4 * i + l]);
+    for (int i = 0; i < 7; i++) cudaEventElapsedTime(&ctx->stage_ms[i], ctx->ev[i], ctx->ev[i + 1]);
+    cudaEventElapsedTime(&ctx->stage_ms[7], ctx->ev[0], ctx->ev[7]);
+#undef RC
+    return 0;
+}
+
+int pb_last_stage_ms(pb_ctx_t* ctx, float ms[8]) {
+    if (!ctx || !ms) return PB_ERR_INVALID_ARG;
+    memcpy(ms, ctx->stage_ms, sizeof ctx->stage_ms);
+    return 0;
+}
+
+uint64_t pb_launch_count(pb_ctx_t* ctx) { return ctx ? ctx->launches : 0; }
+
+int pb_leaf_kernel_profile(pb_ctx_t* ctx, int* n_launches, double* total_ms, double* total_bytes) {
+    if (!ctx || !n_launches || !total_ms || !total_bytes) return PB_ERR_INVALID_ARG;
+    CK(cudaStreamSynchronize(ctx->stream));
+    *n_launches = ctx->kp_n; *total_ms = 0; *total_bytes = 0;
+    for (int i = 0; i < ctx->kp_n; i++) {
+        float ms = 0;
+        CK(cudaEventElapsedTime(&ms, ctx->kp_a[i], ctx->kp_b[i]));
+        *total_ms += ms;
+        *total_bytes += ctx->kp_bytes[i];
+    }
+    ctx->kp_n = 0;
+    return 0;
+}
+
+// ---------------------------------------------------------------------------------------------------------------------
+// stage 0: the reference's exact entry points (default stream, async, cudaGetLastError as the return value)
+int _apc_tracegen(uint32_t* d_output, size_t H, const OriginalAir* d_airs, const Subst* d_subs, size_t n_subs, int num_apc_calls) {
+    if (H == 0 || (H & (H - 1)) != 0) return PB_ERR_INVALID_ARG;     // the reference asserts a power-of-two height
+    if (n_subs == 0) return 0;
+    const unsigned per = tg::GATHER_THREADS * tg::GATHER_ROWS_PER_THREAD;
+    const size_t max_y = 65535;
+    for (size_t s0 = 0; s0 < n_subs; s0 += max_y) {
+        dim3 grid((unsigned)((H + per - 1) / per), (unsigned)std::min(max_y, n_subs - s0));
+        tg::apc_tracegen_kernel<<<grid, tg::GATHER_THREADS>>>(d_output, H, reinterpret_cast<const tg::OriginalAir*>(d_airs),
+                                                              reinterpret_cast<const tg::Subst*>(d_subs) + s0, num_apc_calls);
+    }
+    return (int)cudaGetLastError();
+}
+
+int _apc_apply_derived_expr(uint32_t* d_output, size_t H, int num_apc_calls, const DerivedExprSpec* d_specs, size_t n_cols,
+                            const uint32_t* d_bytecode) {
+    if (n_cols == 0) return 0;
+    tg::apc_apply_derived_expr_kernel<<<(unsigned)((H + 255) / 256), 256>>>(
+        d_output, H, num_apc_calls, reinterpret_cast<const tg::DerivedExprSpec*>(d_specs), n_cols, d_bytecode);
+    return (int)cudaGetLastError();
+}
+
+int _apc_apply_bus(const uint32_t* d_output, int num_apc_calls, const uint32_t* d_bytecode, size_t bytecode_len,
+                   const DevInteraction* d_interactions, size_t n_interactions, const ExprSpan* d_arg_spans, size_t n_arg_spans,
+                   uint32_t var_range_bus_id, uint32_t* d_var_hist, size_t var_num_bins, uint32_t tuple2_bus_id,
+                   uint32_t* d_tuple2_hist, uint32_t sz0, uint32_t sz1, uint32_t bitwise_bus_id, uint32_t* d_bitwise_hist) {
+    (void)bytecode_len; (void)n_arg_spans;
+    if (num_apc_calls <= 0) return 0;
+    tg::apc_apply_bus_kernel<<<(unsigned)((num_apc_calls + 127) / 128), 128>>>(
+        d_output, num_apc_calls, d_bytecode, reinterpret_cast<const tg::DevInteraction*>(d_interactions), n_interactions,
+        reinterpret_cast<const tg::ExprSpan*>(d_arg_spans), var_range_bus_id, d_var_hist, var_num_bins, tuple2_bus_id, d_tuple2_hist,
+        sz0, sz1, bitwise_bus_id, d_bitwise_hist);
+    return (int)cudaGetLastError();
+}
+
+}  // extern "C"

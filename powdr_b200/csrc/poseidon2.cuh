@@ -1,0 +1,177 @@
+// Poseidon2 over BabyBear, width 16, x^7, 8 external + 13 internal rounds -- one permutation state per thread,
+// 16 registers, Montgomery form.  Stage 3a of the north-star path; the reference holds only the
+// type names (BabyBearPoseidon2Config, /root/reference/openvm/src/lib.rs:26-28) and the S-box degree
+// (/root/reference/openvm/src/powdr_extension/trace_generator/cpu/periphery.rs:80).
+//
+// Integer-pipe bound (≈22 mulmod per hashed byte): the design goal is instruction count, not bytes.
+//  * S-box runs in SIGNED Montgomery form: x = s + (rc - p) in [-p,p) costs one IADD, the four products need no
+//    correction (3 IMAD-class ops each), one 2-op fix-up returns to [0,p).
+//  * linear layers are add chains on canonical values (IADD3 + IADD3 + UMIN per modular add).
+#pragma once
+#include "bb31.cuh"
+
+namespace p2 {
+
+struct Consts {
+    uint32_t rc_ext_mp[8][16];   // Montgomery(rc) - p   (as two's-complement u32)
+    uint32_t rc_int_mp[13];      // Montgomery(rc) - p
+    uint32_t diag[16];           // Montgomery(V_i), internal matrix = 1 + diag(V)
+};
+__constant__ Consts c_p2;
+
+__device__ __forceinline__ uint32_t sbox_rc(uint32_t s, uint32_t rc_minus_p) {
+    int32_t x = (int32_t)(s + rc_minus_p);          // [-p, p)
+    int32_t x2 = bb::smul(x, x);
+    int32_t x3 = bb::smul(x2, x);
+    int32_t x4 = bb::smul(x2, x2);
+    return bb::from_signed(bb::smul(x3, x4));
+}
+
+// M4 = [[2,3,1,1],[1,2,3,1],[1,1,2,3],[3,1,1,2]] on each 4-chunk, then add the column sums: circ(2*M4, M4, M4, M4)
+__device__ __forceinline__ void external_linear(uint32_t (&s)[16]) {
+#pragma unroll
+    for (int c = 0; c < 16; c += 4) {
+        uint32_t x0 = s[c], x1 = s[c + 1], x2 = s[c + 2], x3 = s[c + 3];
+        uint32_t t01 = bb::add(x0, x1), t23 = bb::add(x2, x3);
+        uint32_t t0123 = bb::add(t01, t23);
+        uint32_t t01123 = bb::add(t0123, x1), t01233 = bb::add(t0123, x3);
+        s[c + 3] = bb::add(t01233, bb::dbl(x0));
+        s[c + 1] = bb::add(t01123, bb::dbl(x2));
+        s[c] = bb::add(t01123, t01);
+        s[c + 2] = bb::add(t01233, t23);
+    }
+    uint32_t q0 = bb::add(bb::add(s[0], s[4]), bb::add(s[8], s[12]));
+    uint32_t q1 = bb::add(bb::add(s[1], s[5]), bb::add(s[9], s[13]));
+    uint32_t q2 = bb::add(bb::add(s[2], s[6]), bb::add(s[10], s[14]));
+    uint32_t q3 = bb::add(bb::add(s[3], s[7]), bb::add(s[11], s[15]));
+#pragma unroll
+    for (int c = 0; c < 16; c += 4) {
+        s[c] = bb::add(s[c], q0);
+        s[c + 1] = bb::add(s[c + 1], q1);
+        s[c + 2] = bb::add(s[c + 2], q2);
+        s[c + 3] = bb::add(s[c + 3], q3);
+    }
+}
+
+__device__ __forceinline__ void internal_round(uint32_t (&s)[16], int r) {
+    s[0] = sbox_rc(s[0], c_p2.rc_int_mp[r]);
+    uint32_t a = bb::add(bb::add(s[0], s[1]), bb::add(s[2], s[3]));
+    uint32_t b = bb::add(bb::add(s[4], s[5]), bb::add(s[6], s[7]));
+    uint32_t c = bb::add(bb::add(s[8], s[9]), bb::add(s[10], s[11]));
+    uint32_t d = bb::add(bb::add(s[12], s[13]), bb::add(s[14], s[15]));
+    uint32_t sum = bb::add(bb::add(a, b), bb::add(c, d));
+#pragma unroll
+    for (int i = 0; i < 16; i++) s[i] = bb::add(sum, bb::mul(s[i], c_p2.diag[i]));
+}
+
+__device__ __forceinline__ void permute(uint32_t (&s)[16]) {
+    external_linear(s);
+#pragma unroll 1
+    for (int r = 0; r < 4; r++) {
+#pragma unroll
+        for (int i = 0; i < 16; i++) s[i] = sbox_rc(s[i], c_p2.rc_ext_mp[r][i]);
+        external_linear(s);
+    }
+#pragma unroll 1
+    for (int r = 0; r < 13; r++) internal_round(s, r);
+#pragma unroll 1
+    for (int r = 4; r < 8; r++) {
+#pragma unroll
+        for (int i = 0; i < 16; i++) s[i] = sbox_rc(s[i], c_p2.rc_ext_mp[r][i]);
+        external_linear(s);
+    }
+}
+
+// ---------------- kernels ----------------
+
+// leaf r = sponge(row r of the concatenation of all committed matrices); `cols` holds one base pointer per column.
+// Overwrite-mode absorb, rate 8, no padding (PaddingFreeSponge<16,8,8>).  One thread per row; consecutive threads read
+// consecutive rows of a column-major matrix => every load is a fully coalesced 128 B warp transaction.
+__global__ void __launch_bounds__(256) leaf_hash_cols_kernel(const uint32_t* const* __restrict__ cols, uint32_t n_cols,
+                                                              size_t height, uint32_t* __restrict__ digests) {
+    size_t r = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (r >= height) return;
+    uint32_t s[16];
+#pragma unroll
+    for (int i = 0; i < 16; i++) s[i] = 0;
+    uint32_t full = n_cols / 8;
+    uint32_t nxt[8];
+    if (full) {
+#pragma unroll
+        for (int k = 0; k < 8; k++) nxt[k] = __ldg(cols[k] + r);
+    }
+    for (uint32_t c = 0; c < full; c++) {
+#pragma unroll
+        for (int k = 0; k < 8; k++) s[k] = nxt[k];
+        if (c + 1 < full) {
+#pragma unroll
+            for (int k = 0; k < 8; k++) nxt[k] = __ldg(cols[(c + 1) * 8 + k] + r);
+        }
+        permute(s);
+    }
+    uint32_t rem = n_cols - full * 8;
+    if (rem) {
+#pragma unroll
+        for (int k = 0; k < 8; k++)
+            if ((uint32_t)k < rem) s[k] = __ldg(cols[full * 8 + k] + r);
+        permute(s);
+    }
+    uint4* out = reinterpret_cast<uint4*>(digests + 8 * r);
+    out[0] = make_uint4(s[0], s[1], s[2], s[3]);
+    out[1] = make_uint4(s[4], s[5], s[6], s[7]);
+}
+
+// leaves of a row-major width-8 matrix (FRI layer: row = (f[2j], f[2j+1]) as 8 base elements): one permutation each
+__global__ void __launch_bounds__(256) leaf_hash_rows8_kernel(const uint4* __restrict__ rows, size_t height, uint32_t* __restrict__ digests) {
+    size_t r = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (r >= height) return;
+    uint4 a = __ldg(rows + 2 * r), b = __ldg(rows + 2 * r + 1);
+    uint32_t s[16] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w, 0, 0, 0, 0, 0, 0, 0, 0};
+    permute(s);
+    uint4* out = reinterpret_cast<uint4*>(digests + 8 * r);
+    out[0] = make_uint4(s[0], s[1], s[2], s[3]);
+    out[1] = make_uint4(s[4], s[5], s[6], s[7]);
+}
+
+// one Merkle layer: parent j = TruncatedPermutation(left || right)
+__global__ void __launch_bounds__(256) compress_layer_kernel(const uint4* __restrict__ prev, uint4* __restrict__ next, size_t n_parents) {
+    size_t j = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= n_parents) return;
+    uint4 a = prev[4 * j], b = prev[4 * j + 1], c = prev[4 * j + 2], d = prev[4 * j + 3];
+    uint32_t s[16] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w, c.x, c.y, c.z, c.w, d.x, d.y, d.z, d.w};
+    permute(s);
+    next[2 * j] = make_uint4(s[0], s[1], s[2], s[3]);
+    next[2 * j + 1] = make_uint4(s[4], s[5], s[6], s[7]);
+}
+
+// the top of the tree in one CTA: layers of n, n/2, ..., 1 nodes laid out back to back starting at `layer`
+__global__ void __launch_bounds__(512) compress_tail_kernel(uint4* layer, uint32_t n) {
+    uint4* prev = layer;
+    for (uint32_t m = n >> 1; m >= 1; m >>= 1) {
+        uint4* next = prev + 4 * (size_t)m;        // previous layer has 2m nodes = 4m uint4
+        for (uint32_t j = threadIdx.x; j < m; j += blockDim.x) {
+            uint4 a = prev[4 * j], b = prev[4 * j + 1], c = prev[4 * j + 2], d = prev[4 * j + 3];
+            uint32_t s[16] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w, c.x, c.y, c.z, c.w, d.x, d.y, d.z, d.w};
+            permute(s);
+            next[2 * j] = make_uint4(s[0], s[1], s[2], s[3]);
+            next[2 * j + 1] = make_uint4(s[4], s[5], s[6], s[7]);
+        }
+        __syncthreads();
+        prev = next;
+        if (m == 1) break;
+    }
+}
+
+// single permutation per thread on [n][16] states -- used by tests and the throughput micro-benchmark
+__global__ void permute_states_kernel(uint32_t* states, size_t n, int reps) {
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    uint32_t s[16];
+#pragma unroll
+    for (int k = 0; k < 16; k++) s[k] = states[16 * i + k];
+    for (int r = 0; r < reps; r++) permute(s);
+#pragma unroll
+    for (int k = 0; k < 16; k++) states[16 * i + k] = s[k];
+}
+
+}  // namespace p2

@@ -1,0 +1,88 @@
+"""CPU tests of the host side: machine loader / bytecode compiler (mirror of emit_expr), the C-ABI library exporting every
+symbol the header declares, and loud failure without a GPU."""
+import os
+import re
+
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+GOLDEN = os.path.join(ROOT, "tests", "golden")
+
+
+def test_library_exports_every_declared_symbol():
+    import powdr_b200
+    from powdr_b200 import build, capi
+    build.build()
+    lib = powdr_b200.load_library()
+    header = open(os.path.join(ROOT, "include", "powdr_b200.h")).read()
+    declared = set(re.findall(r"^(?:int|uint64_t)\s+(\w+)\(", header, flags=re.M))
+    assert len(declared) >= 28
+    for name in declared:
+        assert hasattr(lib, name), name
+    assert declared == set(capi.EXPORTS)
+
+
+def test_no_cpu_fallback_without_gpu():
+    import powdr_b200
+    from powdr_b200.capi import PbError
+    try:
+        import torch
+        if torch.cuda.is_available():
+            pytest.skip("GPU present")
+    except ImportError:
+        pass
+    with pytest.raises(PbError) as e:
+        powdr_b200.Context(0)
+    assert e.value.code == -5
+
+
+def test_column_order_is_ascending_poly_id():
+    from powdr_b200 import machine as M
+    mach = M.SymbolicMachine([["b@7", "*", "a@3"], ["c@11", "-", "a@3"]])
+    assert mach.column_ids == [3, 7, 11] and mach.width == 3
+    bc, spans = M.compile_constraints(mach)
+    assert bc == [0, 1, 0, 0, 4, 0, 2, 0, 0, 3] and spans == [(0, 5), (5, 5)]
+
+
+def test_derived_and_bus_compilers_follow_reference_layout():
+    from powdr_b200 import machine as M
+    mach = M.SymbolicMachine(
+        [["x@0", "*", "y@1"]],
+        [{"id": 3, "mult": "x@0", "args": [["y@1", "+", 1], 17]}],
+        [["z@2", {"QuotientOrZero": ["x@0", "y@1"]}], ["k@3", {"Constant": 9}]])
+    H = 16
+    specs, bc = M.compile_derived(mach, H)
+    # denominator, INV_OR_ZERO, numerator, MUL (cuda/mod.rs:124-130); PUSH_APC operand = col*H (cuda/mod.rs:61)
+    assert bc[:6] == [0, 1 * H, 6, 0, 0 * H, 4] and specs[0] == (2, 0, 6)
+    assert bc[6:] == [1, 9] and specs[1] == (3, 6, 2)
+    ints, spans, bbc = M.compile_bus(mach, H)
+    assert ints == [(3, 2, 0)] and len(spans) == 3        # [mult, arg0, arg1] (cuda_abi.rs:150-160)
+    assert bbc[spans[0][0]:spans[0][0] + spans[0][1]] == [0, 0]
+    assert bbc[spans[2][0]:spans[2][0] + spans[2][1]] == [1, 17]
+
+
+def test_stack_depth_of_fixtures_fits_reference_capacity():
+    from powdr_b200 import machine as M
+    mach = M.SymbolicMachine.from_json_file(os.path.join(GOLDEN, "single_div_nondet.machine.json"))
+    bc, spans = M.compile_constraints(mach)
+    worst = 0
+    for off, ln in spans:
+        d, ip = 0, off
+        while ip < off + ln:
+            op = bc[ip]
+            ip += 1
+            if op in (0, 1):
+                ip += 1
+                d += 1
+            elif op in (2, 3, 4):
+                d -= 1
+            worst = max(worst, d)
+    assert worst <= 16 and worst == 7      # max eval-stack depth 7 for this fixture
+
+
+def test_synthetic_machine_shape():
+    from powdr_b200 import machine as M
+    mach = M.synthetic_machine(2022, 187, seed=1)
+    assert mach.width == 2022 and len(mach.constraints) == 187
+    assert max(M.degree(c) for c in mach.constraints) == 3

@@ -1,0 +1,251 @@
+"""CPU tests: the oracle against (a) everything the reference tree pins for this path -- field facts, expression
+semantics, the shipped machines (JSON fixtures + 62 optimized snapshots), the sizes the reference's own tests assert --
+(b) algorithm-independent self-checks (naive DFT, restriction, fold identity, Merkle paths) and (c) the committed KATs."""
+import json
+import os
+
+import numpy as np
+import pytest
+
+from util import P, rand_field, bitrev, bitrev_perm
+
+GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+
+
+def load(name):
+    with open(os.path.join(GOLDEN, name)) as f:
+        return json.load(f)
+
+
+# ---- field facts pinned in-tree: /root/reference/number/src/baby_bear.rs:46-55 ((p-1)/2 = 0x3c000000) ----
+def test_modulus_and_generator():
+    assert (P - 1) // 2 == 0x3C000000
+    assert P == 15 * 2**27 + 1
+    for q in (2, 3, 5):
+        assert pow(31, (P - 1) // q, P) != 1          # 31 generates F_p^*
+    assert pow(pow(31, 15, P), 2**26, P) == P - 1     # two-adic generator has exact order 2^27
+
+
+def test_poseidon2_constants_match_published_rc16_prefix():
+    """The Grain-LFSR generator reproduces the first words of the public Horizen-Labs/Plonky3 BabyBear RC16 table
+    (recollected values; the reference tree holds none -- parity unpinned)."""
+    doc = json.load(open(os.path.join(os.path.dirname(GOLDEN), "..", "constants", "poseidon2_babybear_w16.json")))
+    assert doc["external_initial"][0][:8] == [0x69CBB6AF, 0x46AD93F9, 0x60A00F4E, 0x6B1297CD, 0x23189AFE, 0x732E7BEF, 0x72C246DE, 0x2C941900]
+    assert doc["internal"][0] == 0x5A8053C0
+    assert len(doc["external_initial"]) == 4 and len(doc["external_terminal"]) == 4 and len(doc["internal"]) == 13
+    d = doc["internal_diag_m1"]
+    assert d[0] == P - 2 and d[1] == 1 and d[2] == 2 and (2 * d[3]) % P == 1 and (d[12] << 27) % P == 1
+
+
+# ---- self-checks ----
+@pytest.mark.parametrize("log_n", [1, 2, 5, 8])
+def test_ntt_vs_naive(orc, log_n):
+    rng = np.random.default_rng(log_n)
+    a = rand_field(rng, 1 << log_n)
+    assert (orc.ntt(a) == orc.dft_naive(a)).all()
+    assert (orc.intt(orc.ntt(a)) == a).all()
+
+
+def test_lde_is_bitreversed_coset_evaluation(orc):
+    rng = np.random.default_rng(3)
+    log_n = 5
+    n = 1 << log_n
+    co = rand_field(rng, n)
+    lde = orc.lde_batch(orc.ntt(co)[None, :], 1, 31)[0]
+    pad = np.zeros(2 * n, dtype=np.uint32)
+    pad[:n] = co
+    nat = orc.dft_naive(pad, 31)
+    assert (lde[bitrev_perm(log_n + 1)] == nat).all()
+    # restriction: shift = 1 -> first (bit-reversed) half is the trace
+    ev = orc.ntt(co)
+    l1 = orc.lde_batch(ev[None, :], 1, 1)[0]
+    assert (l1[:n][bitrev_perm(log_n)] == ev).all()
+
+
+def test_fold_identity(orc):
+    """fold(f)(x^2) = f_e(x^2) + beta f_o(x^2): folding a low-degree codeword gives the codeword of the folded polynomial"""
+    rng = np.random.default_rng(5)
+    log_len = 6
+    n = 1 << log_len
+
+    def ext_mul(a, b):
+        t = [0] * 7
+        for i in range(4):
+            for j in range(4):
+                t[i + j] = (t[i + j] + int(a[i]) * int(b[j])) % P
+        return [(t[i] + 11 * t[i + 4]) % P if i < 3 else t[i] for i in range(4)]
+
+    co = rand_field(rng, (n // 2, 4))
+    f = np.zeros((n, 4), dtype=np.uint32)
+    for l in range(4):
+        pad = np.zeros(n, dtype=np.uint32)
+        pad[: n // 2] = co[:, l]
+        nat = orc.dft_naive(pad, 31)
+        for i in range(n):
+            f[bitrev(i, log_len), l] = nat[i]
+    beta = rand_field(rng, 4)
+    g = orc.fri_fold(f, 31, beta)
+    cp = np.zeros((n // 4, 4), dtype=np.uint32)
+    for k in range(n // 4):
+        m = ext_mul(beta, co[2 * k + 1])
+        cp[k] = [(int(co[2 * k][i]) + m[i]) % P for i in range(4)]
+    for l in range(4):
+        pad = np.zeros(n // 2, dtype=np.uint32)
+        pad[: n // 4] = cp[:, l]
+        nat = orc.dft_naive(pad, 31 * 31 % P)
+        for i in range(n // 2):
+            assert g[bitrev(i, log_len - 1), l] == nat[i]
+
+
+def test_merkle_structure(orc):
+    rng = np.random.default_rng(7)
+    m0, m1 = rand_field(rng, (11, 8)), rand_field(rng, (3, 8))
+    layers = orc.merkle_commit([m0, m1])
+    assert [l.shape[0] for l in layers] == [8, 4, 2, 1]
+    assert (layers[0][5] == orc.hash_row(np.concatenate([m0[:, 5], m1[:, 5]]))).all()
+    assert (layers[1][2] == orc.compress(layers[0][4], layers[0][5])).all()
+    assert (layers[3][0] == orc.compress(layers[2][0], layers[2][1])).all()
+
+
+def test_sponge_is_overwrite_mode(orc):
+    """PaddingFreeSponge: a 9-element row = permute(permute(row[0:8] || 0^8) with lane 0 overwritten by row[8])"""
+    row = np.arange(100, 109, dtype=np.uint32)
+    st = np.zeros(16, dtype=np.uint32)
+    st[:8] = row[:8]
+    st = orc.poseidon2_permute(st)
+    st[0] = row[8]
+    st = orc.poseidon2_permute(st)
+    assert (orc.hash_row(row) == st[:8]).all()
+
+
+def test_oracle_kats(orc):
+    k = load("oracle_kat.json")
+    assert orc.poseidon2_permute(np.zeros(16, dtype=np.uint32)).tolist() == k["perm_zero"]
+    assert orc.poseidon2_permute(np.arange(16, dtype=np.uint32)).tolist() == k["perm_iota"]
+    assert orc.hash_row(np.array(k["row21"], dtype=np.uint32)).tolist() == k["hash_row21"]
+    assert orc.compress(np.arange(8, dtype=np.uint32), np.arange(8, 16, dtype=np.uint32)).tolist() == k["compress"]
+    ch = orc.Challenger()
+    ch.observe(np.arange(1, 12, dtype=np.uint32))
+    assert [ch.sample() for _ in range(10)] == k["challenger_after_11"]
+    assert orc.lde_batch(np.array(k["lde_in"], dtype=np.uint32), 1, 31).tolist() == k["lde_out"]
+    assert orc.fri_fold(np.array(k["fold_in"], dtype=np.uint32), 31, k["fold_beta"]).tolist() == k["fold_out"]
+
+
+def test_poseidon2_is_a_permutation_with_full_diffusion(orc):
+    a = orc.poseidon2_permute(np.zeros(16, dtype=np.uint32))
+    e = np.zeros(16, dtype=np.uint32)
+    e[15] = 1
+    b = orc.poseidon2_permute(e)
+    assert all(int(x) != int(y) for x, y in zip(a, b))
+
+
+# ---- expression semantics pinned by the reference (expression/src/lib.rs:179-246) ----
+def test_expression_json_codec_example(orc):
+    """the reference's own serde test shape: [[5,"*","x"],"-",3]"""
+    from powdr_b200 import machine as M
+    mach = M.SymbolicMachine([[[5, "*", "x@0"], "-", 3]])
+    bc, spans = M.compile_constraints(mach)
+    assert bc == [1, 5, 0, 0, 4, 1, 3, 3]            # PUSH_CONST 5, PUSH_APC 0, MUL, PUSH_CONST 3, SUB
+    mat = np.array([[7, 0, P - 1]], dtype=np.uint32)
+    out = orc.constraint_fold(bc, spans, mat, [1, 0, 0, 0])
+    assert out[0].tolist() == [32, P - 3, (5 * (P - 1) - 3) % P] and not out[1:].any()
+
+
+def test_inv_or_zero_semantics(orc):
+    bc = [0, 0, 6]                                       # PUSH_APC 0, INV_OR_ZERO
+    mat = np.array([0, 1, 2, P - 1], dtype=np.uint32)
+    vals = [orc.eval_expr(bc, mat, r) for r in range(4)]
+    assert vals == [0, 1, (P + 1) // 2, P - 1]
+
+
+def test_snapshot_machines_vanish_on_zero_row(orc):
+    """All 62 optimized APC snapshots of the reference (778 constraints, degree <= 3) hold on the all-zero padding row
+    (guard invariant, /root/reference/autoprecompiles/src/lib.rs:415-453,470-524; padding at cuda/mod.rs:264-269)."""
+    from powdr_b200 import machine as M
+    snaps = load("apc_snapshots.json")
+    assert len(snaps) == 62
+    total = 0
+    for key, s in snaps.items():
+        mach = M.SymbolicMachine(s["constraints"], s["bus_interactions"])
+        total += len(mach.constraints)
+        assert max([M.degree(c) for c in mach.constraints] + [0]) <= 3
+        for b in mach.bus_interactions:
+            assert max(M.degree(e) for e in [b["mult"]] + b["args"]) <= 2
+        bc, spans = M.compile_constraints(mach)
+        zero = np.zeros((mach.width, 2), dtype=np.uint32)
+        assert not orc.constraint_fold(bc, spans, zero, [3, 1, 4, 1]).any(), key
+    assert total == 778
+
+
+def test_reference_fixture_sizes():
+    """sizes asserted by the reference's own optimizer tests (/root/reference/autoprecompiles/tests/optimizer.rs:72-83,...)"""
+    st = load("fixture_stats.json")
+    assert (st["keccak_apc_pre_opt"]["columns"], st["keccak_apc_pre_opt"]["bus_interactions"], st["keccak_apc_pre_opt"]["constraints"]) == (27521, 13262, 28627)
+    assert st["keccak_apc_pre_opt"]["degree_hist"] == [1551, 4978, 12029, 10069]
+    assert st["single_div_nondet"]["constraints"] == 74 and st["single_div_nondet"]["columns"] == 59
+
+
+def test_single_div_fixture_against_python_evaluator(orc):
+    """independent check of the bytecode path: evaluate the fixture's expression trees directly in Python"""
+    from powdr_b200 import machine as M
+    mach = M.SymbolicMachine.from_json_file(os.path.join(GOLDEN, "single_div_nondet.machine.json"))
+    bc, spans = M.compile_constraints(mach)
+    rng = np.random.default_rng(41)
+    mat = rand_field(rng, (mach.width, 3))
+
+    def ev(e, r):
+        if isinstance(e, int):
+            return e % P
+        if isinstance(e, str):
+            return int(mat[mach.col_of(e), r])
+        if len(e) == 2:
+            return (-ev(e[1], r)) % P
+        a, b = ev(e[0], r), ev(e[2], r)
+        return (a + b) % P if e[1] == "+" else (a - b) % P if e[1] == "-" else (a * b) % P
+
+    for k, c in enumerate(mach.constraints):
+        o, l = spans[k]
+        sub = [(0, l)]
+        got = orc.constraint_fold(bc[o:o + l], sub, mat, [1, 0, 0, 0])[0]
+        assert got.tolist() == [ev(c, r) for r in range(3)]
+
+
+def test_quotient_times_vanishing_is_fold(orc):
+    from powdr_b200 import machine as M
+    mach = M.synthetic_machine(9, 4, seed=2)
+    bc, spans = M.compile_constraints(mach)
+    rng = np.random.default_rng(43)
+    log_n = 4
+    n = 1 << log_n
+    lde = rand_field(rng, (mach.width, 2 * n))
+    alpha = rand_field(rng, 4)
+    q = orc.quotient(bc, spans, lde, log_n, alpha)
+    fold = orc.constraint_fold(bc, spans, lde, alpha)
+    gn = pow(31, n, P)
+    for r in range(2 * n):
+        i = bitrev(r, log_n + 1)
+        z = (gn * (1 if i % 2 == 0 else P - 1) - 1) % P
+        chunk, j = r >> log_n, r & (n - 1)
+        assert chunk == i % 2
+        for l in range(4):
+            assert int(q[chunk, l, j]) * z % P == int(fold[l, r])
+
+
+# ---- stage 0 oracle vs a direct numpy statement of the reference kernels ----
+def test_tracegen_oracle(orc):
+    rng = np.random.default_rng(47)
+    a0, a1 = rand_field(rng, (5, 16)), rand_field(rng, (3, 32))
+    subs = [(0, 2, 0, 0), (1, 1, 1, 3), (0, 4, 0, 1)]
+    out = orc.apc_tracegen(8, 4, [(a0, 1), (a1, 2)], subs, 6)
+    assert (out[0, :6] == a0[2, :6]).all() and not out[0, 6:].any()
+    assert (out[3, :6] == a1[1, 1:13:2]).all() and not out[3, 6:].any()
+    assert (out[1, :6] == a0[4, :6]).all()
+    # derived: col2 = QuotientOrZero(col0, col1) = col0 / col1 (0 when col1 == 0), absolute-offset bytecode
+    H = 8
+    out[1, 2] = 0
+    bc = [0, 1 * H, 6, 0, 0 * H, 4]
+    orc.apc_apply_derived(out, 6, [(2, 0, len(bc))], bc)
+    for r in range(6):
+        d = int(out[1, r])
+        assert int(out[2, r]) == (int(out[0, r]) * pow(d, P - 2, P)) % P
+    assert not out[2, 6:].any()
