@@ -298,9 +298,10 @@ int pb_ctx_create(pb_ctx_t** out, int device, void* cuda_stream) {
     ctx->stream = (cudaStream_t)cuda_stream;
     for (auto& e : ctx->ev) CK(cudaEventCreate(&e));
     for (int i = 0; i < pb_ctx::KPROF; i++) { CK(cudaEventCreate(&ctx->kp_a[i])); CK(cudaEventCreate(&ctx->kp_b[i])); }
-    CK(cudaFuncSetAttribute(ntt::inv_hi_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 4 << ntt::LOG_TILE_HI_MAX));
-    CK(cudaFuncSetAttribute(ntt::fwd_hi_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 4 << ntt::LOG_TILE_HI_MAX));
-    CK(cudaFuncSetAttribute(ntt::lo_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 8 << ntt::LOG_TILE_LO));
+    CK(cudaFuncSetAttribute(ntt::strided_pass_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 4 << ntt::LOG_TILE_MAX));
+    CK(cudaFuncSetAttribute(ntt::strided_pass_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 4 << ntt::LOG_TILE_MAX));
+    CK(cudaFuncSetAttribute(ntt::transposed_pass_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 4 << ntt::LOG_TILE_MAX));
+    CK(cudaFuncSetAttribute(ntt::transposed_pass_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 4 << ntt::LOG_TILE_MAX));
     int rc = upload_p2(ctx, PB_P2_RC_EXT, PB_P2_RC_INT, PB_P2_DIAG_M1);
     if (rc) { delete ctx; return rc; }
     *out = ctx;
@@ -375,36 +376,59 @@ int pb_lde_batch(pb_ctx_t* ctx, const uint32_t* d_trace, size_t log_n, size_t wi
     const TwiddleSet* tw;
     int rc = get_twiddles(ctx, n, (int)log_blowup, shift, &tw);
     if (rc) return rc;
-    const int n_lo = n <= 12 ? n : (n + 1) / 2;
+    const int n_lo = n <= 10 ? n : (n + 1) / 2;
     const int n_hi = n - n_lo;
-    int log_lc = std::min(5, n_lo);
-    if (n_hi + log_lc > ntt::LOG_TILE_HI_MAX) log_lc = ntt::LOG_TILE_HI_MAX - n_hi;
-    const int log_tile_lo = std::min(ntt::LOG_TILE_LO, n);
+    const int log_lc_hi = std::min(5, ntt::LOG_TILE_MAX - n_hi);          // K1/K3 tile: 2^n_hi rows x 2^log_lc_hi lanes
+    const int log_lc_lo = std::min(5, ntt::LOG_TILE_MAX - n_lo);          // K2 tile:    2^n_lo rows x 2^log_lc_lo blocks
+    auto make_rounds = [](int bits, bool descending) {
+        ntt::Rounds r{};
+        const int nr = (bits + 4) / 5;
+        r.n = nr;
+        int q[ntt::MAX_ROUNDS], b0[ntt::MAX_ROUNDS], acc = 0;
+        for (int i = 0; i < nr; i++) { q[i] = bits / nr + (i < bits % nr ? 1 : 0); b0[i] = acc; acc += q[i]; }
+        for (int i = 0; i < nr; i++) { const int k = descending ? nr - 1 - i : i; r.q[i] = q[k]; r.b0[i] = b0[k]; }
+        return r;
+    };
     // column batch sized so both intermediates (4N + 4N*cosets bytes per column) stay L2-resident (~48 MB)
     size_t batch = std::max<size_t>(1, ((size_t)48 << 20) / (4 * N * (1 + cosets)));
     batch = std::min<size_t>(std::min<size_t>(batch, width), 32768);
-    if (n_hi > 0) { rc = ctx->tmp.ensure(batch * N); if (rc) return rc; }
-    rc = ctx->tmp2.ensure(batch * N * cosets);
-    if (rc) return rc;
-    const size_t smem_hi = (size_t)4 << (n_hi + log_lc);
-    const size_t smem_lo = (size_t)8 << log_tile_lo;
+    rc = ctx->tmp.ensure(batch * N); if (rc) return rc;
+    rc = ctx->tmp2.ensure(batch * N * cosets); if (rc) return rc;
+    const size_t smem_hi = (size_t)4 << (n_hi + log_lc_hi);
+    const size_t smem_lo = (size_t)4 << (n_lo + log_lc_lo);
+    const ntt::Rounds r_inv_hi = make_rounds(n_hi, true), r_fwd_hi = make_rounds(n_hi, false);
+    const ntt::Rounds r_inv_lo = make_rounds(n_lo, true), r_fwd_lo = make_rounds(n_lo, false);
     for (size_t c0 = 0; c0 < width; c0 += batch) {
         const unsigned nb = (unsigned)std::min(batch, width - c0);
         const uint32_t* src = d_trace + c0 * N;
         if (n_hi > 0) {
-            dim3 g1((unsigned)(1u << (n_lo - log_lc)), nb);
-            ntt::inv_hi_kernel<<<g1, ntt::K13_THREADS, smem_hi, ctx->stream>>>(src, N, ctx->tmp.p, n, n_lo, log_lc, tw->d_inv);
+            dim3 g1((unsigned)(1u << (n_lo - log_lc_hi)), nb);
+            ntt::strided_pass_kernel<true><<<g1, ntt::THREADS, smem_hi, ctx->stream>>>(src, N, ctx->tmp.p, N, n, n_lo, log_lc_hi,
+                                                                                       (int)log_blowup, tw->d_inv, r_inv_hi);
             LAUNCHED(ctx);
             src = ctx->tmp.p;
         }
-        dim3 g2((unsigned)(N >> log_tile_lo), nb);
-        ntt::lo_kernel<<<g2, ntt::K2_THREADS, smem_lo, ctx->stream>>>(src, N, ctx->tmp2.p, n, n_lo, log_tile_lo, tw->d_inv, tw->d_fwd,
-                                                                      tw->ninv, cosets);
+        const size_t total_blocks = (size_t)nb << n_hi;
+        const unsigned gx = (unsigned)((total_blocks + ((size_t)1 << log_lc_lo) - 1) >> log_lc_lo);
+        ntt::transposed_pass_kernel<true><<<dim3(gx), ntt::THREADS, smem_lo, ctx->stream>>>(src, N, ctx->tmp.p, n, n_lo, log_lc_lo,
+                                                                                            (int)log_blowup, total_blocks, tw->d_inv,
+                                                                                            tw->ninv, r_inv_lo);
         LAUNCHED(ctx);
-        dim3 g3((unsigned)(1u << (n_lo - log_lc)), nb, (unsigned)cosets);
-        ntt::fwd_hi_kernel<<<g3, ntt::K13_THREADS, smem_hi, ctx->stream>>>(ctx->tmp2.p, d_lde + c0 * N * cosets, N * cosets, n, n_lo,
-                                                                           log_lc, (int)log_blowup, tw->d_fwd);
+        ntt::transposed_pass_kernel<false><<<dim3(gx, 1, (unsigned)cosets), ntt::THREADS, smem_lo, ctx->stream>>>(
+            ctx->tmp.p, N, ctx->tmp2.p, n, n_lo, log_lc_lo, (int)log_blowup, total_blocks, tw->d_fwd, 0u, r_fwd_lo);
         LAUNCHED(ctx);
+        uint32_t* out = d_lde + c0 * N * cosets;
+        if (n_hi > 0) {
+            dim3 g3((unsigned)(1u << (n_lo - log_lc_hi)), nb, (unsigned)cosets);
+            ntt::strided_pass_kernel<false><<<g3, ntt::THREADS, smem_hi, ctx->stream>>>(ctx->tmp2.p, 0, out, N * cosets, n, n_lo,
+                                                                                        log_lc_hi, (int)log_blowup, tw->d_fwd, r_fwd_hi);
+            LAUNCHED(ctx);
+        } else {
+            const size_t tot = ((size_t)nb * cosets) << n;
+            ntt::bitrev_store_kernel<<<(unsigned)((tot + 255) / 256), 256, 0, ctx->stream>>>(ctx->tmp2.p, out, N * cosets, n,
+                                                                                             (int)log_blowup, nb);
+            LAUNCHED(ctx);
+        }
     }
     CK(cudaGetLastError());
     return 0;
