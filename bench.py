@@ -138,6 +138,7 @@ def run_native(a):
     import numpy as np
     import torch
     import powdr_b200
+    from powdr_b200 import parallel
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
@@ -159,13 +160,12 @@ def run_native(a):
     # uniform field elements; the buffer is read as Montgomery-form words (uniform either way)
     trace = torch.randint(0, P, (w, n), dtype=torch.int32, device=dev, generator=gen)
     caps = torch.zeros(16, dtype=torch.int32, device=dev)
-    all_caps = torch.zeros(16 * world, dtype=torch.int32, device=dev) if world > 1 else None
 
     def step_device():
         proof = ctx.prove_segment(air, trace.data_ptr(), a.log_n, w, on_device=True)
         if world > 1:   # the path's one exchange: all-gather of the segment commitments (Merkle caps) over NCCL/NVLink
             caps.copy_(torch.tensor(proof["trace_root"] + proof["quotient_root"], dtype=torch.int64).to(torch.int32), non_blocking=True)
-            dist.all_gather_into_tensor(all_caps, caps)
+            parallel.all_gather_caps(caps.view(2, 8), dist)
         return proof
 
     def sync_all():

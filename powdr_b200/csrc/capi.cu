@@ -5,6 +5,7 @@
 // /root/reference/openvm-riscv/src/lib.rs:327-332).  No CPU fallback exists: every entry point needs a CUDA device.
 #include <cuda_runtime.h>
 #include <stdint.h>
+#include <stdlib.h>
 #include <string.h>
 #include <algorithm>
 #include <unordered_map>
@@ -161,7 +162,9 @@ struct pb_ctx {
     DevBuf<uint32_t> tmp, tmp2;       // LDE intermediates (L2-sized)
     DevBuf<const uint32_t*> coltab;
     // pb_prove_segment workspace
-    DevBuf<uint32_t> ws_trace, ws_lde, ws_layers, ws_q, ws_qnat, ws_qlde, ws_f0, ws_f1;
+    DevBuf<uint32_t> ws_trace, ws_lde, ws_layers, ws_q, ws_qnat, ws_qlde, ws_f0, ws_f1, ws_state;
+    cudaStream_t copy_stream = nullptr;   // H2D chunks of the host-input pipeline
+    cudaEvent_t ev_copy[2] = {nullptr}, ev_free[2] = {nullptr};
     cudaEvent_t ev[8] = {nullptr};
     float stage_ms[8] = {0};
     // live timing of the dominant kernel (Poseidon2 leaf hashing over column-major matrices): event pairs on the stream
@@ -297,6 +300,11 @@ int pb_ctx_create(pb_ctx_t** out, int device, void* cuda_stream) {
     ctx->device = device;
     ctx->stream = (cudaStream_t)cuda_stream;
     for (auto& e : ctx->ev) CK(cudaEventCreate(&e));
+    CK(cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking));
+    for (int i = 0; i < 2; i++) {
+        CK(cudaEventCreateWithFlags(&ctx->ev_copy[i], cudaEventDisableTiming));
+        CK(cudaEventCreateWithFlags(&ctx->ev_free[i], cudaEventDisableTiming));
+    }
     for (int i = 0; i < pb_ctx::KPROF; i++) { CK(cudaEventCreate(&ctx->kp_a[i])); CK(cudaEventCreate(&ctx->kp_b[i])); }
     CK(cudaFuncSetAttribute(ntt::strided_pass_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 4 << ntt::LOG_TILE_MAX));
     CK(cudaFuncSetAttribute(ntt::strided_pass_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 4 << ntt::LOG_TILE_MAX));
@@ -316,7 +324,9 @@ int pb_ctx_destroy(pb_ctx_t* ctx) {
     if (ctx->d_fold_tab) cudaFree(ctx->d_fold_tab);
     ctx->tmp.release(); ctx->tmp2.release(); ctx->coltab.release();
     ctx->ws_trace.release(); ctx->ws_lde.release(); ctx->ws_layers.release(); ctx->ws_q.release();
-    ctx->ws_qnat.release(); ctx->ws_qlde.release(); ctx->ws_f0.release(); ctx->ws_f1.release();
+    ctx->ws_qnat.release(); ctx->ws_qlde.release(); ctx->ws_f0.release(); ctx->ws_f1.release(); ctx->ws_state.release();
+    if (ctx->copy_stream) cudaStreamDestroy(ctx->copy_stream);
+    for (int i = 0; i < 2; i++) { if (ctx->ev_copy[i]) cudaEventDestroy(ctx->ev_copy[i]); if (ctx->ev_free[i]) cudaEventDestroy(ctx->ev_free[i]); }
     for (auto& e : ctx->ev) if (e) cudaEventDestroy(e);
     for (int i = 0; i < pb_ctx::KPROF; i++) { if (ctx->kp_a[i]) cudaEventDestroy(ctx->kp_a[i]); if (ctx->kp_b[i]) cudaEventDestroy(ctx->kp_b[i]); }
     delete ctx;
@@ -389,8 +399,15 @@ int pb_lde_batch(pb_ctx_t* ctx, const uint32_t* d_trace, size_t log_n, size_t wi
         for (int i = 0; i < nr; i++) { const int k = descending ? nr - 1 - i : i; r.q[i] = q[k]; r.b0[i] = b0[k]; }
         return r;
     };
-    // column batch sized so both intermediates (4N + 4N*cosets bytes per column) stay L2-resident (~48 MB)
-    size_t batch = std::max<size_t>(1, ((size_t)48 << 20) / (4 * N * (1 + cosets)));
+    // Column batch: the passes are integer-pipe bound (ncu: DRAM < 15 % busy), so filling the machine evenly matters more
+    // than keeping the intermediates L2-resident: size the batch so every pass launches a whole number of 148-CTA waves
+    // (one 128 KB-tile CTA per SM).  PB_LDE_BATCH overrides for experiments.
+    size_t batch;
+    {
+        const size_t tiles_per_col = std::max<size_t>(1, N >> ntt::LOG_TILE_MAX);
+        batch = std::max<size_t>(1, (size_t)148 * 8 / tiles_per_col);
+        if (const char* e = getenv("PB_LDE_BATCH")) batch = std::max<size_t>(1, (size_t)atol(e));
+    }
     batch = std::min<size_t>(std::min<size_t>(batch, width), 32768);
     rc = ctx->tmp.ensure(batch * N); if (rc) return rc;
     rc = ctx->tmp2.ensure(batch * N * cosets); if (rc) return rc;
@@ -635,12 +652,6 @@ int pb_prove_segment(pb_ctx_t* ctx, const pb_air_t* a, const uint32_t* trace, si
     cudaStream_t st = ctx->stream;
 #define RC(x) do { rc = (x); if (rc) return rc; } while (0)
     CK(cudaEventRecord(ctx->ev[0], st));
-    const uint32_t* d_trace = trace;
-    if (!(flags & PB_TRACE_ON_DEVICE)) {
-        RC(ctx->ws_trace.ensure(width * N));
-        CK(cudaMemcpyAsync(ctx->ws_trace.p, trace, width * N * 4, cudaMemcpyHostToDevice, st));
-        d_trace = ctx->ws_trace.p;
-    }
     RC(ctx->ws_lde.ensure(width * M));
     RC(ctx->ws_layers.ensure(8 * (2 * M)));
     RC(ctx->ws_q.ensure(8 * N));
@@ -652,13 +663,47 @@ int pb_prove_segment(pb_ctx_t* ctx, const pb_air_t* a, const uint32_t* trace, si
     ch.k = &ctx->p2;
     uint32_t root_m[8];
 
-    // main trace commit: LDE then Merkle
-    CK(cudaEventRecord(ctx->ev[1], st));
-    RC(pb_lde_batch(ctx, d_trace, log_n, width, log_blowup, bb::GEN, ctx->ws_lde.p));
-    CK(cudaEventRecord(ctx->ev[2], st));
-    const uint32_t* mats1[1] = {ctx->ws_lde.p};
-    RC(pb_merkle_commit(ctx, mats1, &width, 1, log_m, ctx->ws_layers.p, nullptr));
-    CK(cudaEventRecord(ctx->ev[3], st));
+    if (flags & PB_TRACE_ON_DEVICE) {
+        // main trace commit: LDE then Merkle
+        CK(cudaEventRecord(ctx->ev[1], st));
+        RC(pb_lde_batch(ctx, trace, log_n, width, log_blowup, bb::GEN, ctx->ws_lde.p));
+        CK(cudaEventRecord(ctx->ev[2], st));
+        const uint32_t* mats1[1] = {ctx->ws_lde.p};
+        RC(pb_merkle_commit(ctx, mats1, &width, 1, log_m, ctx->ws_layers.p, nullptr));
+        CK(cudaEventRecord(ctx->ev[3], st));
+    } else {
+        // Host trace: software pipeline over column chunks.  The PCIe copy of chunk k+1 (copy stream, double-buffered
+        // staging) overlaps the LDE and the sponge absorption of chunk k (compute stream); per-row sponge states live in
+        // HBM between chunks.  Stage clocks in this mode: [1]->[2] = copy+LDE+leaf hashing overlapped, [2]->[3] = upper layers.
+        size_t cw = std::min<size_t>(width, std::max<size_t>(8, ((((size_t)256 << 20) / (4 * N)) / 8) * 8));
+        const size_t n_chunks = (width + cw - 1) / cw;
+        RC(ctx->ws_trace.ensure(2 * cw * N));
+        RC(ctx->ws_state.ensure(16 * M));
+        std::vector<const uint32_t*> cols(width);
+        for (size_t c = 0; c < width; c++) cols[c] = ctx->ws_lde.p + c * M;
+        RC(ctx->coltab.ensure(width));
+        CK(cudaMemcpyAsync(ctx->coltab.p, cols.data(), width * sizeof(void*), cudaMemcpyHostToDevice, st));
+        CK(cudaEventRecord(ctx->ev[1], st));
+        CK(cudaEventRecord(ctx->ev_free[0], st));          // orders the first copies after everything already queued on st
+        CK(cudaEventRecord(ctx->ev_free[1], st));
+        for (size_t k = 0; k < n_chunks; k++) {
+            const int b = (int)(k & 1);
+            const size_t c0 = k * cw, wk = std::min(cw, width - c0);
+            uint32_t* stage = ctx->ws_trace.p + (size_t)b * cw * N;
+            CK(cudaStreamWaitEvent(ctx->copy_stream, ctx->ev_free[b], 0));
+            CK(cudaMemcpyAsync(stage, trace + c0 * N, wk * N * 4, cudaMemcpyHostToDevice, ctx->copy_stream));
+            CK(cudaEventRecord(ctx->ev_copy[b], ctx->copy_stream));
+            CK(cudaStreamWaitEvent(st, ctx->ev_copy[b], 0));
+            RC(pb_lde_batch(ctx, stage, log_n, wk, log_blowup, bb::GEN, ctx->ws_lde.p + c0 * M));
+            CK(cudaEventRecord(ctx->ev_free[b], st));
+            p2::leaf_absorb_cols_kernel<<<(unsigned)((M + 255) / 256), 256, 0, st>>>(ctx->coltab.p + c0, (uint32_t)wk, M, ctx->ws_state.p,
+                                                                                    ctx->ws_layers.p, k == 0, k + 1 == n_chunks);
+            LAUNCHED(ctx);
+        }
+        CK(cudaEventRecord(ctx->ev[2], st));
+        RC(merkle_upper(ctx, ctx->ws_layers.p, log_m));
+        CK(cudaEventRecord(ctx->ev[3], st));
+    }
     RC(read_root(ctx, ctx->ws_layers.p, log_m, root_m));
     for (int i = 0; i < 8; i++) proof->trace_root[i] = h_from_m(root_m[i]);
     ch.observe(root_m, 8);

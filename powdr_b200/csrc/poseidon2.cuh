@@ -121,6 +121,54 @@ __global__ void __launch_bounds__(256) leaf_hash_cols_kernel(const uint32_t* con
     out[1] = make_uint4(s[4], s[5], s[6], s[7]);
 }
 
+// Streaming variant of the leaf sponge for the host-input pipeline: absorbs one CHUNK of columns (a multiple of 8 unless
+// it is the last chunk) into per-row sponge states kept in HBM as [16][height] (word-major => coalesced), so hashing of
+// chunk k overlaps the PCIe copy and the LDE of chunk k+1.  first: start from the zero state; last: emit the digest.
+__global__ void __launch_bounds__(256) leaf_absorb_cols_kernel(const uint32_t* const* __restrict__ cols, uint32_t n_cols, size_t height,
+                                                                uint32_t* __restrict__ state, uint32_t* __restrict__ digests,
+                                                                int first, int last) {
+    size_t r = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (r >= height) return;
+    uint32_t s[16];
+    if (first) {
+#pragma unroll
+        for (int i = 0; i < 16; i++) s[i] = 0;
+    } else {
+#pragma unroll
+        for (int i = 0; i < 16; i++) s[i] = state[(size_t)i * height + r];
+    }
+    uint32_t full = n_cols / 8;
+    uint32_t nxt[8];
+    if (full) {
+#pragma unroll
+        for (int k = 0; k < 8; k++) nxt[k] = __ldg(cols[k] + r);
+    }
+    for (uint32_t c = 0; c < full; c++) {
+#pragma unroll
+        for (int k = 0; k < 8; k++) s[k] = nxt[k];
+        if (c + 1 < full) {
+#pragma unroll
+            for (int k = 0; k < 8; k++) nxt[k] = __ldg(cols[(c + 1) * 8 + k] + r);
+        }
+        permute(s);
+    }
+    uint32_t rem = n_cols - full * 8;
+    if (rem) {
+#pragma unroll
+        for (int k = 0; k < 8; k++)
+            if ((uint32_t)k < rem) s[k] = __ldg(cols[full * 8 + k] + r);
+        permute(s);
+    }
+    if (last) {
+        uint4* out = reinterpret_cast<uint4*>(digests + 8 * r);
+        out[0] = make_uint4(s[0], s[1], s[2], s[3]);
+        out[1] = make_uint4(s[4], s[5], s[6], s[7]);
+    } else {
+#pragma unroll
+        for (int i = 0; i < 16; i++) state[(size_t)i * height + r] = s[i];
+    }
+}
+
 // leaves of a row-major width-8 matrix (FRI layer: row = (f[2j], f[2j+1]) as 8 base elements): one permutation each
 __global__ void __launch_bounds__(256) leaf_hash_rows8_kernel(const uint4* __restrict__ rows, size_t height, uint32_t* __restrict__ digests) {
     size_t r = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
