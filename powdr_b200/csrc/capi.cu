@@ -17,6 +17,7 @@
 #include "bb31.cuh"
 #include "fri.cuh"
 #include "ntt.cuh"
+#include "ntt_fast.cuh"
 #include "poseidon2.cuh"
 #include "tracegen.cuh"
 
@@ -415,30 +416,38 @@ int pb_lde_batch(pb_ctx_t* ctx, const uint32_t* d_trace, size_t log_n, size_t wi
     const size_t smem_lo = (size_t)4 << (n_lo + log_lc_lo);
     const ntt::Rounds r_inv_hi = make_rounds(n_hi, true), r_fwd_hi = make_rounds(n_hi, false);
     const ntt::Rounds r_inv_lo = make_rounds(n_lo, true), r_fwd_lo = make_rounds(n_lo, false);
+    const bool use_fast = getenv("PB_LDE_GENERIC") == nullptr;     // compile-time specialised passes (ntt_fast.cuh) when available
     for (size_t c0 = 0; c0 < width; c0 += batch) {
         const unsigned nb = (unsigned)std::min(batch, width - c0);
         const uint32_t* src = d_trace + c0 * N;
+        const bool fast = use_fast && nttf::supported(n_hi, n_lo);
         if (n_hi > 0) {
             dim3 g1((unsigned)(1u << (n_lo - log_lc_hi)), nb);
-            ntt::strided_pass_kernel<true><<<g1, ntt::THREADS, smem_hi, ctx->stream>>>(src, N, ctx->tmp.p, N, n, n_lo, log_lc_hi,
-                                                                                       (int)log_blowup, tw->d_inv, r_inv_hi);
+            if (!fast || !nttf::launch_strided(true, n_hi, n_lo, g1, ctx->stream, src, N, ctx->tmp.p, N, (int)log_blowup, tw->d_inv))
+                ntt::strided_pass_kernel<true><<<g1, ntt::THREADS, smem_hi, ctx->stream>>>(src, N, ctx->tmp.p, N, n, n_lo, log_lc_hi,
+                                                                                           (int)log_blowup, tw->d_inv, r_inv_hi);
             LAUNCHED(ctx);
             src = ctx->tmp.p;
         }
         const size_t total_blocks = (size_t)nb << n_hi;
         const unsigned gx = (unsigned)((total_blocks + ((size_t)1 << log_lc_lo) - 1) >> log_lc_lo);
-        ntt::transposed_pass_kernel<true><<<dim3(gx), ntt::THREADS, smem_lo, ctx->stream>>>(src, N, ctx->tmp.p, n, n_lo, log_lc_lo,
-                                                                                            (int)log_blowup, total_blocks, tw->d_inv,
-                                                                                            tw->ninv, r_inv_lo);
+        if (!fast || !nttf::launch_transposed(true, n, n_lo, dim3(gx), ctx->stream, src, N, ctx->tmp.p, (int)log_blowup, total_blocks,
+                                              tw->d_inv, tw->ninv))
+            ntt::transposed_pass_kernel<true><<<dim3(gx), ntt::THREADS, smem_lo, ctx->stream>>>(src, N, ctx->tmp.p, n, n_lo, log_lc_lo,
+                                                                                                (int)log_blowup, total_blocks, tw->d_inv,
+                                                                                                tw->ninv, r_inv_lo);
         LAUNCHED(ctx);
-        ntt::transposed_pass_kernel<false><<<dim3(gx, 1, (unsigned)cosets), ntt::THREADS, smem_lo, ctx->stream>>>(
-            ctx->tmp.p, N, ctx->tmp2.p, n, n_lo, log_lc_lo, (int)log_blowup, total_blocks, tw->d_fwd, 0u, r_fwd_lo);
+        if (!fast || !nttf::launch_transposed(false, n, n_lo, dim3(gx, 1, (unsigned)cosets), ctx->stream, ctx->tmp.p, N, ctx->tmp2.p,
+                                              (int)log_blowup, total_blocks, tw->d_fwd, 0u))
+            ntt::transposed_pass_kernel<false><<<dim3(gx, 1, (unsigned)cosets), ntt::THREADS, smem_lo, ctx->stream>>>(
+                ctx->tmp.p, N, ctx->tmp2.p, n, n_lo, log_lc_lo, (int)log_blowup, total_blocks, tw->d_fwd, 0u, r_fwd_lo);
         LAUNCHED(ctx);
         uint32_t* out = d_lde + c0 * N * cosets;
         if (n_hi > 0) {
             dim3 g3((unsigned)(1u << (n_lo - log_lc_hi)), nb, (unsigned)cosets);
-            ntt::strided_pass_kernel<false><<<g3, ntt::THREADS, smem_hi, ctx->stream>>>(ctx->tmp2.p, 0, out, N * cosets, n, n_lo,
-                                                                                        log_lc_hi, (int)log_blowup, tw->d_fwd, r_fwd_hi);
+            if (!fast || !nttf::launch_strided(false, n_hi, n_lo, g3, ctx->stream, ctx->tmp2.p, 0, out, N * cosets, (int)log_blowup, tw->d_fwd))
+                ntt::strided_pass_kernel<false><<<g3, ntt::THREADS, smem_hi, ctx->stream>>>(ctx->tmp2.p, 0, out, N * cosets, n, n_lo,
+                                                                                            log_lc_hi, (int)log_blowup, tw->d_fwd, r_fwd_hi);
             LAUNCHED(ctx);
         } else {
             const size_t tot = ((size_t)nb * cosets) << n;
