@@ -117,6 +117,13 @@ def poseidon2_permute(state):
     return s
 
 
+def poseidon2_permute_with(state, rc_ext, rc_int, diag):
+    s, a, b, c = _u32(state).copy(), _u32(rc_ext), _u32(rc_int), _u32(diag)
+    assert s.size == 16 and a.size == 128 and b.size == 13 and c.size == 16
+    lib().orc_poseidon2_permute_with(_p(s), _p(a), _p(b), _p(c))
+    return s
+
+
 def hash_row(row):
     r = _u32(row)
     d = np.empty(8, dtype=np.uint32)

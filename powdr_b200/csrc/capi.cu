@@ -190,7 +190,15 @@ int upload_p2(pb_ctx* ctx, const uint32_t rc_ext[8][16], const uint32_t rc_int[1
         ctx->p2.rc_int[r] = m;
         c.rc_int_mp[r] = m - bb::P;
     }
-    for (int i = 0; i < 16; i++) ctx->p2.diag[i] = c.diag[i] = h_to_m(diag[i]);
+    bool p3 = true;
+    for (int i = 0; i < 16; i++) {
+        const uint32_t w = diag[i] % bb::P;
+        ctx->p2.diag[i] = h_to_m(w);
+        c.diag_w[i] = w;
+        c.diag_wp[i] = (uint32_t)(((uint64_t)w << 32) / bb::P);
+        p3 = p3 && w == PB_P2_DIAG_M1[i];
+    }
+    c.p3_diag = p3 ? 1u : 0u;
     CK(cudaMemcpyToSymbolAsync(p2::c_p2, &c, sizeof c, 0, cudaMemcpyHostToDevice, ctx->stream));
     CK(cudaStreamSynchronize(ctx->stream));
     return 0;

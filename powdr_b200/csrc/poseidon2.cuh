@@ -15,7 +15,9 @@ namespace p2 {
 struct Consts {
     uint32_t rc_ext_mp[8][16];   // Montgomery(rc) - p   (as two's-complement u32)
     uint32_t rc_int_mp[13];      // Montgomery(rc) - p
-    uint32_t diag[16];           // Montgomery(V_i), internal matrix = 1 + diag(V)
+    uint32_t diag_w[16];         // V_i canonical, internal matrix = 1 + diag(V): multiplying a Montgomery value by a CANONICAL
+    uint32_t diag_wp[16];        // constant keeps it in Montgomery form -> Shoup's method, wp = floor(w * 2^32 / p)
+    uint32_t p3_diag;            // 1 when V is the Plonky3 vector [-2,1,2,1/2,3,4,-1/2,-3,-4,2^-8,1/4,1/8,2^-27,-2^-8,-1/16,-2^-27]
 };
 __constant__ Consts c_p2;
 
@@ -53,6 +55,14 @@ __device__ __forceinline__ void external_linear(uint32_t (&s)[16]) {
     }
 }
 
+// a * w mod p for a fixed w (Shoup): q = hi(a*w'), r = a*w - q*p in [0,2p), one correction.  IMAD.HI + 2 IMAD = 8 FMA-pipe
+// cycles per warp against 10 for a Montgomery product (IMAD.WIDE and IMAD.HI are half rate on sm_100), and no fix-up adds.
+__device__ __forceinline__ uint32_t mul_const(uint32_t a, uint32_t w, uint32_t wp) {
+    const uint32_t q = __umulhi(a, wp);
+    return bb::reduce_2p(a * w - q * bb::P);
+}
+__device__ __forceinline__ uint32_t halve(uint32_t x) { return (x >> 1) + (x & 1u) * ((bb::P + 1) / 2); }
+
 __device__ __forceinline__ void internal_round(uint32_t (&s)[16], int r) {
     s[0] = sbox_rc(s[0], c_p2.rc_int_mp[r]);
     uint32_t a = bb::add(bb::add(s[0], s[1]), bb::add(s[2], s[3]));
@@ -60,8 +70,21 @@ __device__ __forceinline__ void internal_round(uint32_t (&s)[16], int r) {
     uint32_t c = bb::add(bb::add(s[8], s[9]), bb::add(s[10], s[11]));
     uint32_t d = bb::add(bb::add(s[12], s[13]), bb::add(s[14], s[15]));
     uint32_t sum = bb::add(bb::add(a, b), bb::add(c, d));
+    if (c_p2.p3_diag) {
+        // the cheap entries of the Plonky3 diagonal go to the ALU pipe (which has slack), the rest to Shoup products
+        s[0] = bb::sub(bb::sub(sum, s[0]), s[0]);          // -2
+        s[1] = bb::add(sum, s[1]);                         //  1
+        s[2] = bb::add(sum, bb::dbl(s[2]));                //  2
+        s[3] = bb::add(sum, halve(s[3]));                  //  1/2
+        s[6] = bb::sub(sum, halve(s[6]));                  // -1/2
+        s[4] = bb::add(sum, mul_const(s[4], c_p2.diag_w[4], c_p2.diag_wp[4]));
+        s[5] = bb::add(sum, mul_const(s[5], c_p2.diag_w[5], c_p2.diag_wp[5]));
 #pragma unroll
-    for (int i = 0; i < 16; i++) s[i] = bb::add(sum, bb::mul(s[i], c_p2.diag[i]));
+        for (int i = 7; i < 16; i++) s[i] = bb::add(sum, mul_const(s[i], c_p2.diag_w[i], c_p2.diag_wp[i]));
+    } else {
+#pragma unroll
+        for (int i = 0; i < 16; i++) s[i] = bb::add(sum, mul_const(s[i], c_p2.diag_w[i], c_p2.diag_wp[i]));
+    }
 }
 
 __device__ __forceinline__ void permute(uint32_t (&s)[16]) {

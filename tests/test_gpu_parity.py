@@ -84,6 +84,41 @@ def test_poseidon2_permutation(ctx, orc):
     assert (got == exp).all()
 
 
+def test_poseidon2_custom_constants_generic_diagonal():
+    """pb_ctx_set_poseidon2 with arbitrary constants takes the generic (all-Shoup) internal layer; own context so the
+    session-wide constants stay untouched"""
+    import powdr_b200
+    from oracle import orc
+    ctx2 = powdr_b200.Context(0)
+    try:
+        rng = np.random.default_rng(12)
+        rc_ext, rc_int, diag = rand_field(rng, (8, 16)), rand_field(rng, 13), rand_field(rng, 16)
+        diag[0] = 0
+        diag[1] = P - 1
+        rc = ctx2.lib.pb_ctx_set_poseidon2(ctx2.h, rc_ext.ctypes.data_as(C.c_void_p), rc_int.ctypes.data_as(C.c_void_p),
+                                           diag.ctypes.data_as(C.c_void_p))
+        assert rc == 0
+        st = rand_field(rng, (64, 16))
+        d = ctx2.to_device(st)
+        ctx2.poseidon2_permute(d.ptr, st.shape[0], 1)
+        got = ctx2.to_host(d, st.shape)
+        exp = np.stack([orc.poseidon2_permute_with(s, rc_ext, rc_int, diag) for s in st])
+        assert (got == exp).all()
+        # restore the default instantiation (device constants are per process, not per context)
+        import json
+        doc = json.load(open(os.path.join(os.path.dirname(GOLDEN), "..", "constants", "poseidon2_babybear_w16.json")))
+        e = np.array(doc["external_initial"] + doc["external_terminal"], dtype=np.uint32)
+        i = np.array(doc["internal"], dtype=np.uint32)
+        dg = np.array(doc["internal_diag_m1"], dtype=np.uint32)
+        assert ctx2.lib.pb_ctx_set_poseidon2(ctx2.h, e.ctypes.data_as(C.c_void_p), i.ctypes.data_as(C.c_void_p), dg.ctypes.data_as(C.c_void_p)) == 0
+        st2 = rand_field(rng, (8, 16))
+        d2 = ctx2.to_device(st2)
+        ctx2.poseidon2_permute(d2.ptr, 8, 1)
+        assert (ctx2.to_host(d2, st2.shape) == np.stack([orc.poseidon2_permute(s) for s in st2])).all()
+    finally:
+        ctx2.close()
+
+
 @pytest.mark.parametrize("widths,log_h", [([1], 0), ([8], 1), ([3], 3), ([17], 5), ([8, 8], 6), ([4, 4], 11), ([5, 2, 9], 4), ([33], 12)])
 def test_merkle_matches_oracle(ctx, orc, widths, log_h):
     rng = np.random.default_rng(13 + log_h)
