@@ -64,6 +64,23 @@ BB_HD uint32_t from_signed(int32_t x) {     // (-p,p) -> [0,p)
     return v < u ? v : u;
 }
 
+// Shoup product with a fixed multiplier: w.x = w (canonical), w.y = floor(w * 2^32 / p); a may be any u32 (lazy operands ok).
+// r = a*w - hi(a*w')*p lies in [0, 2p); one correction makes it canonical.  A Montgomery-form `a` stays in Montgomery form.
+BB_HD uint32_t mul_shoup(uint32_t a, uint2 w) {
+#ifdef __CUDA_ARCH__
+    const uint32_t q = __umulhi(a, w.y);
+#else
+    const uint32_t q = (uint32_t)(((uint64_t)a * w.y) >> 32);
+#endif
+    return reduce_2p(a * w.x - q * P);
+}
+BB_HD uint2 shoup_pair(uint32_t w_canonical) {
+    uint2 r;
+    r.x = w_canonical;
+    r.y = (uint32_t)(((uint64_t)w_canonical << 32) / P);
+    return r;
+}
+
 BB_HD uint32_t to_monty(uint32_t canonical) { return mul(canonical, R2); }
 BB_HD uint32_t from_monty(uint32_t m) { return reduce_2p(mul_lazy(m, 1u)); }
 

@@ -110,9 +110,9 @@ struct Challenger {
 struct TwiddleSet {
     int n, log_blowup;
     uint32_t shift;      // canonical
-    uint32_t ninv;       // Montgomery 1/N
-    uint32_t* d_inv;     // [2^n]           tw_inv[2^u + k] = w_{2^(u+1)}^{-k}
-    uint32_t* d_fwd;     // [cosets][2^n]   tw_fwd[c][2^u + k] = S_c^(2^(n-1-u)) * w_{2^(u+1)}^{k},  S_c = shift * w_{N 2^b}^c
+    uint2 ninv;          // Shoup pair of 1/N
+    uint2* d_inv;        // [2^n]           tw_inv[2^u + k] = w_{2^(u+1)}^{-k}            (Shoup pairs: w, floor(w 2^32/p))
+    uint2* d_fwd;        // [cosets][2^n]   tw_fwd[c][2^u + k] = S_c^(2^(n-1-u)) * w_{2^(u+1)}^{k},  S_c = shift * w_{N 2^b}^c
 };
 
 template <typename T>
@@ -209,33 +209,34 @@ int get_twiddles(pb_ctx* ctx, int n, int log_blowup, uint32_t shift, const Twidd
         if (t.n == n && t.log_blowup == log_blowup && t.shift == shift) { *out = &t; return 0; }
     const size_t N = (size_t)1 << n;
     const int cosets = 1 << log_blowup;
-    std::vector<uint32_t> inv(N), fwd(N * cosets);
-    inv[0] = 0;
+    // entries are Shoup pairs (w canonical, floor(w 2^32 / p)); powers are walked in Montgomery form and converted on store
+    std::vector<uint2> inv(N), fwd(N * cosets);
+    inv[0] = make_uint2(0u, 0u);
     for (int u = 0; u < n; u++) {
         uint32_t w = bb::inv(h_root_of_unity_m(u + 1)), x = bb::R1;
-        for (size_t k = 0; k < ((size_t)1 << u); k++) { inv[((size_t)1 << u) + k] = x; x = bb::mul(x, w); }
+        for (size_t k = 0; k < ((size_t)1 << u); k++) { inv[((size_t)1 << u) + k] = bb::shoup_pair(h_from_m(x)); x = bb::mul(x, w); }
     }
     const uint32_t shift_m = h_to_m(shift);
     const uint32_t w_ext = h_root_of_unity_m(n + log_blowup);
     for (int c = 0; c < cosets; c++) {
         uint32_t sc = bb::mul(shift_m, bb::pow(w_ext, (uint64_t)c));
-        uint32_t* f = fwd.data() + (size_t)c * N;
-        f[0] = 0;
+        uint2* f = fwd.data() + (size_t)c * N;
+        f[0] = make_uint2(0u, 0u);
         // factor for stage u is S_c^(2^(n-1-u)): walk u from n-1 down, squaring
         uint32_t fac = sc;
         for (int u = n - 1; u >= 0; u--) {
             uint32_t w = h_root_of_unity_m(u + 1), x = fac;
-            for (size_t k = 0; k < ((size_t)1 << u); k++) { f[((size_t)1 << u) + k] = x; x = bb::mul(x, w); }
+            for (size_t k = 0; k < ((size_t)1 << u); k++) { f[((size_t)1 << u) + k] = bb::shoup_pair(h_from_m(x)); x = bb::mul(x, w); }
             fac = bb::mul(fac, fac);
         }
     }
     TwiddleSet t;
     t.n = n; t.log_blowup = log_blowup; t.shift = shift;
-    t.ninv = bb::inv(h_to_m((uint32_t)(N % bb::P)));
-    CK(cudaMalloc((void**)&t.d_inv, N * 4));
-    CK(cudaMalloc((void**)&t.d_fwd, N * cosets * 4));
-    CK(cudaMemcpyAsync(t.d_inv, inv.data(), N * 4, cudaMemcpyHostToDevice, ctx->stream));
-    CK(cudaMemcpyAsync(t.d_fwd, fwd.data(), N * cosets * 4, cudaMemcpyHostToDevice, ctx->stream));
+    t.ninv = bb::shoup_pair(h_from_m(bb::inv(h_to_m((uint32_t)(N % bb::P)))));
+    CK(cudaMalloc((void**)&t.d_inv, N * sizeof(uint2)));
+    CK(cudaMalloc((void**)&t.d_fwd, N * cosets * sizeof(uint2)));
+    CK(cudaMemcpyAsync(t.d_inv, inv.data(), N * sizeof(uint2), cudaMemcpyHostToDevice, ctx->stream));
+    CK(cudaMemcpyAsync(t.d_fwd, fwd.data(), N * cosets * sizeof(uint2), cudaMemcpyHostToDevice, ctx->stream));
     CK(cudaStreamSynchronize(ctx->stream));
     if (ctx->tws.size() >= 12) {   // bounded cache
         cudaFree(ctx->tws.front().d_inv);
@@ -446,9 +447,9 @@ int pb_lde_batch(pb_ctx_t* ctx, const uint32_t* d_trace, size_t log_n, size_t wi
                                                                                                 tw->ninv, r_inv_lo);
         LAUNCHED(ctx);
         if (!fast || !nttf::launch_transposed(false, n, n_lo, dim3(gx, 1, (unsigned)cosets), ctx->stream, ctx->tmp.p, N, ctx->tmp2.p,
-                                              (int)log_blowup, total_blocks, tw->d_fwd, 0u))
+                                              (int)log_blowup, total_blocks, tw->d_fwd, make_uint2(0u, 0u)))
             ntt::transposed_pass_kernel<false><<<dim3(gx, 1, (unsigned)cosets), ntt::THREADS, smem_lo, ctx->stream>>>(
-                ctx->tmp.p, N, ctx->tmp2.p, n, n_lo, log_lc_lo, (int)log_blowup, total_blocks, tw->d_fwd, 0u, r_fwd_lo);
+                ctx->tmp.p, N, ctx->tmp2.p, n, n_lo, log_lc_lo, (int)log_blowup, total_blocks, tw->d_fwd, make_uint2(0u, 0u), r_fwd_lo);
         LAUNCHED(ctx);
         uint32_t* out = d_lde + c0 * N * cosets;
         if (n_hi > 0) {

@@ -40,8 +40,8 @@ __device__ __forceinline__ uint32_t brev(uint32_t x, int bits) { return bits ? (
 // koff      : lane-dependent part of the twiddle index (position mod 2^u0, pre-shifted)
 // kstride   : twiddle-index stride of local bit 0
 template <int Q, bool INV>
-__device__ __forceinline__ void reg_stages(uint32_t (&x)[1 << Q], const uint32_t* __restrict__ tw, int u0, uint32_t koff,
-                                           uint32_t kstride, uint32_t ninv) {
+__device__ __forceinline__ void reg_stages(uint32_t (&x)[1 << Q], const uint2* __restrict__ tw, int u0, uint32_t koff,
+                                           uint32_t kstride, uint2 ninv) {
     if (INV) {
 #pragma unroll
         for (int s = Q - 1; s >= 0; s--) {
@@ -49,20 +49,20 @@ __device__ __forceinline__ void reg_stages(uint32_t (&x)[1 << Q], const uint32_t
 #pragma unroll
                 for (int e = 0; e < (1 << Q); e += 2) {
                     uint32_t a = x[e], b = x[e + 1];
-                    x[e] = bb::mul(bb::add(a, b), ninv);
-                    x[e + 1] = bb::mul(bb::sub(a, b), ninv);
+                    x[e] = bb::mul_shoup(a + b, ninv);
+                    x[e + 1] = bb::mul_shoup(a - b + bb::P, ninv);
                 }
             } else {
-                const uint32_t* t = tw + ((size_t)1 << (u0 + s)) + koff;
+                const uint2* t = tw + ((size_t)1 << (u0 + s)) + koff;
 #pragma unroll
                 for (int el = 0; el < (1 << s); el++) {
-                    const uint32_t w = __ldg(t + (size_t)el * kstride);
+                    const uint2 w = __ldg(t + (size_t)el * kstride);
 #pragma unroll
                     for (int eh = 0; eh < (1 << (Q - 1 - s)); eh++) {
                         const int e = (eh << (s + 1)) | el;
                         uint32_t a = x[e], b = x[e | (1 << s)];
                         x[e] = bb::add(a, b);
-                        x[e | (1 << s)] = bb::mul(bb::sub(a, b), w);
+                        x[e | (1 << s)] = bb::mul_shoup(a - b + bb::P, w);
                     }
                 }
             }
@@ -70,14 +70,14 @@ __device__ __forceinline__ void reg_stages(uint32_t (&x)[1 << Q], const uint32_t
     } else {
 #pragma unroll
         for (int s = 0; s < Q; s++) {
-            const uint32_t* t = tw + ((size_t)1 << (u0 + s)) + koff;
+            const uint2* t = tw + ((size_t)1 << (u0 + s)) + koff;
 #pragma unroll
             for (int el = 0; el < (1 << s); el++) {
-                const uint32_t w = __ldg(t + (size_t)el * kstride);
+                const uint2 w = __ldg(t + (size_t)el * kstride);
 #pragma unroll
                 for (int eh = 0; eh < (1 << (Q - 1 - s)); eh++) {
                     const int e = (eh << (s + 1)) | el;
-                    uint32_t a = x[e], m = bb::mul(x[e | (1 << s)], w);
+                    uint32_t a = x[e], m = bb::mul_shoup(x[e | (1 << s)], w);
                     x[e] = bb::add(a, m);
                     x[e | (1 << s)] = bb::sub(a, m);
                 }
@@ -94,8 +94,8 @@ __device__ __forceinline__ uint32_t sidx(uint32_t t, uint32_t j, int log_lc, int
 
 // One register round over the whole tile.  SRC/DST: 0 = shared memory, 1 = global memory through the address functor.
 template <int Q, bool INV, bool G_IN, bool G_OUT, typename AddrIn, typename AddrOut>
-__device__ __forceinline__ void tile_round(uint32_t* sm, int log_rows, int log_lc, int sshift, int b0, const uint32_t* __restrict__ tw,
-                                           int ubase, uint32_t lane_koff_mul, uint32_t ninv, AddrIn gin, AddrOut gout, uint32_t lanes_live) {
+__device__ __forceinline__ void tile_round(uint32_t* sm, int log_rows, int log_lc, int sshift, int b0, const uint2* __restrict__ tw,
+                                           int ubase, uint32_t lane_koff_mul, uint2 ninv, AddrIn gin, AddrOut gout, uint32_t lanes_live) {
     const uint32_t lc = 1u << log_lc;
     const uint32_t tasks = (1u << (log_rows - Q)) << log_lc;
     const uint32_t lowmask = (1u << b0) - 1;
@@ -123,8 +123,8 @@ __device__ __forceinline__ void tile_round(uint32_t* sm, int log_rows, int log_l
 }
 
 template <bool INV, bool G_IN, bool G_OUT, typename AddrIn, typename AddrOut>
-__device__ __forceinline__ void tile_round_q(int q, uint32_t* sm, int log_rows, int log_lc, int sshift, int b0, const uint32_t* tw,
-                                             int ubase, uint32_t lane_koff_mul, uint32_t ninv, AddrIn gin, AddrOut gout, uint32_t lanes_live) {
+__device__ __forceinline__ void tile_round_q(int q, uint32_t* sm, int log_rows, int log_lc, int sshift, int b0, const uint2* tw,
+                                             int ubase, uint32_t lane_koff_mul, uint2 ninv, AddrIn gin, AddrOut gout, uint32_t lanes_live) {
     switch (q) {
     case 5: tile_round<5, INV, G_IN, G_OUT>(sm, log_rows, log_lc, sshift, b0, tw, ubase, lane_koff_mul, ninv, gin, gout, lanes_live); break;
     case 4: tile_round<4, INV, G_IN, G_OUT>(sm, log_rows, log_lc, sshift, b0, tw, ubase, lane_koff_mul, ninv, gin, gout, lanes_live); break;
@@ -145,7 +145,7 @@ struct NoAddr {
 template <bool INV>
 __global__ void __launch_bounds__(THREADS) strided_pass_kernel(const uint32_t* __restrict__ src, size_t src_col_stride,
                                                                uint32_t* __restrict__ dst, size_t dst_col_stride, int n, int n_lo,
-                                                               int log_lc, int log_blowup, const uint32_t* __restrict__ tw_all,
+                                                               int log_lc, int log_blowup, const uint2* __restrict__ tw_all,
                                                                Rounds rounds) {
     extern __shared__ uint32_t sm[];
     const int n_hi = n - n_lo;
@@ -154,7 +154,7 @@ __global__ void __launch_bounds__(THREADS) strided_pass_kernel(const uint32_t* _
     const int cosets = INV ? 1 : (1 << log_blowup);
     const uint32_t* s = INV ? src + (size_t)blockIdx.y * src_col_stride : src + (((size_t)blockIdx.y * cosets + c) << n);
     // the lane part of a twiddle index is the position itself, j0 + j: fold j0 into the table pointer
-    const uint32_t* tw = tw_all + ((size_t)c << n) + j0;
+    const uint2* tw = tw_all + ((size_t)c << n) + j0;
     const int sshift = n_hi >= log_lc ? n_hi - log_lc : 0;
     auto gin = [&](uint32_t t, uint32_t j) -> uint32_t { return __ldg(s + ((size_t)t << n_lo) + j0 + j); };
     uint32_t* d1 = dst + (size_t)blockIdx.y * dst_col_stride;
@@ -162,10 +162,10 @@ __global__ void __launch_bounds__(THREADS) strided_pass_kernel(const uint32_t* _
     for (int r = 0; r < rounds.n; r++) {
         const bool first = r == 0, last = r == rounds.n - 1;
         const bool g_out = last && INV;               // K3 always finishes through shared memory (transposed store)
-        if (first && g_out) tile_round_q<INV, true, true>(rounds.q[r], sm, n_hi, log_lc, sshift, rounds.b0[r], tw, n_lo, 1u, 0u, gin, gout, 1u << log_lc);
-        else if (first) tile_round_q<INV, true, false>(rounds.q[r], sm, n_hi, log_lc, sshift, rounds.b0[r], tw, n_lo, 1u, 0u, gin, gout, 1u << log_lc);
-        else if (g_out) tile_round_q<INV, false, true>(rounds.q[r], sm, n_hi, log_lc, sshift, rounds.b0[r], tw, n_lo, 1u, 0u, gin, gout, 1u << log_lc);
-        else tile_round_q<INV, false, false>(rounds.q[r], sm, n_hi, log_lc, sshift, rounds.b0[r], tw, n_lo, 1u, 0u, gin, gout, 1u << log_lc);
+        if (first && g_out) tile_round_q<INV, true, true>(rounds.q[r], sm, n_hi, log_lc, sshift, rounds.b0[r], tw, n_lo, 1u, make_uint2(0u, 0u), gin, gout, 1u << log_lc);
+        else if (first) tile_round_q<INV, true, false>(rounds.q[r], sm, n_hi, log_lc, sshift, rounds.b0[r], tw, n_lo, 1u, make_uint2(0u, 0u), gin, gout, 1u << log_lc);
+        else if (g_out) tile_round_q<INV, false, true>(rounds.q[r], sm, n_hi, log_lc, sshift, rounds.b0[r], tw, n_lo, 1u, make_uint2(0u, 0u), gin, gout, 1u << log_lc);
+        else tile_round_q<INV, false, false>(rounds.q[r], sm, n_hi, log_lc, sshift, rounds.b0[r], tw, n_lo, 1u, make_uint2(0u, 0u), gin, gout, 1u << log_lc);
         __syncthreads();
     }
     if (!INV) {
@@ -186,8 +186,8 @@ __global__ void __launch_bounds__(THREADS) strided_pass_kernel(const uint32_t* _
 template <bool INV>
 __global__ void __launch_bounds__(THREADS) transposed_pass_kernel(const uint32_t* __restrict__ src, size_t src_col_stride,
                                                                   uint32_t* __restrict__ dst, int n, int n_lo, int log_lc,
-                                                                  int log_blowup, size_t total_blocks, const uint32_t* __restrict__ tw_all,
-                                                                  uint32_t ninv, Rounds rounds) {
+                                                                  int log_blowup, size_t total_blocks, const uint2* __restrict__ tw_all,
+                                                                  uint2 ninv, Rounds rounds) {
     extern __shared__ uint32_t sm[];
     const int c = INV ? 0 : (int)blockIdx.z;
     const int cosets = INV ? 1 : (1 << log_blowup);
@@ -195,7 +195,7 @@ __global__ void __launch_bounds__(THREADS) transposed_pass_kernel(const uint32_t
     const size_t b_first = (size_t)blockIdx.x << log_lc;
     const uint32_t live = (uint32_t)min((size_t)lc, total_blocks - b_first);
     const int log_bpc = n - n_lo;                                   // blocks per column
-    const uint32_t* tw = tw_all + ((size_t)c << n);
+    const uint2* tw = tw_all + ((size_t)c << n);
     // fill: consecutive threads read consecutive positions of one block (coalesced), scatter into [t][l] with the swizzle
     for (uint32_t e = threadIdx.x; e < tile; e += THREADS) {
         const uint32_t t = e & (rows - 1), l = e >> n_lo;

@@ -27,10 +27,12 @@ __device__ __forceinline__ uint32_t sidx(uint32_t t, uint32_t j) {
     return (t << LLC) + j;
 }
 
-// Q radix-2 stages in registers.  tw points at table entry [2^U0ish] -- see callers; KS = twiddle-index stride of local bit 0.
+// Q radix-2 stages in registers.  Twiddles are (w, w') pairs for Shoup's constant product (w canonical, w' = floor(w 2^32/p)):
+// IMAD.HI + 2 IMAD = 8 FMA-pipe cycles instead of 10, lazy [0,2p) operands accepted, data stays in Montgomery form.
+// KS = twiddle-index stride of local bit 0.
 template <int Q, bool INV, int KS>
-__device__ __forceinline__ void stages(uint32_t (&x)[1 << Q], const uint32_t* __restrict__ tw, int u0, uint32_t koff, bool last_inverse,
-                                       uint32_t ninv) {
+__device__ __forceinline__ void stages(uint32_t (&x)[1 << Q], const uint2* __restrict__ tw, int u0, uint32_t koff, bool last_inverse,
+                                       uint2 ninv) {
     if (INV) {
 #pragma unroll
         for (int s = Q - 1; s >= 0; s--) {
@@ -38,20 +40,20 @@ __device__ __forceinline__ void stages(uint32_t (&x)[1 << Q], const uint32_t* __
 #pragma unroll
                 for (int e = 0; e < (1 << Q); e += 2) {
                     uint32_t a = x[e], b = x[e + 1];
-                    x[e] = bb::mul(bb::add(a, b), ninv);
-                    x[e + 1] = bb::mul(bb::sub(a, b), ninv);
+                    x[e] = bb::mul_shoup(a + b, ninv);
+                    x[e + 1] = bb::mul_shoup(a - b + bb::P, ninv);
                 }
             } else {
-                const uint32_t* t = tw + ((size_t)1 << (u0 + s)) + koff;
+                const uint2* t = tw + ((size_t)1 << (u0 + s)) + koff;
 #pragma unroll
                 for (int el = 0; el < (1 << s); el++) {
-                    const uint32_t w = __ldg(t + (size_t)el * KS);
+                    const uint2 w = __ldg(t + (size_t)el * KS);
 #pragma unroll
                     for (int eh = 0; eh < (1 << (Q - 1 - s)); eh++) {
                         const int e = (eh << (s + 1)) | el;
                         uint32_t a = x[e], b = x[e | (1 << s)];
                         x[e] = bb::add(a, b);
-                        x[e | (1 << s)] = bb::mul(bb::sub(a, b), w);
+                        x[e | (1 << s)] = bb::mul_shoup(a - b + bb::P, w);      // lazy difference in (0, 2p)
                     }
                 }
             }
@@ -59,14 +61,14 @@ __device__ __forceinline__ void stages(uint32_t (&x)[1 << Q], const uint32_t* __
     } else {
 #pragma unroll
         for (int s = 0; s < Q; s++) {
-            const uint32_t* t = tw + ((size_t)1 << (u0 + s)) + koff;
+            const uint2* t = tw + ((size_t)1 << (u0 + s)) + koff;
 #pragma unroll
             for (int el = 0; el < (1 << s); el++) {
-                const uint32_t w = __ldg(t + (size_t)el * KS);
+                const uint2 w = __ldg(t + (size_t)el * KS);
 #pragma unroll
                 for (int eh = 0; eh < (1 << (Q - 1 - s)); eh++) {
                     const int e = (eh << (s + 1)) | el;
-                    uint32_t a = x[e], m = bb::mul(x[e | (1 << s)], w);
+                    uint32_t a = x[e], m = bb::mul_shoup(x[e | (1 << s)], w);
                     x[e] = bb::add(a, m);
                     x[e | (1 << s)] = bb::sub(a, m);
                 }
@@ -77,7 +79,7 @@ __device__ __forceinline__ void stages(uint32_t (&x)[1 << Q], const uint32_t* __
 
 // one register round over a [2^RB rows][2^LLC lanes] tile; UB = global bit index of row bit 0 (NLO strided, 0 transposed)
 template <int RB, int LLC, int Q, int B0, int UB, bool INV, int SWZ, bool LANE_K, bool G_IN, bool G_OUT>
-__device__ __forceinline__ void round_dev(uint32_t* __restrict__ sm, const uint32_t* __restrict__ tw, uint32_t ninv,
+__device__ __forceinline__ void round_dev(uint32_t* __restrict__ sm, const uint2* __restrict__ tw, uint2 ninv,
                                           const uint32_t* __restrict__ gsrc, uint32_t* __restrict__ gdst, uint32_t live) {
     constexpr uint32_t LC = 1u << LLC;
     constexpr uint32_t TASKS = (1u << (RB - Q)) << LLC;
@@ -107,7 +109,7 @@ __device__ __forceinline__ void round_dev(uint32_t* __restrict__ sm, const uint3
 
 // all rounds of a pass, unrolled at compile time in processing order (inverse: high bits first; forward: low bits first)
 template <int RB, int LLC, int UB, bool INV, int SWZ, bool LANE_K, bool G_FIRST, bool G_LAST, int I = 0>
-__device__ __forceinline__ void pass_rounds(uint32_t* sm, const uint32_t* tw, uint32_t ninv, const uint32_t* gsrc, uint32_t* gdst,
+__device__ __forceinline__ void pass_rounds(uint32_t* sm, const uint2* tw, uint2 ninv, const uint32_t* gsrc, uint32_t* gdst,
                                             uint32_t live) {
     constexpr int NR = n_rounds(RB);
     if constexpr (I < NR) {
@@ -123,7 +125,7 @@ __device__ __forceinline__ void pass_rounds(uint32_t* sm, const uint32_t* tw, ui
 template <int RB, int NLO, bool INV>
 __global__ void __launch_bounds__(THREADS) strided_kernel(const uint32_t* __restrict__ src, size_t src_col_stride,
                                                           uint32_t* __restrict__ dst, size_t dst_col_stride, int log_blowup,
-                                                          const uint32_t* __restrict__ tw_all) {
+                                                          const uint2* __restrict__ tw_all) {
     extern __shared__ uint32_t sm[];
     constexpr int LLC = log_lc_of(RB);
     constexpr int n = RB + NLO;
@@ -131,9 +133,9 @@ __global__ void __launch_bounds__(THREADS) strided_kernel(const uint32_t* __rest
     const int c = INV ? 0 : (int)blockIdx.z;
     const int cosets = INV ? 1 : (1 << log_blowup);
     const uint32_t* s = (INV ? src + (size_t)blockIdx.y * src_col_stride : src + (((size_t)blockIdx.y * cosets + c) << n)) + j0;
-    const uint32_t* tw = tw_all + ((size_t)c << n) + j0;      // lane part of the twiddle index is the position j0 + j
+    const uint2* tw = tw_all + ((size_t)c << n) + j0;         // lane part of the twiddle index is the position j0 + j
     uint32_t* d1 = dst + (size_t)blockIdx.y * dst_col_stride + j0;
-    pass_rounds<RB, LLC, NLO, INV, INV ? SWZ_NONE : SWZ_TOP, true, true, INV>(sm, tw, 0u, s, d1, 1u << LLC);
+    pass_rounds<RB, LLC, NLO, INV, INV ? SWZ_NONE : SWZ_TOP, true, true, INV>(sm, tw, make_uint2(0u, 0u), s, d1, 1u << LLC);
     if (!INV) {
         __syncthreads();
         // natural evaluation index k = j0 + j + (t << NLO) of coset c lands at row  bitrev_b(c)*N + bitrev_n(k)
@@ -152,7 +154,7 @@ __global__ void __launch_bounds__(THREADS) strided_kernel(const uint32_t* __rest
 template <int RB, bool INV>
 __global__ void __launch_bounds__(THREADS) transposed_kernel(const uint32_t* __restrict__ src, size_t src_col_stride,
                                                              uint32_t* __restrict__ dst, int n, int log_blowup, size_t total_blocks,
-                                                             const uint32_t* __restrict__ tw_all, uint32_t ninv) {
+                                                             const uint2* __restrict__ tw_all, uint2 ninv) {
     extern __shared__ uint32_t sm[];
     constexpr int LLC = log_lc_of(RB);
     constexpr uint32_t LC = 1u << LLC, ROWS = 1u << RB;
@@ -161,7 +163,7 @@ __global__ void __launch_bounds__(THREADS) transposed_kernel(const uint32_t* __r
     const size_t b_first = (size_t)blockIdx.x << LLC;
     const uint32_t live = (uint32_t)min((size_t)LC, total_blocks - b_first);
     const int log_bpc = n - RB;
-    const uint32_t* tw = tw_all + ((size_t)c << n);
+    const uint2* tw = tw_all + ((size_t)c << n);
     const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     for (uint32_t l = warp; l < live; l += THREADS / 32) {
         const size_t b = b_first + l, col = b >> log_bpc, blk = b & (((size_t)1 << log_bpc) - 1);
@@ -195,7 +197,7 @@ inline void ensure_smem() {
 }
 
 inline bool launch_strided(bool inv, int n_hi, int n_lo, dim3 grid, cudaStream_t st, const uint32_t* src, size_t src_col_stride,
-                           uint32_t* dst, size_t dst_col_stride, int log_blowup, const uint32_t* tw) {
+                           uint32_t* dst, size_t dst_col_stride, int log_blowup, const uint2* tw) {
 #define PB_CASE(RB, NLO)                                                                                                        \
     if (n_hi == RB && n_lo == NLO) {                                                                                            \
         const size_t smem = (size_t)4 << (RB + log_lc_of(RB));                                                                  \
@@ -214,7 +216,7 @@ inline bool launch_strided(bool inv, int n_hi, int n_lo, dim3 grid, cudaStream_t
 }
 
 inline bool launch_transposed(bool inv, int n, int n_lo, dim3 grid, cudaStream_t st, const uint32_t* src, size_t src_col_stride,
-                              uint32_t* dst, int log_blowup, size_t total_blocks, const uint32_t* tw, uint32_t ninv) {
+                              uint32_t* dst, int log_blowup, size_t total_blocks, const uint2* tw, uint2 ninv) {
 #define PB_CASE(RB)                                                                                                               \
     if (n_lo == RB) {                                                                                                             \
         const size_t smem = (size_t)4 << (RB + log_lc_of(RB));                                                                    \
