@@ -25,6 +25,11 @@ __global__ void __launch_bounds__(256) k(uint32_t* out, uint32_t seed) {
             if (KIND == 6) x[i] = __umulhi(x[i], y) + 3u;                              // IMAD.HI
             if (KIND == 7) { uint32_t t = bb::mul(x[(i + 1) % ILP], y); uint32_t a = x[i]; x[i] = bb::add(a, t); x[(i + 1) % ILP] = bb::sub(a, t); }  // butterfly
             if (KIND == 8) x[i] = bb::mul_lazy(x[i], y);                               // lazy mul (no correction)
+            if (KIND == 10) { uint32_t t = x[i] + 0x87ffffffu; x[i] = t < x[i] ? t : x[i]; x[i] += (uint32_t)it; }   // VIADDMNMX + IADD
+            if (KIND == 11) { x[i] = x[i] + x[(i + 1) % ILP] + y; y ^= x[i]; }                                        // IADD3 (3 regs) + LOP3
+            if (KIND == 12) { x[i] = bb::mul_shoup(x[i], make_uint2(y, 0x12345677u)); }                               // Shoup constant product
+            if (KIND == 13) { uint32_t a = x[i], b = x[(i + 1) % ILP]; x[i] = bb::add(a, b); x[(i + 1) % ILP] = bb::mul_shoup(a - b + bb::P, make_uint2(y, 0x12345677u)); }  // DIF butterfly
+            if (KIND == 14) { uint64_t t = (uint64_t)x[i] * y; x[i] = (uint32_t)t + (uint32_t)(t >> 32); }             // IMAD.WIDE + IADD
             if (KIND == 9) { x[i] = bb::mul(x[i], y); x[i] = bb::add(x[i], y); x[i] = bb::add(x[i], x[(i+1)%ILP]); x[i] = bb::add(x[i], 5u);}  // 1 mul : 3 add mix
         }
     }
@@ -65,5 +70,10 @@ int main() {
     run<4>("Montgomery mul, signed", 1);
     run<7>("radix-2 butterfly (mul+add+sub)", 1);
     run<9>("1 mul + 3 add mix", 4);
+    run<10>("VIADDMNMX + IADD", 1);
+    run<11>("IADD3 + LOP3", 1);
+    run<14>("IMAD.WIDE + IADD", 1);
+    run<12>("Shoup constant product", 1);
+    run<13>("DIF butterfly (Shoup, lazy diff)", 1);
     return 0;
 }
