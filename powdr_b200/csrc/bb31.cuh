@@ -30,10 +30,6 @@ BB_HD uint32_t sub(uint32_t a, uint32_t b) {
     uint32_t d = a - b, e = d + P;
     return e < d ? e : d;                   // a>=b: d<p<=e (no wrap) -> d ; a<b: d wraps high, e = d+P wraps low -> e
 }
-// modular add with the raw addition pinned to the ALU pipe (see smul); for FMA-bound code such as the Poseidon2 full rounds
-__device__ __forceinline__ uint32_t add_alu(uint32_t a, uint32_t b) {
-    return reduce_2p(__viaddmin_u32(a, b, 0xffffffffu));     // VIADDMNMX exists only on the ALU pipe
-}
 BB_HD uint32_t neg(uint32_t a) { return a ? P - a : 0u; }
 BB_HD uint32_t dbl(uint32_t a) { return reduce_2p(a + a); }
 
@@ -55,9 +51,7 @@ BB_HD int32_t smul(int32_t a, int32_t b) {
     asm("mul.wide.s32 %0, %1, %2;" : "=l"(t) : "r"(a), "r"(b));
     asm("mov.b64 {%0, %1}, %2;" : "=r"(lo), "=r"(hi) : "l"(t));
     int32_t m = (int32_t)((uint32_t)lo * PINV);
-    // min(hi - u, INT_MAX) pins the subtraction to the ALU pipe (VIADDMNMX): ptxas otherwise emits IMAD.IADD on the FMA pipe, which is the
-    // saturated one here (IMAD.WIDE / IMAD.HI are half rate on sm_100)
-    return __viaddmin_s32(hi, -__mulhi(m, (int32_t)P), 0x7fffffff);
+    return hi - __mulhi(m, (int32_t)P);
 #else
     int64_t t = (int64_t)a * (int64_t)b;
     int32_t m = (int32_t)((uint32_t)t * PINV);

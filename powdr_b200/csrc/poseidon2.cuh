@@ -22,7 +22,7 @@ struct Consts {
 __constant__ Consts c_p2;
 
 __device__ __forceinline__ uint32_t sbox_rc(uint32_t s, uint32_t rc_minus_p) {
-    int32_t x = __viaddmin_s32((int32_t)s, (int32_t)rc_minus_p, 0x7fffffff);   // s + (rc - p) in [-p, p), pinned to the ALU pipe
+    int32_t x = (int32_t)(s + rc_minus_p);          // [-p, p)
     int32_t x2 = bb::smul(x, x);
     int32_t x3 = bb::smul(x2, x);
     int32_t x4 = bb::smul(x2, x2);
@@ -34,24 +34,24 @@ __device__ __forceinline__ void external_linear(uint32_t (&s)[16]) {
 #pragma unroll
     for (int c = 0; c < 16; c += 4) {
         uint32_t x0 = s[c], x1 = s[c + 1], x2 = s[c + 2], x3 = s[c + 3];
-        uint32_t t01 = bb::add_alu(x0, x1), t23 = bb::add_alu(x2, x3);
-        uint32_t t0123 = bb::add_alu(t01, t23);
-        uint32_t t01123 = bb::add_alu(t0123, x1), t01233 = bb::add_alu(t0123, x3);
-        s[c + 3] = bb::add_alu(t01233, bb::add_alu(x0, x0));
-        s[c + 1] = bb::add_alu(t01123, bb::add_alu(x2, x2));
-        s[c] = bb::add_alu(t01123, t01);
-        s[c + 2] = bb::add_alu(t01233, t23);
+        uint32_t t01 = bb::add(x0, x1), t23 = bb::add(x2, x3);
+        uint32_t t0123 = bb::add(t01, t23);
+        uint32_t t01123 = bb::add(t0123, x1), t01233 = bb::add(t0123, x3);
+        s[c + 3] = bb::add(t01233, bb::dbl(x0));
+        s[c + 1] = bb::add(t01123, bb::dbl(x2));
+        s[c] = bb::add(t01123, t01);
+        s[c + 2] = bb::add(t01233, t23);
     }
-    uint32_t q0 = bb::add_alu(bb::add_alu(s[0], s[4]), bb::add_alu(s[8], s[12]));
-    uint32_t q1 = bb::add_alu(bb::add_alu(s[1], s[5]), bb::add_alu(s[9], s[13]));
-    uint32_t q2 = bb::add_alu(bb::add_alu(s[2], s[6]), bb::add_alu(s[10], s[14]));
-    uint32_t q3 = bb::add_alu(bb::add_alu(s[3], s[7]), bb::add_alu(s[11], s[15]));
+    uint32_t q0 = bb::add(bb::add(s[0], s[4]), bb::add(s[8], s[12]));
+    uint32_t q1 = bb::add(bb::add(s[1], s[5]), bb::add(s[9], s[13]));
+    uint32_t q2 = bb::add(bb::add(s[2], s[6]), bb::add(s[10], s[14]));
+    uint32_t q3 = bb::add(bb::add(s[3], s[7]), bb::add(s[11], s[15]));
 #pragma unroll
     for (int c = 0; c < 16; c += 4) {
-        s[c] = bb::add_alu(s[c], q0);
-        s[c + 1] = bb::add_alu(s[c + 1], q1);
-        s[c + 2] = bb::add_alu(s[c + 2], q2);
-        s[c + 3] = bb::add_alu(s[c + 3], q3);
+        s[c] = bb::add(s[c], q0);
+        s[c + 1] = bb::add(s[c + 1], q1);
+        s[c + 2] = bb::add(s[c + 2], q2);
+        s[c + 3] = bb::add(s[c + 3], q3);
     }
 }
 
