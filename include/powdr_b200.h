@@ -69,6 +69,11 @@ typedef struct { uint32_t off; uint32_t len; } pb_expr_span_t;   /* == ExprSpan,
 int pb_air_compile(pb_ctx_t* ctx, const uint32_t* bytecode, size_t n_words, const pb_expr_span_t* constraints,
                    size_t n_constraints, uint32_t width, pb_air_t** out);
 int pb_air_free(pb_air_t* air);
+/* 1 when the AIR runs on its NVRTC-generated straight-line kernel, 0 when on the bytecode interpreter kernel */
+int pb_air_is_jit(const pb_air_t* air);
+/* host-only check of the code generator: packs the program, generates CUDA C and compiles it for sm_100a (no device needed) */
+int pb_air_jit_compile_only(const uint32_t* bytecode, size_t n_words, const pb_expr_span_t* constraints, size_t n_constraints,
+                            uint32_t width, size_t* cubin_bytes);
 /* d_quotient: [2 chunks][4 limbs][2^log_n], chunk = parity of the natural LDE index (= top bit of the bit-reversed row),
  * rows inside a chunk in bit-reversed order.  log_blowup must be 1 (constraint degree <= 3, openvm/src/lib.rs:97-101). */
 int pb_quotient(pb_ctx_t* ctx, const pb_air_t* air, const uint32_t* d_lde, size_t log_n, uint32_t log_blowup, uint32_t shift,

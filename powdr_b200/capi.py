@@ -14,7 +14,7 @@ LIB_PATH = os.path.join(_HERE, "_lib", "libpowdr_b200.so")
 EXPORTS = [
     "pb_ctx_create", "pb_ctx_destroy", "pb_ctx_synchronize", "pb_ctx_set_poseidon2", "pb_host_alloc", "pb_host_free",
     "pb_device_alloc", "pb_device_free", "pb_copy_h2d", "pb_copy_d2h", "pb_memset_zero", "pb_to_monty", "pb_from_monty",
-    "pb_lde_batch", "pb_air_compile", "pb_air_free", "pb_quotient", "pb_constraint_fold", "pb_merkle_commit",
+    "pb_lde_batch", "pb_air_compile", "pb_air_free", "pb_air_is_jit", "pb_air_jit_compile_only", "pb_quotient", "pb_constraint_fold", "pb_merkle_commit",
     "pb_merkle_commit_rows8", "pb_poseidon2_permute", "pb_fri_fold", "pb_prove_segment", "pb_last_stage_ms",
     "pb_launch_count", "pb_leaf_kernel_profile", "_apc_tracegen", "_apc_apply_derived_expr", "_apc_apply_bus",
 ]
@@ -144,6 +144,10 @@ class Air:
         _chk(ctx.lib.pb_air_compile(ctx.h, bc.ctypes.data_as(C.c_void_p), C.c_size_t(bc.size), sp, C.c_size_t(len(spans)),
                                     C.c_uint32(width), C.byref(h)), "pb_air_compile")
         self.h = h
+
+    @property
+    def is_jit(self):
+        return bool(self.ctx.lib.pb_air_is_jit(self.h))
 
     def free(self):
         if self.h:

@@ -1,0 +1,223 @@
+// Per-AIR code generation for stage 2.  The bytecode interpreter (air.cuh) spends ~28 instructions per expression node
+// (ncu r01: 143 k instructions per LDE row for the keccak-shaped AIR, 20 % of the HBM roof).  An autoprecompile's constraint
+// set is fixed at key-generation time, so pb_air_compile turns the packed program into straight-line CUDA C -- one SSA value
+// per node, constants folded into Shoup products, constraints grouped into small __noinline__ functions to keep ptxas
+// basic blocks short -- and compiles it with NVRTC for sm_100a.  NVRTC and the driver API are dlopen'ed lazily so the
+// library itself links against nothing but cudart; when either is missing, or PB_AIR_NO_JIT is set, the interpreter
+// kernel (still CUDA) is used instead.
+#pragma once
+#include <cuda.h>
+#include <dlfcn.h>
+#include <nvrtc.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <stdlib.h>
+#include <string>
+#include <vector>
+
+#include "air.cuh"
+#include "bb31.cuh"
+
+namespace airjit {
+
+struct Api {
+    bool tried = false, ok = false /* nvrtc + driver */, nvrtc_ok = false;
+    nvrtcResult (*CreateProgram)(nvrtcProgram*, const char*, const char*, int, const char* const*, const char* const*) = nullptr;
+    nvrtcResult (*CompileProgram)(nvrtcProgram, int, const char* const*) = nullptr;
+    nvrtcResult (*GetCUBINSize)(nvrtcProgram, size_t*) = nullptr;
+    nvrtcResult (*GetCUBIN)(nvrtcProgram, char*) = nullptr;
+    nvrtcResult (*GetProgramLogSize)(nvrtcProgram, size_t*) = nullptr;
+    nvrtcResult (*GetProgramLog)(nvrtcProgram, char*) = nullptr;
+    nvrtcResult (*DestroyProgram)(nvrtcProgram*) = nullptr;
+    CUresult (*ModuleLoadData)(CUmodule*, const void*) = nullptr;
+    CUresult (*ModuleGetFunction)(CUfunction*, CUmodule, const char*) = nullptr;
+    CUresult (*ModuleUnload)(CUmodule) = nullptr;
+    CUresult (*LaunchKernel)(CUfunction, unsigned, unsigned, unsigned, unsigned, unsigned, unsigned, unsigned, CUstream, void**, void**) = nullptr;
+};
+
+inline Api& api() {
+    static Api a;
+    if (a.tried) return a;
+    a.tried = true;
+    void* hn = nullptr;
+    for (const char* n : {"libnvrtc.so.12", "libnvrtc.so", "/usr/local/cuda/lib64/libnvrtc.so.12", "/usr/local/cuda/lib64/libnvrtc.so"})
+        if ((hn = dlopen(n, RTLD_NOW | RTLD_GLOBAL))) break;
+    void* hc = dlopen("libcuda.so.1", RTLD_NOW | RTLD_GLOBAL);
+    if (!hn) return a;
+#define PB_SYM(field, handle, name) *(void**)(&a.field) = dlsym(handle, name); if (!a.field) return a;
+    PB_SYM(CreateProgram, hn, "nvrtcCreateProgram") PB_SYM(CompileProgram, hn, "nvrtcCompileProgram")
+    PB_SYM(GetCUBINSize, hn, "nvrtcGetCUBINSize") PB_SYM(GetCUBIN, hn, "nvrtcGetCUBIN")
+    PB_SYM(GetProgramLogSize, hn, "nvrtcGetProgramLogSize") PB_SYM(GetProgramLog, hn, "nvrtcGetProgramLog")
+    PB_SYM(DestroyProgram, hn, "nvrtcDestroyProgram")
+    a.nvrtc_ok = true;
+    if (!hc) return a;
+    PB_SYM(ModuleLoadData, hc, "cuModuleLoadData") PB_SYM(ModuleGetFunction, hc, "cuModuleGetFunction")
+    PB_SYM(ModuleUnload, hc, "cuModuleUnload") PB_SYM(LaunchKernel, hc, "cuLaunchKernel")
+#undef PB_SYM
+    a.ok = true;
+    return a;
+}
+
+struct Kernel {
+    CUmodule mod = nullptr;
+    CUfunction fn = nullptr;
+};
+
+static const char* PRELUDE = R"(
+typedef unsigned int u32; typedef unsigned long long u64;
+#define P 0x78000001u
+__device__ __forceinline__ u32 red(u32 x) { u32 y = x - P; return y < x ? y : x; }
+__device__ __forceinline__ u32 add(u32 a, u32 b) { return red(a + b); }
+__device__ __forceinline__ u32 sub(u32 a, u32 b) { u32 d = a - b, e = d + P; return e < d ? e : d; }
+__device__ __forceinline__ u32 neg(u32 a) { return a ? P - a : 0u; }
+__device__ __forceinline__ u32 mul(u32 a, u32 b) { u64 t = (u64)a * b; u32 m = (u32)t * 0x77ffffffu; u64 d = (u64)m * P + t; return red((u32)(d >> 32)); }
+__device__ __forceinline__ u32 mulc(u32 a, u32 w, u32 wp) { u32 q = __umulhi(a, wp); return red(a * w - q * P); }
+__device__ __noinline__ u32 inv(u32 a) { u32 r = 0x0ffffffeu; u32 e = P - 2; while (e) { if (e & 1) r = mul(r, a); a = mul(a, a); e >>= 1; } return r; }
+__device__ __forceinline__ uint4 fold(uint4 acc, u32 c, uint4 w) {
+    acc.x = add(acc.x, mul(c, w.x)); acc.y = add(acc.y, mul(c, w.y)); acc.z = add(acc.z, mul(c, w.z)); acc.w = add(acc.w, mul(c, w.w)); return acc; }
+)";
+
+// packed program (air.cuh encoding) -> CUDA C.  Literals stay symbolic so constant operands become Shoup products.
+inline std::string generate(const std::vector<uint32_t>& code, const std::vector<air::Span>& spans, const std::vector<uint32_t>& pool) {
+    std::string src = PRELUDE;
+    struct Val { bool lit; uint32_t mont; std::string name; };
+    char buf[256];
+    const size_t GROUP_OPS = 600;
+    size_t k = 0, n_groups = 0, vid = 0;
+    while (k < spans.size()) {
+        snprintf(buf, sizeof buf, "__device__ __noinline__ uint4 g%zu(const u32* __restrict__ b, u64 m, const uint4* __restrict__ ap, uint4 acc) {\n", n_groups);
+        src += buf;
+        size_t ops = 0;
+        while (k < spans.size() && (ops == 0 || ops + spans[k].len <= GROUP_OPS)) {
+            std::vector<Val> st;
+            for (uint32_t ip = spans[k].off; ip < spans[k].off + spans[k].len; ip++) {
+                const uint32_t w = code[ip], op = w >> 28, arg = w & 0x0fffffffu;
+                auto lit_str = [&](const Val& v) { snprintf(buf, sizeof buf, "0x%08xu", v.mont); return std::string(buf); };
+                auto as_str = [&](const Val& v) { return v.lit ? lit_str(v) : v.name; };
+                auto fresh = [&]() { snprintf(buf, sizeof buf, "v%zu", vid++); return std::string(buf); };
+                if (op == air::OP_PUSH_APC) {
+                    Val v{false, 0, fresh()};
+                    snprintf(buf, sizeof buf, " u32 %s = __ldg(b + %uull * m);\n", v.name.c_str(), arg);
+                    src += buf;
+                    st.push_back(v);
+                } else if (op == air::OP_PUSH_CONST) {
+                    st.push_back(Val{true, pool[arg], ""});
+                } else if (op == air::OP_ADD || op == air::OP_SUB || op == air::OP_MUL) {
+                    Val bb_ = st.back(); st.pop_back();
+                    Val aa = st.back(); st.pop_back();
+                    if (aa.lit && bb_.lit) {
+                        uint32_t r = op == air::OP_ADD ? bb::add(aa.mont, bb_.mont) : op == air::OP_SUB ? bb::sub(aa.mont, bb_.mont) : bb::mul(aa.mont, bb_.mont);
+                        st.push_back(Val{true, r, ""});
+                    } else {
+                        Val v{false, 0, fresh()};
+                        if (op == air::OP_MUL && (aa.lit || bb_.lit)) {
+                            const Val& c = aa.lit ? aa : bb_;
+                            const Val& x = aa.lit ? bb_ : aa;
+                            const uint32_t wc = bb::from_monty(c.mont);
+                            snprintf(buf, sizeof buf, " u32 %s = mulc(%s, 0x%08xu, 0x%08xu);\n", v.name.c_str(), x.name.c_str(), wc,
+                                     (uint32_t)(((uint64_t)wc << 32) / bb::P));
+                        } else {
+                            snprintf(buf, sizeof buf, " u32 %s = %s(%s, %s);\n", v.name.c_str(), op == air::OP_ADD ? "add" : op == air::OP_SUB ? "sub" : "mul",
+                                     as_str(aa).c_str(), as_str(bb_).c_str());
+                        }
+                        src += buf;
+                        st.push_back(v);
+                    }
+                } else {
+                    Val aa = st.back(); st.pop_back();
+                    if (aa.lit) {
+                        st.push_back(Val{true, op == air::OP_NEG ? bb::neg(aa.mont) : bb::inv(aa.mont), ""});
+                    } else {
+                        Val v{false, 0, fresh()};
+                        snprintf(buf, sizeof buf, " u32 %s = %s(%s);\n", v.name.c_str(), op == air::OP_NEG ? "neg" : "inv", aa.name.c_str());
+                        src += buf;
+                        st.push_back(v);
+                    }
+                }
+            }
+            const Val& c = st.back();
+            char lit[16];
+            snprintf(lit, sizeof lit, "0x%08xu", c.mont);
+            snprintf(buf, sizeof buf, " acc = fold(acc, %s, __ldg(ap + %zu));\n", c.lit ? lit : c.name.c_str(), k);
+            src += buf;
+            ops += spans[k].len;
+            k++;
+        }
+        src += " return acc;\n}\n";
+        n_groups++;
+    }
+    src += R"(
+extern "C" __global__ void __launch_bounds__(256) pbq(const u32* __restrict__ mat, u64 m, int log_n, const uint4* __restrict__ ap,
+                                                       u32 zinv0, u32 zinv1, u32* __restrict__ out, int apply_zinv) {
+    const u64 r = (u64)blockIdx.x * 256ull + threadIdx.x;
+    if (r >= m) return;
+    const u32* b = mat + r;
+    uint4 acc = make_uint4(0u, 0u, 0u, 0u);
+)";
+    for (size_t g = 0; g < n_groups; g++) {
+        snprintf(buf, sizeof buf, "    acc = g%zu(b, m, ap, acc);\n", g);
+        src += buf;
+    }
+    src += R"(
+    if (apply_zinv) {
+        const u64 n = 1ull << log_n, chunk = r >> log_n, j = r & (n - 1);
+        const u32 z = chunk ? zinv1 : zinv0;
+        out[(chunk * 4 + 0) * n + j] = mul(acc.x, z); out[(chunk * 4 + 1) * n + j] = mul(acc.y, z);
+        out[(chunk * 4 + 2) * n + j] = mul(acc.z, z); out[(chunk * 4 + 3) * n + j] = mul(acc.w, z);
+    } else {
+        out[r] = acc.x; out[m + r] = acc.y; out[2 * m + r] = acc.z; out[3 * m + r] = acc.w;
+    }
+}
+)";
+    return src;
+}
+
+// returns 0 and fills `out` on success; non-zero when the JIT path is unavailable (caller keeps the interpreter)
+inline int build(const std::vector<uint32_t>& code, const std::vector<air::Span>& spans, const std::vector<uint32_t>& pool, Kernel* out,
+                 std::vector<char>* cubin_out = nullptr) {
+    if (getenv("PB_AIR_NO_JIT")) return 1;
+    if (code.size() > 400000) return 2;                        // keep compile time bounded; huge AIRs stay on the interpreter
+    Api& a = api();
+    if (!a.nvrtc_ok || (out && !a.ok)) return 3;
+    const std::string src = generate(code, spans, pool);
+    nvrtcProgram prog;
+    if (a.CreateProgram(&prog, src.c_str(), "pb_air.cu", 0, nullptr, nullptr) != NVRTC_SUCCESS) return 4;
+    const char* opts[] = {"--gpu-architecture=sm_100a", "-std=c++17", "-lineinfo"};
+    nvrtcResult rc = a.CompileProgram(prog, 3, opts);
+    if (rc != NVRTC_SUCCESS) {
+        if (getenv("PB_AIR_JIT_VERBOSE")) {
+            size_t ls = 0;
+            a.GetProgramLogSize(prog, &ls);
+            std::vector<char> log(ls + 1, 0);
+            a.GetProgramLog(prog, log.data());
+            fprintf(stderr, "[powdr_b200] NVRTC failed (%d):\n%s\n", (int)rc, log.data());
+        }
+        a.DestroyProgram(&prog);
+        return 5;
+    }
+    size_t sz = 0;
+    a.GetCUBINSize(prog, &sz);
+    std::vector<char> cubin(sz);
+    a.GetCUBIN(prog, cubin.data());
+    a.DestroyProgram(&prog);
+    if (cubin_out) *cubin_out = cubin;
+    if (!out) return 0;
+    if (a.ModuleLoadData(&out->mod, cubin.data()) != CUDA_SUCCESS) return 6;
+    if (a.ModuleGetFunction(&out->fn, out->mod, "pbq") != CUDA_SUCCESS) { a.ModuleUnload(out->mod); out->mod = nullptr; return 7; }
+    return 0;
+}
+
+inline int launch(const Kernel& k, cudaStream_t st, const uint32_t* mat, unsigned long long m, int log_n, const uint32_t* ap, uint32_t zinv0,
+                  uint32_t zinv1, uint32_t* out, int apply_zinv) {
+    void* args[] = {(void*)&mat, (void*)&m, (void*)&log_n, (void*)&ap, (void*)&zinv0, (void*)&zinv1, (void*)&out, (void*)&apply_zinv};
+    CUresult rc = api().LaunchKernel(k.fn, (unsigned)((m + 255) / 256), 1, 1, 256, 1, 1, 0, (CUstream)st, args, nullptr);
+    return rc == CUDA_SUCCESS ? 0 : 700 + (int)rc;
+}
+
+inline void destroy(Kernel& k) {
+    if (k.mod) api().ModuleUnload(k.mod);
+    k.mod = nullptr;
+    k.fn = nullptr;
+}
+
+}  // namespace airjit

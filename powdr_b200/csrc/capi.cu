@@ -14,6 +14,7 @@
 #include "../../include/pb_poseidon2_constants.h"
 #include "../../include/powdr_b200.h"
 #include "air.cuh"
+#include "air_jit.cuh"
 #include "bb31.cuh"
 #include "fri.cuh"
 #include "ntt.cuh"
@@ -150,6 +151,8 @@ struct pb_air {
     uint32_t* d_pool = nullptr;
     uint32_t* d_alpha_pows = nullptr;   // [C][4]
     size_t n_code = 0, n_pool = 0;
+    airjit::Kernel jit;                 // NVRTC-compiled straight-line evaluator of this AIR
+    bool jit_ok = false;
 };
 
 struct pb_ctx {
@@ -470,11 +473,9 @@ int pb_lde_batch(pb_ctx_t* ctx, const uint32_t* d_trace, size_t log_n, size_t wi
 }
 
 // ---------------------------------------------------------------------------------------------------------------------
-int pb_air_compile(pb_ctx_t* ctx, const uint32_t* bc, size_t n_words, const pb_expr_span_t* cons, size_t n_constraints,
-                   uint32_t width, pb_air_t** out) {
-    if (!ctx || !out || (!bc && n_words) || (!cons && n_constraints)) return PB_ERR_INVALID_ARG;
-    std::vector<uint32_t> code, pool;
-    std::vector<air::Span> spans;
+// reference-format bytecode -> validated, packed program (one word per instruction + Montgomery constant pool)
+static int pack_program(const uint32_t* bc, size_t n_words, const pb_expr_span_t* cons, size_t n_constraints, uint32_t width,
+                        std::vector<uint32_t>& code, std::vector<uint32_t>& pool, std::vector<air::Span>& spans) {
     std::unordered_map<uint32_t, uint32_t> pool_idx;
     for (size_t k = 0; k < n_constraints; k++) {
         const size_t off = cons[k].off, len = cons[k].len;
@@ -513,6 +514,31 @@ int pb_air_compile(pb_ctx_t* ctx, const uint32_t* bc, size_t n_words, const pb_e
         sp.len = (uint32_t)code.size() - sp.off;
         spans.push_back(sp);
     }
+    return 0;
+}
+
+int pb_air_jit_compile_only(const uint32_t* bc, size_t n_words, const pb_expr_span_t* cons, size_t n_constraints, uint32_t width,
+                            size_t* cubin_bytes) {
+    if ((!bc && n_words) || (!cons && n_constraints)) return PB_ERR_INVALID_ARG;
+    std::vector<uint32_t> code, pool;
+    std::vector<air::Span> spans;
+    int rc = pack_program(bc, n_words, cons, n_constraints, width, code, pool, spans);
+    if (rc) return rc;
+    std::vector<char> cubin;
+    rc = airjit::build(code, spans, pool, nullptr, &cubin);
+    if (cubin_bytes) *cubin_bytes = cubin.size();
+    return rc ? PB_ERR_UNSUPPORTED : 0;
+}
+
+int pb_air_compile(pb_ctx_t* ctx, const uint32_t* bc, size_t n_words, const pb_expr_span_t* cons, size_t n_constraints,
+                   uint32_t width, pb_air_t** out) {
+    if (!ctx || !out || (!bc && n_words) || (!cons && n_constraints)) return PB_ERR_INVALID_ARG;
+    std::vector<uint32_t> code, pool;
+    std::vector<air::Span> spans;
+    {
+        int prc = pack_program(bc, n_words, cons, n_constraints, width, code, pool, spans);
+        if (prc) return prc;
+    }
     pb_air* a = new pb_air();
     a->width = width;
     a->n_constraints = (uint32_t)n_constraints;
@@ -526,12 +552,16 @@ int pb_air_compile(pb_ctx_t* ctx, const uint32_t* bc, size_t n_words, const pb_e
     CK(cudaMemcpyAsync(a->d_spans, spans.data(), spans.size() * sizeof(air::Span), cudaMemcpyHostToDevice, ctx->stream));
     CK(cudaMemcpyAsync(a->d_pool, pool.data(), pool.size() * 4, cudaMemcpyHostToDevice, ctx->stream));
     CK(cudaStreamSynchronize(ctx->stream));
+    a->jit_ok = n_constraints > 0 && airjit::build(code, spans, pool, &a->jit) == 0;   // straight-line per-AIR kernel (air_jit.cuh)
     *out = a;
     return 0;
 }
 
+int pb_air_is_jit(const pb_air_t* a) { return a && a->jit_ok ? 1 : 0; }
+
 int pb_air_free(pb_air_t* a) {
     if (!a) return 0;
+    if (a->jit_ok) airjit::destroy(a->jit);
     cudaFree(a->d_code); cudaFree(a->d_spans); cudaFree(a->d_pool); cudaFree(a->d_alpha_pows);
     delete a;
     return 0;
@@ -558,6 +588,11 @@ int pb_quotient(pb_ctx_t* ctx, const pb_air_t* a, const uint32_t* d_lde, size_t 
     const uint32_t sn = bb::pow(h_to_m(shift), (uint64_t)1 << log_n);
     const uint32_t zinv0 = bb::inv(bb::sub(sn, bb::R1)), zinv1 = bb::inv(bb::sub(bb::neg(sn), bb::R1));
     const size_t m = (size_t)2 << log_n;
+    if (a->jit_ok) {
+        rc = airjit::launch(a->jit, ctx->stream, d_lde, m, (int)log_n, a->d_alpha_pows, zinv0, zinv1, d_q, 1);
+        LAUNCHED(ctx);
+        return rc;
+    }
     air::quotient_kernel<<<(unsigned)((m + air::THREADS - 1) / air::THREADS), air::THREADS, 0, ctx->stream>>>(
         a->d_code, a->d_spans, a->n_constraints, a->d_pool, d_lde, (int)log_n, a->d_alpha_pows, zinv0, zinv1, d_q, 1);
     LAUNCHED(ctx);
@@ -570,6 +605,11 @@ int pb_constraint_fold(pb_ctx_t* ctx, const pb_air_t* a, const uint32_t* d_mat, 
     if (!height) return 0;
     int rc = upload_alpha_pows(ctx, a, h_e4_from_canon(alpha));
     if (rc) return rc;
+    if (a->jit_ok) {
+        rc = airjit::launch(a->jit, ctx->stream, d_mat, height, 0, a->d_alpha_pows, 0u, 0u, d_out, 0);
+        LAUNCHED(ctx);
+        return rc;
+    }
     air::constraint_fold_kernel<<<(unsigned)((height + air::THREADS - 1) / air::THREADS), air::THREADS, 0, ctx->stream>>>(
         a->d_code, a->d_spans, a->n_constraints, a->d_pool, d_mat, height, a->d_alpha_pows, d_out);
     LAUNCHED(ctx);

@@ -279,3 +279,32 @@ def test_satisfying_trace_gives_low_degree_quotient(ctx):
     got = ctx.prove_segment(air, d.ptr, log_n, mach.width, on_device=True)
     assert all(v == [0, 0, 0, 0] for v in got["final_poly"])
     assert got["n_fri_layers"] == log_n
+
+
+# ---------------------------------------------------------------- stage 2: generated kernel vs interpreter kernel
+def test_air_jit_and_interpreter_agree_with_oracle(ctx, orc, monkeypatch):
+    """the NVRTC-generated straight-line evaluator and the bytecode interpreter kernel are both CUDA paths of stage 2;
+    both must match the oracle on the reference fixture (incl. an INV_OR_ZERO expression)"""
+    m = _machine()
+    mach = m.SymbolicMachine.from_json_file(os.path.join(GOLDEN, "wasm_register_reuse.machine.json"))
+    bc, spans = m.compile_constraints(mach)
+    bc = bc + [0, 0, 6, 0, 1, 4]                 # extra constraint: inv_or_zero(col0) * col1
+    spans = spans + [(len(bc) - 6, 6)]
+    rng = np.random.default_rng(53)
+    log_n = 9
+    lde = rand_field(rng, (mach.width, 2 << log_n))
+    lde[0, :5] = 0
+    alpha = rand_field(rng, 4)
+    exp = orc.quotient(bc, spans, lde, log_n, alpha)
+    d = ctx.to_device(lde)
+    d_q = ctx.alloc(4 * 8 << log_n)
+    air_jit = ctx.air(bc, spans, mach.width)
+    assert air_jit.is_jit
+    ctx.quotient(air_jit, d.ptr, log_n, alpha, d_q.ptr)
+    assert (ctx.to_host(d_q, (2, 4, 1 << log_n)) == exp).all()
+    monkeypatch.setenv("PB_AIR_NO_JIT", "1")
+    air_int = ctx.air(bc, spans, mach.width)
+    assert not air_int.is_jit
+    d_q.zero()
+    ctx.quotient(air_int, d.ptr, log_n, alpha, d_q.ptr)
+    assert (ctx.to_host(d_q, (2, 4, 1 << log_n)) == exp).all()

@@ -86,3 +86,26 @@ def test_synthetic_machine_shape():
     mach = M.synthetic_machine(2022, 187, seed=1)
     assert mach.width == 2022 and len(mach.constraints) == 187
     assert max(M.degree(c) for c in mach.constraints) == 3
+
+
+def test_jit_codegen_compiles_for_sm100a_without_a_device():
+    """pb_air_jit_compile_only: pack the reference fixture's constraints, generate CUDA C, NVRTC-compile for sm_100a"""
+    import ctypes as C
+    import powdr_b200
+    from powdr_b200 import machine as M
+    from powdr_b200.capi import Span
+    lib = powdr_b200.load_library()
+    mach = M.SymbolicMachine.from_json_file(os.path.join(GOLDEN, "single_div_nondet.machine.json"))
+    bc, spans = M.compile_constraints(mach)
+    b = np.array(bc, dtype=np.uint32)
+    sp = (Span * len(spans))()
+    for i, (o, l) in enumerate(spans):
+        sp[i].off, sp[i].len = o, l
+    sz = C.c_size_t()
+    rc = lib.pb_air_jit_compile_only(b.ctypes.data_as(C.c_void_p), C.c_size_t(b.size), sp, C.c_size_t(len(spans)), C.c_uint32(mach.width), C.byref(sz))
+    assert rc == 0 and sz.value > 1000
+    # malformed program is rejected before any code generation
+    bad = np.array([0, 99], dtype=np.uint32)
+    sp1 = (Span * 1)()
+    sp1[0].off, sp1[0].len = 0, 2
+    assert lib.pb_air_jit_compile_only(bad.ctypes.data_as(C.c_void_p), C.c_size_t(2), sp1, C.c_size_t(1), C.c_uint32(3), C.byref(sz)) == -4
