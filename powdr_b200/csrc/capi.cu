@@ -401,8 +401,11 @@ int pb_lde_batch(pb_ctx_t* ctx, const uint32_t* d_trace, size_t log_n, size_t wi
     if (rc) return rc;
     const int n_lo = n <= 10 ? n : (n + 1) / 2;
     const int n_hi = n - n_lo;
-    const int log_lc_hi = std::min(5, ntt::LOG_TILE_MAX - n_hi);          // K1/K3 tile: 2^n_hi rows x 2^log_lc_hi lanes
-    const int log_lc_lo = std::min(5, ntt::LOG_TILE_MAX - n_lo);          // K2 tile:    2^n_lo rows x 2^log_lc_lo blocks
+    const bool use_fast = getenv("PB_LDE_GENERIC") == nullptr;     // compile-time specialised passes (ntt_fast.cuh) when available
+    const bool fast_geom = use_fast && nttf::supported(n_hi, n_lo);
+    // K1/K3 tile: 2^n_hi rows x 2^log_lc_hi lanes;  K2 tile: 2^n_lo rows x 2^log_lc_lo blocks
+    const int log_lc_hi = fast_geom ? nttf::log_lc_of(n_hi) : std::min(5, ntt::LOG_TILE_MAX - n_hi);
+    const int log_lc_lo = fast_geom ? nttf::log_lc_of(n_lo) : std::min(5, ntt::LOG_TILE_MAX - n_lo);
     auto make_rounds = [](int bits, bool descending) {
         ntt::Rounds r{};
         const int nr = (bits + 4) / 5;
@@ -428,11 +431,10 @@ int pb_lde_batch(pb_ctx_t* ctx, const uint32_t* d_trace, size_t log_n, size_t wi
     const size_t smem_lo = (size_t)4 << (n_lo + log_lc_lo);
     const ntt::Rounds r_inv_hi = make_rounds(n_hi, true), r_fwd_hi = make_rounds(n_hi, false);
     const ntt::Rounds r_inv_lo = make_rounds(n_lo, true), r_fwd_lo = make_rounds(n_lo, false);
-    const bool use_fast = getenv("PB_LDE_GENERIC") == nullptr;     // compile-time specialised passes (ntt_fast.cuh) when available
     for (size_t c0 = 0; c0 < width; c0 += batch) {
         const unsigned nb = (unsigned)std::min(batch, width - c0);
         const uint32_t* src = d_trace + c0 * N;
-        const bool fast = use_fast && nttf::supported(n_hi, n_lo);
+        const bool fast = fast_geom;
         if (n_hi > 0) {
             dim3 g1((unsigned)(1u << (n_lo - log_lc_hi)), nb);
             if (!fast || !nttf::launch_strided(true, n_hi, n_lo, g1, ctx->stream, src, N, ctx->tmp.p, N, (int)log_blowup, tw->d_inv))

@@ -10,9 +10,13 @@
 namespace nttf {
 
 using ntt::brev;
-constexpr int THREADS = 512;
+// 256-thread CTAs on 64 KB tiles: two or three CTAs are co-resident per SM, so the load phase of one overlaps the butterfly
+// phase of another (ncu r01b: one 512-thread / 128 KB CTA per SM kept issue utilisation at 40-60 % -- all 16 warps wait on the
+// same barrier-separated phases).  Rows of 16 lanes are still 64-byte coalesced segments.
+constexpr int THREADS = 256;
+constexpr int LOG_TILE = 14;
 
-__host__ __device__ constexpr int log_lc_of(int rb) { return rb <= 10 ? 5 : 15 - rb; }
+__host__ __device__ constexpr int log_lc_of(int rb) { return rb <= LOG_TILE - 4 ? 4 : LOG_TILE - rb; }
 __host__ __device__ constexpr int n_rounds(int rb) { return (rb + 4) / 5; }
 __host__ __device__ constexpr int q_of(int rb, int i) { return rb / n_rounds(rb) + (i < rb % n_rounds(rb) ? 1 : 0); }
 __host__ __device__ constexpr int b0_of(int rb, int i) { return i == 0 ? 0 : b0_of(rb, i - 1) + q_of(rb, i - 1); }
@@ -191,7 +195,7 @@ template <auto Kernel>
 inline void ensure_smem() {
     static bool done = false;
     if (!done) {
-        cudaFuncSetAttribute(Kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 4 << ntt::LOG_TILE_MAX);
+        cudaFuncSetAttribute(Kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 4 << LOG_TILE);
         done = true;
     }
 }
