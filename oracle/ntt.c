@@ -90,7 +90,7 @@ void orc_fri_fold(const uint32_t* in, unsigned log_len, uint32_t shift, const ui
     uint32_t w = bb_root_of_unity(log_len);
     uint32_t two_inv = bb_inv(2);
     bb4_t b = {{beta[0], beta[1], beta[2], beta[3]}};
-#pragma omp parallel for schedule(static)
+#pragma omp parallel for schedule(static) if (half >= 4096)
     for (long j = 0; j < (long)half; j++) {
         bb4_t lo, hi;
         memcpy(lo.c, in + 8 * (size_t)j, 16);

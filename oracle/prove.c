@@ -21,11 +21,11 @@ static double now_s(void) { struct timespec t; clock_gettime(CLOCK_MONOTONIC, &t
 static void merkle_root_rowmajor(const uint32_t* mat, size_t width, unsigned log_h, uint32_t root[8]) {
     size_t h = (size_t)1 << log_h;
     uint32_t* layer = (uint32_t*)malloc(8 * h * sizeof(uint32_t));
-#pragma omp parallel for schedule(static) if (h > 64)
+#pragma omp parallel for schedule(static) if (h >= 2048)
     for (long r = 0; r < (long)h; r++) orc_hash_row(mat + (size_t)r * width, width, layer + 8 * (size_t)r);
     for (size_t n = h >> 1; n >= 1; n >>= 1) {
         uint32_t* next = (uint32_t*)malloc(8 * n * sizeof(uint32_t));
-#pragma omp parallel for schedule(static) if (n > 64)
+#pragma omp parallel for schedule(static) if (n >= 2048)
         for (long j = 0; j < (long)n; j++) orc_compress(layer + 16 * (size_t)j, layer + 16 * (size_t)j + 8, next + 8 * (size_t)j);
         free(layer);
         layer = next;

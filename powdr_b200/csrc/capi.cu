@@ -735,7 +735,9 @@ int pb_prove_segment(pb_ctx_t* ctx, const pb_air_t* a, const uint32_t* trace, si
         // Host trace: software pipeline over column chunks.  The PCIe copy of chunk k+1 (copy stream, double-buffered
         // staging) overlaps the LDE and the sponge absorption of chunk k (compute stream); per-row sponge states live in
         // HBM between chunks.  Stage clocks in this mode: [1]->[2] = copy+LDE+leaf hashing overlapped, [2]->[3] = upper layers.
-        size_t cw = std::min<size_t>(width, std::max<size_t>(8, ((((size_t)256 << 20) / (4 * N)) / 8) * 8));
+        size_t cw = std::max<size_t>(8, ((((size_t)256 << 20) / (4 * N)) / 8) * 8);     // ~256 MB per chunk, multiple of the sponge rate
+        if (const char* e = getenv("PB_PIPE_CHUNK_COLS")) cw = std::max<size_t>(8, ((size_t)atol(e) / 8) * 8);
+        cw = std::min<size_t>(width, cw);
         const size_t n_chunks = (width + cw - 1) / cw;
         RC(ctx->ws_trace.ensure(2 * cw * N));
         RC(ctx->ws_state.ensure(16 * M));

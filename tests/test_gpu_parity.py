@@ -308,3 +308,21 @@ def test_air_jit_and_interpreter_agree_with_oracle(ctx, orc, monkeypatch):
     d_q.zero()
     ctx.quotient(air_int, d.ptr, log_n, alpha, d_q.ptr)
     assert (ctx.to_host(d_q, (2, 4, 1 << log_n)) == exp).all()
+
+
+def test_host_pipeline_with_many_chunks_matches_device_path(ctx, orc, monkeypatch):
+    """the host-input path streams column chunks (PCIe copy || LDE || sponge absorption with states parked in HBM);
+    force 8-column chunks so a 43-column trace takes 6 chunks incl. a ragged last one"""
+    mach = _machine().synthetic_machine(43, 9, seed=11)
+    air, bc, spans = _compile(ctx, mach)
+    rng = np.random.default_rng(59)
+    log_n = 11
+    trace = rand_field(rng, (mach.width, 1 << log_n))
+    exp, _ = orc.prove_segment(trace, bc, spans)
+    from powdr_b200.capi import R_MOD_P
+    host = ((trace.astype(np.uint64) * np.uint64(R_MOD_P)) % np.uint64(P)).astype(np.uint32)
+    monkeypatch.setenv("PB_PIPE_CHUNK_COLS", "8")
+    got = ctx.prove_segment(air, host.ctypes.data, log_n, mach.width, on_device=False)
+    assert got == exp
+    monkeypatch.setenv("PB_PIPE_CHUNK_COLS", "16")
+    assert ctx.prove_segment(air, host.ctypes.data, log_n, mach.width, on_device=False) == exp
