@@ -214,7 +214,7 @@ inline bool launch_strided(bool inv, int n_hi, int n_lo, dim3 grid, cudaStream_t
         }                                                                                                                       \
         return true;                                                                                                            \
     }
-    PB_CASE(9, 9) PB_CASE(9, 10) PB_CASE(10, 10) PB_CASE(10, 11) PB_CASE(11, 11)
+    PB_CASE(8, 8) PB_CASE(8, 9) PB_CASE(9, 9) PB_CASE(9, 10) PB_CASE(10, 10) PB_CASE(10, 11) PB_CASE(11, 11) PB_CASE(11, 12) PB_CASE(12, 12)
 #undef PB_CASE
     return false;
 }
@@ -233,13 +233,13 @@ inline bool launch_transposed(bool inv, int n, int n_lo, dim3 grid, cudaStream_t
         }                                                                                                                         \
         return true;                                                                                                              \
     }
-    PB_CASE(9) PB_CASE(10) PB_CASE(11)
+    PB_CASE(8) PB_CASE(9) PB_CASE(10) PB_CASE(11) PB_CASE(12)
 #undef PB_CASE
     return false;
 }
 
 inline bool supported(int n_hi, int n_lo) {
-    return (n_hi == 9 && (n_lo == 9 || n_lo == 10)) || (n_hi == 10 && (n_lo == 10 || n_lo == 11)) || (n_hi == 11 && n_lo == 11);
+    return n_hi >= 8 && n_hi <= 12 && (n_lo == n_hi || n_lo == n_hi + 1) && n_lo <= 12;     // 16 <= n <= 24
 }
 
 }  // namespace nttf
