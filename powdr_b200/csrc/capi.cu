@@ -633,7 +633,7 @@ int pb_merkle_commit(pb_ctx_t* ctx, const uint32_t* const* d_mats, const size_t*
     CK(cudaMemcpyAsync(ctx->coltab.p, cols.data(), cols.size() * sizeof(void*), cudaMemcpyHostToDevice, ctx->stream));
     const int slot = ctx->kp_n < pb_ctx::KPROF ? ctx->kp_n : -1;
     if (slot >= 0) CK(cudaEventRecord(ctx->kp_a[slot], ctx->stream));
-    p2::leaf_hash_cols_kernel<<<(unsigned)((h + 255) / 256), 256, 0, ctx->stream>>>(ctx->coltab.p, (uint32_t)cols.size(), h, d_layers);
+    p2::leaf_hash_cols_kernel<<<(unsigned)((h + p2::LEAF_THREADS - 1) / p2::LEAF_THREADS), p2::LEAF_THREADS, 0, ctx->stream>>>(ctx->coltab.p, (uint32_t)cols.size(), h, d_layers);
     LAUNCHED(ctx);
     if (slot >= 0) {
         CK(cudaEventRecord(ctx->kp_b[slot], ctx->stream));
@@ -758,7 +758,7 @@ int pb_prove_segment(pb_ctx_t* ctx, const pb_air_t* a, const uint32_t* trace, si
             CK(cudaStreamWaitEvent(st, ctx->ev_copy[b], 0));
             RC(pb_lde_batch(ctx, stage, log_n, wk, log_blowup, bb::GEN, ctx->ws_lde.p + c0 * M));
             CK(cudaEventRecord(ctx->ev_free[b], st));
-            p2::leaf_absorb_cols_kernel<<<(unsigned)((M + 255) / 256), 256, 0, st>>>(ctx->coltab.p + c0, (uint32_t)wk, M, ctx->ws_state.p,
+            p2::leaf_absorb_cols_kernel<<<(unsigned)((M + p2::LEAF_THREADS - 1) / p2::LEAF_THREADS), p2::LEAF_THREADS, 0, st>>>(ctx->coltab.p + c0, (uint32_t)wk, M, ctx->ws_state.p,
                                                                                     ctx->ws_layers.p, k == 0, k + 1 == n_chunks);
             LAUNCHED(ctx);
         }

@@ -22,7 +22,11 @@ struct Consts {
 __constant__ Consts c_p2;
 
 __device__ __forceinline__ uint32_t sbox_rc(uint32_t s, uint32_t rc_minus_p) {
+#ifdef PB_V_RC_PIN
+    int32_t x = __viaddmin_s32((int32_t)s, (int32_t)rc_minus_p, 0x7fffffff);
+#else
     int32_t x = (int32_t)(s + rc_minus_p);          // [-p, p)
+#endif
     int32_t x2 = bb::smul(x, x);
     int32_t x3 = bb::smul(x2, x);
     int32_t x4 = bb::smul(x2, x2);
@@ -34,24 +38,24 @@ __device__ __forceinline__ void external_linear(uint32_t (&s)[16]) {
 #pragma unroll
     for (int c = 0; c < 16; c += 4) {
         uint32_t x0 = s[c], x1 = s[c + 1], x2 = s[c + 2], x3 = s[c + 3];
-        uint32_t t01 = bb::add(x0, x1), t23 = bb::add(x2, x3);
-        uint32_t t0123 = bb::add(t01, t23);
-        uint32_t t01123 = bb::add(t0123, x1), t01233 = bb::add(t0123, x3);
-        s[c + 3] = bb::add(t01233, bb::dbl(x0));
-        s[c + 1] = bb::add(t01123, bb::dbl(x2));
-        s[c] = bb::add(t01123, t01);
-        s[c + 2] = bb::add(t01233, t23);
+        uint32_t t01 = bb::add_lin(x0, x1), t23 = bb::add_lin(x2, x3);
+        uint32_t t0123 = bb::add_lin(t01, t23);
+        uint32_t t01123 = bb::add_lin(t0123, x1), t01233 = bb::add_lin(t0123, x3);
+        s[c + 3] = bb::add_lin(t01233, bb::add_lin(x0, x0));
+        s[c + 1] = bb::add_lin(t01123, bb::add_lin(x2, x2));
+        s[c] = bb::add_lin(t01123, t01);
+        s[c + 2] = bb::add_lin(t01233, t23);
     }
-    uint32_t q0 = bb::add(bb::add(s[0], s[4]), bb::add(s[8], s[12]));
-    uint32_t q1 = bb::add(bb::add(s[1], s[5]), bb::add(s[9], s[13]));
-    uint32_t q2 = bb::add(bb::add(s[2], s[6]), bb::add(s[10], s[14]));
-    uint32_t q3 = bb::add(bb::add(s[3], s[7]), bb::add(s[11], s[15]));
+    uint32_t q0 = bb::add_lin(bb::add_lin(s[0], s[4]), bb::add_lin(s[8], s[12]));
+    uint32_t q1 = bb::add_lin(bb::add_lin(s[1], s[5]), bb::add_lin(s[9], s[13]));
+    uint32_t q2 = bb::add_lin(bb::add_lin(s[2], s[6]), bb::add_lin(s[10], s[14]));
+    uint32_t q3 = bb::add_lin(bb::add_lin(s[3], s[7]), bb::add_lin(s[11], s[15]));
 #pragma unroll
     for (int c = 0; c < 16; c += 4) {
-        s[c] = bb::add(s[c], q0);
-        s[c + 1] = bb::add(s[c + 1], q1);
-        s[c + 2] = bb::add(s[c + 2], q2);
-        s[c + 3] = bb::add(s[c + 3], q3);
+        s[c] = bb::add_lin(s[c], q0);
+        s[c + 1] = bb::add_lin(s[c + 1], q1);
+        s[c + 2] = bb::add_lin(s[c + 2], q2);
+        s[c + 3] = bb::add_lin(s[c + 3], q3);
     }
 }
 
@@ -106,6 +110,11 @@ __device__ __forceinline__ void permute(uint32_t (&s)[16]) {
 }
 
 // ---------------- kernels ----------------
+
+// Leaf kernels run 64-thread CTAs: every thread does the same long job (253 permutations for the keccak width), so a grid of
+// 2^21 rows is 9.2 waves of the 48 resident warps per SM; with 256-thread CTAs the last 0.2 wave ran on 34 SMs at full
+// duration (+8 %).  Small CTAs let the block scheduler spread that tail over all 148 SMs.
+constexpr int LEAF_THREADS = 64;
 
 // leaf r = sponge(row r of the concatenation of all committed matrices); `cols` holds one base pointer per column.
 // Overwrite-mode absorb, rate 8, no padding (PaddingFreeSponge<16,8,8>).  One thread per row; consecutive threads read
@@ -234,7 +243,10 @@ __global__ void __launch_bounds__(512) compress_tail_kernel(uint4* layer, uint32
 }
 
 // single permutation per thread on [n][16] states -- used by tests and the throughput micro-benchmark
-__global__ void permute_states_kernel(uint32_t* states, size_t n, int reps) {
+#ifndef PB_V_MINBLOCKS
+#define PB_V_MINBLOCKS 1
+#endif
+__global__ void __launch_bounds__(256, PB_V_MINBLOCKS) permute_states_kernel(uint32_t* states, size_t n, int reps) {
     size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
     uint32_t s[16];
