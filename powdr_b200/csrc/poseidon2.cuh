@@ -114,7 +114,7 @@ __device__ __forceinline__ void permute(uint32_t (&s)[16]) {
 // Leaf kernels: __launch_bounds__(256, 1) lets ptxas take 64 registers (it stops at 40 with the default bound); the extra
 // registers buy instruction-level parallelism across the 16 independent S-boxes and measured +8.6 % permutations/s
 // (4.07 vs 3.75 G/s) even though resident warps drop from 48 to 32 per SM.  Forcing 32 registers (64 warps) is slower (3.8).
-constexpr int LEAF_THREADS = 256;
+constexpr int LEAF_THREADS = 128;
 
 // leaf r = sponge(row r of the concatenation of all committed matrices); `cols` holds one base pointer per column.
 // Overwrite-mode absorb, rate 8, no padding (PaddingFreeSponge<16,8,8>).  One thread per row; consecutive threads read
