@@ -97,15 +97,28 @@ int pb_poseidon2_permute(pb_ctx_t* ctx, uint32_t* d_states, size_t n, int reps);
  * d_in: 2^log_len Ext4 elements [len][4], bit-reversed evaluations over shift*<w_len>; d_out: [len/2][4]. */
 int pb_fri_fold(pb_ctx_t* ctx, const uint32_t* d_in, size_t log_len, uint32_t shift, const uint32_t beta[4], uint32_t* d_out);
 
+/* ---- openings + reduced opening (the opening phase of pcs_opening; SURVEY.md §8f-4, widened in round 1) -------------------
+ * pb_eval_at_point: y_k = f_k(zeta) for `width` columns given as 2^log_n evaluations over shift*H (natural order);
+ *   d_ys: [width][4] Ext4 values (Montgomery limbs).
+ * pb_deep_quotient: ro[r] = (sum_j gamma^j (f_j[r] - y_j)) / (x_r - zeta) over the LDE domain shift*H' (bit-reversed rows),
+ *   j over all columns of d_mats in order; d_ys as produced by pb_eval_at_point; d_out: [2^log_m][4]. Synchronises (reads d_ys). */
+int pb_eval_at_point(pb_ctx_t* ctx, const uint32_t* d_mat, size_t log_n, size_t width, uint32_t shift, const uint32_t zeta[4],
+                     uint32_t* d_ys);
+int pb_deep_quotient(pb_ctx_t* ctx, const uint32_t* const* d_mats, const size_t* widths, size_t n_mats, size_t log_m, uint32_t shift,
+                     const uint32_t zeta[4], const uint32_t gamma[4], const uint32_t* d_ys, uint32_t* d_out);
+
 /* ---- whole segment: the metric's unit of work ------------------------------------------------------------------------
  * Replaces engine.prove(pk, ProvingContext{common_main}) for one APC chip behind sdk.app_prover(exe)?.prove(stdin)
  * (/root/reference/openvm-riscv/src/lib.rs:327-332; AirProvingContext built at
  * /root/reference/openvm/src/powdr_extension/trace_generator/cuda/mod.rs:415-419): main trace commit (LDE + Merkle),
- * quotient, quotient commit, FRI commit phase.  Transcript documented in DESIGN.md. */
+ * quotient, quotient commit, openings at zeta, reduced opening, FRI commit phase.  Transcript documented in DESIGN.md. */
 typedef struct {
     uint32_t trace_root[8];
     uint32_t quotient_root[8];
     uint32_t alpha[4];
+    uint32_t zeta[4];              /* out-of-domain opening point */
+    uint32_t openings_root[8];     /* Merkle root (rows of 8, zero padded to a power of two) over the opened values */
+    uint32_t gamma[4];             /* batching challenge of the reduced opening */
     uint32_t n_fri_layers;
     uint32_t fri_roots[32][8];
     uint32_t fri_betas[32][4];
@@ -115,8 +128,8 @@ typedef struct {
 #define PB_TRACE_ON_DEVICE 1u       /* `trace` is a device pointer (value-only timing); else host memory, copied in */
 int pb_prove_segment(pb_ctx_t* ctx, const pb_air_t* air, const uint32_t* trace, size_t log_n, size_t width, uint32_t flags,
                      pb_segment_proof_t* proof);
-/* per-stage device milliseconds of the last pb_prove_segment: [h2d, lde, merkle, quotient, qlde, qmerkle, fri, total] */
-int pb_last_stage_ms(pb_ctx_t* ctx, float ms[8]);
+/* per-stage device milliseconds of the last pb_prove_segment: [h2d, lde, merkle, quotient, qlde, qmerkle, open, fri, total] */
+int pb_last_stage_ms(pb_ctx_t* ctx, float ms[9]);
 /* kernels launched by this context since creation (bench.py's gpu_launches) */
 uint64_t pb_launch_count(pb_ctx_t* ctx);
 /* CUDA-event timing of the dominant kernel (Poseidon2 leaf hashing of column-major matrices) since the last call:

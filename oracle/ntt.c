@@ -103,3 +103,62 @@ void orc_fri_fold(const uint32_t* in, unsigned log_len, uint32_t shift, const ui
         memcpy(out + 4 * (size_t)j, r.c, 16);
     }
 }
+
+/* ---- openings (widened in round 1): f(zeta) for columns given as evaluations over shift*H (natural order).
+   Restated independently of the GPU's barycentric formula: interpolate (iNTT of g(y) = f(shift*y)), then Horner at zeta/shift
+   in the extension field.  out: [width][4]. */
+void orc_eval_at_point(const uint32_t* mat, unsigned log_n, size_t width, uint32_t shift, const uint32_t zeta[4], uint32_t* out) {
+    size_t n = (size_t)1 << log_n;
+    bb4_t z = {{zeta[0], zeta[1], zeta[2], zeta[3]}};
+    bb4_t zs = bb4_scale(z, bb_inv(shift));
+#pragma omp parallel
+    {
+        uint32_t* buf = (uint32_t*)malloc(n * sizeof(uint32_t));
+#pragma omp for schedule(dynamic, 1)
+        for (long c = 0; c < (long)width; c++) {
+            memcpy(buf, mat + (size_t)c * n, n * sizeof(uint32_t));
+            orc_intt(buf, log_n);
+            bb4_t acc = bb4_from_base(0);
+            for (size_t i = n; i-- > 0;) {
+                acc = bb4_mul(acc, zs);
+                acc.c[0] = bb_add(acc.c[0], buf[i]);
+            }
+            memcpy(out + 4 * (size_t)c, acc.c, 16);
+        }
+        free(buf);
+    }
+}
+
+/* reduced opening at one point over the LDE domain shift*H' (bit-reversed rows):
+   ro[r] = ( sum_j gamma^j * (f_j[r] - y_j) ) / (x_r - zeta),   x_r = shift * w_m^{bitrev(r)},  j runs over all columns of all
+   matrices in order.  mats: column-major, height m = 2^log_m.  ys: [total_width][4].  out: [m][4]. */
+void orc_deep_quotient(const uint32_t* const* mats, const size_t* widths, size_t n_mats, unsigned log_m, uint32_t shift,
+                       const uint32_t zeta[4], const uint32_t gamma[4], const uint32_t* ys, uint32_t* out) {
+    size_t m = (size_t)1 << log_m, total = 0;
+    for (size_t i = 0; i < n_mats; i++) total += widths[i];
+    bb4_t g = {{gamma[0], gamma[1], gamma[2], gamma[3]}}, z = {{zeta[0], zeta[1], zeta[2], zeta[3]}};
+    bb4_t* gp = (bb4_t*)malloc(total * sizeof(bb4_t));
+    bb4_t cur = bb4_from_base(1), ysum = bb4_from_base(0);
+    for (size_t j = 0; j < total; j++) {
+        gp[j] = cur;
+        bb4_t y;
+        memcpy(y.c, ys + 4 * j, 16);
+        ysum = bb4_add(ysum, bb4_mul(cur, y));
+        cur = bb4_mul(cur, g);
+    }
+    uint32_t w = bb_root_of_unity(log_m);
+#pragma omp parallel for schedule(static)
+    for (long r = 0; r < (long)m; r++) {
+        bb4_t acc = bb4_from_base(0);
+        size_t j = 0;
+        for (size_t i = 0; i < n_mats; i++)
+            for (size_t c = 0; c < widths[i]; c++, j++) acc = bb4_add(acc, bb4_scale(gp[j], mats[i][c * m + (size_t)r]));
+        acc = bb4_sub(acc, ysum);
+        uint32_t x = bb_mul(shift, bb_pow(w, bitrev32((uint32_t)r, log_m)));
+        bb4_t d = bb4_from_base(x);
+        d = bb4_sub(d, z);
+        bb4_t v = bb4_mul(acc, bb4_inv(d));
+        memcpy(out + 4 * (size_t)r, v.c, 16);
+    }
+    free(gp);
+}

@@ -58,6 +58,11 @@ void orc_constraint_fold(const uint32_t* bc, const orc_span_t* spans, size_t n_c
    in: len=2^log_len ext elements as [len][4]; out [len/2][4].  out[j] = (lo+hi)/2 + beta*(lo-hi)/(2 x_j). */
 void orc_fri_fold(const uint32_t* in, unsigned log_len, uint32_t shift, const uint32_t beta[4], uint32_t* out);
 
+/* ---- openings + DEEP reduced opening (row f-4 of SURVEY.md §8, widened in round 1) ---- */
+void orc_eval_at_point(const uint32_t* mat, unsigned log_n, size_t width, uint32_t shift, const uint32_t zeta[4], uint32_t* out);
+void orc_deep_quotient(const uint32_t* const* mats, const size_t* widths, size_t n_mats, unsigned log_m, uint32_t shift,
+                       const uint32_t zeta[4], const uint32_t gamma[4], const uint32_t* ys, uint32_t* out);
+
 /* ---- DuplexChallenger<BabyBear, Perm16, 16, 8> ---- */
 typedef struct { uint32_t sponge[16]; uint32_t in_buf[8]; int n_in; uint32_t out_buf[8]; int n_out; } orc_challenger_t;
 void orc_challenger_init(orc_challenger_t* c);
@@ -82,6 +87,9 @@ typedef struct {
     uint32_t trace_root[8];
     uint32_t quotient_root[8];
     uint32_t alpha[4];
+    uint32_t zeta[4];              /* out-of-domain opening point */
+    uint32_t openings_root[8];     /* Merkle root (rows of 8, zero padded to a power of two) over the opened values */
+    uint32_t gamma[4];             /* batching challenge of the reduced opening */
     uint32_t n_fri_layers;
     uint32_t fri_roots[32][8];
     uint32_t fri_betas[32][4];

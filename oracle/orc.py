@@ -43,6 +43,7 @@ class Interaction(C.Structure):
 
 class SegmentProof(C.Structure):
     _fields_ = [("trace_root", C.c_uint32 * 8), ("quotient_root", C.c_uint32 * 8), ("alpha", C.c_uint32 * 4),
+                ("zeta", C.c_uint32 * 4), ("openings_root", C.c_uint32 * 8), ("gamma", C.c_uint32 * 4),
                 ("n_fri_layers", C.c_uint32), ("fri_roots", (C.c_uint32 * 8) * 32), ("fri_betas", (C.c_uint32 * 4) * 32),
                 ("final_poly", (C.c_uint32 * 4) * 8), ("final_len", C.c_uint32)]
 
@@ -50,6 +51,7 @@ class SegmentProof(C.Structure):
         n = self.n_fri_layers
         return {
             "trace_root": list(self.trace_root), "quotient_root": list(self.quotient_root), "alpha": list(self.alpha),
+            "zeta": list(self.zeta), "openings_root": list(self.openings_root), "gamma": list(self.gamma),
             "n_fri_layers": int(n), "fri_roots": [list(self.fri_roots[i]) for i in range(n)],
             "fri_betas": [list(self.fri_betas[i]) for i in range(n)],
             "final_poly": [list(self.final_poly[i]) for i in range(self.final_len)], "final_len": int(self.final_len),
@@ -182,6 +184,27 @@ def quotient(bc, spans, lde, log_n, alpha, shift=GENERATOR):
     out = np.empty((2, 4, n), dtype=np.uint32)
     lib().orc_quotient(_p(bc), compile_spans(spans), C.c_size_t(len(spans)), _p(m), C.c_uint(log_n), C.c_uint(1),
                        C.c_uint32(shift), _p(al), _p(out))
+    return out
+
+
+def eval_at_point(mat, shift, zeta):
+    """mat: (width, n) evaluations over shift*H, natural order -> (width, 4) values f(zeta)"""
+    m, z = _u32(mat), _u32(zeta)
+    w, n = m.shape
+    out = np.empty((w, 4), dtype=np.uint32)
+    lib().orc_eval_at_point(_p(m), C.c_uint(n.bit_length() - 1), C.c_size_t(w), C.c_uint32(shift), _p(z), _p(out))
+    return out
+
+
+def deep_quotient(mats, shift, zeta, gamma, ys):
+    """mats: list of (width_i, m) column-major LDE matrices (bit-reversed rows over shift*H'); ys: (sum width, 4) -> (m, 4)"""
+    mats = [_u32(x) for x in mats]
+    m = mats[0].shape[1]
+    ptrs = (C.c_void_p * len(mats))(*[x.ctypes.data for x in mats])
+    widths = (C.c_size_t * len(mats))(*[x.shape[0] for x in mats])
+    z, g, y = _u32(zeta), _u32(gamma), _u32(ys)
+    out = np.empty((m, 4), dtype=np.uint32)
+    lib().orc_deep_quotient(ptrs, widths, C.c_size_t(len(mats)), C.c_uint(m.bit_length() - 1), C.c_uint32(shift), _p(z), _p(g), _p(y), _p(out))
     return out
 
 

@@ -6,8 +6,9 @@
  * engine.prove(pk, ProvingContext) behind sdk.app_prover(exe)?.prove(stdin)
  * (/root/reference/openvm-riscv/src/lib.rs:327-332); the engine itself is un-vendored => parity unpinned.
  *
- * Transcript (simplified, documented in DESIGN.md): observe(trace_root) -> alpha; observe(quotient_root) -> gamma;
- * FRI input = Q0 + gamma*Q1 (the two quotient-chunk LDEs read as Ext4 columns); per layer observe(root_i) -> beta_i.
+ * Transcript (simplified, documented in DESIGN.md): observe(trace_root) -> alpha; observe(quotient_root) -> zeta;
+ * open every trace column and quotient-chunk column at zeta, observe(Merkle root of the opened values) -> gamma;
+ * FRI input = reduced opening sum_j gamma^j (f_j(x) - f_j(zeta))/(x - zeta); per layer observe(root_i) -> beta_i.
  */
 #include "oracle.h"
 #include "bb31.h"
@@ -61,19 +62,17 @@ void orc_prove_segment(const uint32_t* trace, unsigned log_n, size_t width, cons
     uint32_t* q = (uint32_t*)malloc(8 * n * sizeof(uint32_t));
     orc_quotient(bc, spans, n_constraints, lde, log_n, log_blowup, BB_GENERATOR, proof->alpha, q);
     double t3 = now_s();
-    free(lde);
 
     /* quotient commit: chunk b holds evals over g*w_{2N}^b*H in bit-reversed order -> natural, LDE with shift g/s_b */
     uint32_t* qlde = (uint32_t*)malloc(8 * m * sizeof(uint32_t));
     uint32_t w2n = bb_root_of_unity(log_n + 1);
-    uint32_t* nat = (uint32_t*)malloc(4 * n * sizeof(uint32_t));
+    uint32_t* nat = (uint32_t*)malloc(8 * n * sizeof(uint32_t));
     for (int b = 0; b < 2; b++) {
         for (int l = 0; l < 4; l++)
-            for (size_t j = 0; j < n; j++) nat[(size_t)l * n + bitrev32((uint32_t)j, log_n)] = q[((size_t)b * 4 + l) * n + j];
+            for (size_t j = 0; j < n; j++) nat[((size_t)b * 4 + l) * n + bitrev32((uint32_t)j, log_n)] = q[((size_t)b * 4 + l) * n + j];
         uint32_t shift = b ? bb_inv(w2n) : 1;
-        orc_lde_batch(nat, log_n, 4, log_blowup, shift, qlde + (size_t)b * 4 * m);
+        orc_lde_batch(nat + (size_t)b * 4 * n, log_n, 4, log_blowup, shift, qlde + (size_t)b * 4 * m);
     }
-    free(nat);
     free(q);
     double t4 = now_s();
     const uint32_t* mats2[2] = {qlde, qlde + 4 * m};
@@ -83,19 +82,32 @@ void orc_prove_segment(const uint32_t* trace, unsigned log_n, size_t width, cons
     free(layers);
     double t5 = now_s();
     orc_challenger_observe(&ch, proof->quotient_root, 8);
-    uint32_t gamma[4];
-    orc_challenger_sample_ext(&ch, gamma);
+    orc_challenger_sample_ext(&ch, proof->zeta);
 
-    /* stage 3b: FRI commit phase on f = Q0 + gamma*Q1, ext elements [m][4], bit-reversed over g*H' */
+    /* openings at zeta: trace columns over H, quotient chunk b over g*w_{2N}^b*H; committed as rows of 8 and observed */
+    size_t n_open = width + 8;
+    size_t open_words = 4 * n_open, open_rows = 1;
+    while (open_rows * 8 < open_words) open_rows <<= 1;
+    unsigned log_open_rows = 0;
+    while (((size_t)1 << log_open_rows) < open_rows) log_open_rows++;
+    uint32_t* ys = (uint32_t*)calloc(open_rows * 8, sizeof(uint32_t));
+    orc_eval_at_point(trace, log_n, width, 1, proof->zeta, ys);
+    orc_eval_at_point(nat, log_n, 4, BB_GENERATOR, proof->zeta, ys + 4 * width);
+    orc_eval_at_point(nat + 4 * n, log_n, 4, bb_mul(BB_GENERATOR, w2n), proof->zeta, ys + 4 * (width + 4));
+    free(nat);
+    merkle_root_rowmajor(ys, 8, log_open_rows, proof->openings_root);
+    orc_challenger_observe(&ch, proof->openings_root, 8);
+    orc_challenger_sample_ext(&ch, proof->gamma);
+
+    /* stage 3b: FRI commit phase on the reduced opening ro(x) = sum_j gamma^j (f_j(x) - f_j(zeta)) / (x - zeta) over g*H' */
     uint32_t* f = (uint32_t*)malloc(4 * m * sizeof(uint32_t));
-    bb4_t g4 = {{gamma[0], gamma[1], gamma[2], gamma[3]}};
-#pragma omp parallel for schedule(static)
-    for (long r = 0; r < (long)m; r++) {
-        bb4_t a, b;
-        for (int l = 0; l < 4; l++) { a.c[l] = qlde[(size_t)l * m + r]; b.c[l] = qlde[(size_t)(4 + l) * m + r]; }
-        bb4_t v = bb4_add(a, bb4_mul(g4, b));
-        memcpy(f + 4 * (size_t)r, v.c, 16);
+    {
+        const uint32_t* mats3[3] = {lde, qlde, qlde + 4 * m};
+        size_t w3[3] = {width, 4, 4};
+        orc_deep_quotient(mats3, w3, 3, log_m, BB_GENERATOR, proof->zeta, proof->gamma, ys, f);
     }
+    free(ys);
+    free(lde);
     free(qlde);
     unsigned log_len = log_m;
     uint32_t shift = BB_GENERATOR;

@@ -15,7 +15,7 @@ EXPORTS = [
     "pb_ctx_create", "pb_ctx_destroy", "pb_ctx_synchronize", "pb_ctx_set_poseidon2", "pb_host_alloc", "pb_host_free",
     "pb_device_alloc", "pb_device_free", "pb_copy_h2d", "pb_copy_d2h", "pb_memset_zero", "pb_to_monty", "pb_from_monty",
     "pb_lde_batch", "pb_air_compile", "pb_air_free", "pb_air_is_jit", "pb_air_jit_compile_only", "pb_quotient", "pb_constraint_fold", "pb_merkle_commit",
-    "pb_merkle_commit_rows8", "pb_poseidon2_permute", "pb_fri_fold", "pb_prove_segment", "pb_last_stage_ms",
+    "pb_merkle_commit_rows8", "pb_poseidon2_permute", "pb_fri_fold", "pb_eval_at_point", "pb_deep_quotient", "pb_prove_segment", "pb_last_stage_ms",
     "pb_launch_count", "pb_leaf_kernel_profile", "_apc_tracegen", "_apc_apply_derived_expr", "_apc_apply_bus",
 ]
 
@@ -52,6 +52,7 @@ class DevInteraction(C.Structure):
 
 class SegmentProof(C.Structure):
     _fields_ = [("trace_root", C.c_uint32 * 8), ("quotient_root", C.c_uint32 * 8), ("alpha", C.c_uint32 * 4),
+                ("zeta", C.c_uint32 * 4), ("openings_root", C.c_uint32 * 8), ("gamma", C.c_uint32 * 4),
                 ("n_fri_layers", C.c_uint32), ("fri_roots", (C.c_uint32 * 8) * 32), ("fri_betas", (C.c_uint32 * 4) * 32),
                 ("final_poly", (C.c_uint32 * 4) * 8), ("final_len", C.c_uint32)]
 
@@ -59,6 +60,7 @@ class SegmentProof(C.Structure):
         n = self.n_fri_layers
         return {
             "trace_root": list(self.trace_root), "quotient_root": list(self.quotient_root), "alpha": list(self.alpha),
+            "zeta": list(self.zeta), "openings_root": list(self.openings_root), "gamma": list(self.gamma),
             "n_fri_layers": int(n), "fri_roots": [list(self.fri_roots[i]) for i in range(n)],
             "fri_betas": [list(self.fri_betas[i]) for i in range(n)],
             "final_poly": [list(self.final_poly[i]) for i in range(self.final_len)], "final_len": int(self.final_len),
@@ -231,6 +233,20 @@ class Context:
         _chk(self.lib.pb_fri_fold(self.h, C.c_void_p(d_in_ptr), C.c_size_t(log_len), C.c_uint32(shift), b, C.c_void_p(d_out_ptr)),
              "pb_fri_fold")
 
+    def eval_at_point(self, d_mat_ptr, log_n, width, shift, zeta, d_ys_ptr):
+        z = (C.c_uint32 * 4)(*[int(x) for x in zeta])
+        _chk(self.lib.pb_eval_at_point(self.h, C.c_void_p(d_mat_ptr), C.c_size_t(log_n), C.c_size_t(width), C.c_uint32(shift), z,
+                                       C.c_void_p(d_ys_ptr)), "pb_eval_at_point")
+
+    def deep_quotient(self, mat_ptrs, widths, log_m, shift, zeta, gamma, d_ys_ptr, d_out_ptr):
+        n = len(mat_ptrs)
+        ptrs = (C.c_void_p * n)(*mat_ptrs)
+        ws = (C.c_size_t * n)(*widths)
+        z = (C.c_uint32 * 4)(*[int(x) for x in zeta])
+        g = (C.c_uint32 * 4)(*[int(x) for x in gamma])
+        _chk(self.lib.pb_deep_quotient(self.h, ptrs, ws, C.c_size_t(n), C.c_size_t(log_m), C.c_uint32(shift), z, g, C.c_void_p(d_ys_ptr),
+                                       C.c_void_p(d_out_ptr)), "pb_deep_quotient")
+
     def prove_segment(self, air, trace_ptr, log_n, width, on_device=False):
         proof = SegmentProof()
         _chk(self.lib.pb_prove_segment(self.h, air.h, C.c_void_p(trace_ptr), C.c_size_t(log_n), C.c_size_t(width),
@@ -238,9 +254,9 @@ class Context:
         return proof.as_dict()
 
     def last_stage_ms(self):
-        ms = (C.c_float * 8)()
+        ms = (C.c_float * 9)()
         _chk(self.lib.pb_last_stage_ms(self.h, ms), "pb_last_stage_ms")
-        return dict(zip(["h2d", "lde", "merkle", "quotient", "qlde", "qmerkle", "fri", "total"], [float(x) for x in ms]))
+        return dict(zip(["h2d", "lde", "merkle", "quotient", "qlde", "qmerkle", "open", "fri", "total"], [float(x) for x in ms]))
 
     def launch_count(self):
         return int(self.lib.pb_launch_count(self.h))

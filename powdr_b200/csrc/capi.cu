@@ -16,6 +16,7 @@
 #include "air.cuh"
 #include "air_jit.cuh"
 #include "bb31.cuh"
+#include "deep.cuh"
 #include "fri.cuh"
 #include "ntt.cuh"
 #include "ntt_fast.cuh"
@@ -166,11 +167,14 @@ struct pb_ctx {
     DevBuf<uint32_t> tmp, tmp2;       // LDE intermediates (L2-sized)
     DevBuf<const uint32_t*> coltab;
     // pb_prove_segment workspace
-    DevBuf<uint32_t> ws_trace, ws_lde, ws_layers, ws_q, ws_qnat, ws_qlde, ws_f0, ws_f1, ws_state;
+    DevBuf<uint32_t> ws_trace, ws_lde, ws_layers, ws_q, ws_qnat, ws_qlde, ws_f0, ws_f1, ws_state, ws_ys;
+    DevBuf<uint4> ws_w, ws_part;          // barycentric weights [N], per-CTA partial sums of the openings
+    DevBuf<uint2> ws_gp;                  // Shoup pairs of the gamma powers of the reduced opening
+    DevBuf<const uint32_t*> coltab2;
     cudaStream_t copy_stream = nullptr;   // H2D chunks of the host-input pipeline
     cudaEvent_t ev_copy[2] = {nullptr}, ev_free[2] = {nullptr};
-    cudaEvent_t ev[8] = {nullptr};
-    float stage_ms[8] = {0};
+    cudaEvent_t ev[10] = {nullptr};
+    float stage_ms[9] = {0};               // h2d, lde, merkle, quotient, qlde, qmerkle, open(+deep), fri, total
     // live timing of the dominant kernel (Poseidon2 leaf hashing over column-major matrices): event pairs on the stream
     static constexpr int KPROF = 16;
     cudaEvent_t kp_a[KPROF] = {nullptr}, kp_b[KPROF] = {nullptr};
@@ -337,6 +341,7 @@ int pb_ctx_destroy(pb_ctx_t* ctx) {
     if (ctx->d_fold_tab) cudaFree(ctx->d_fold_tab);
     ctx->tmp.release(); ctx->tmp2.release(); ctx->coltab.release();
     ctx->ws_trace.release(); ctx->ws_lde.release(); ctx->ws_layers.release(); ctx->ws_q.release();
+    ctx->ws_ys.release(); ctx->ws_w.release(); ctx->ws_part.release(); ctx->ws_gp.release(); ctx->coltab2.release();
     ctx->ws_qnat.release(); ctx->ws_qlde.release(); ctx->ws_f0.release(); ctx->ws_f1.release(); ctx->ws_state.release();
     if (ctx->copy_stream) cudaStreamDestroy(ctx->copy_stream);
     for (int i = 0; i < 2; i++) { if (ctx->ev_copy[i]) cudaEventDestroy(ctx->ev_copy[i]); if (ctx->ev_free[i]) cudaEventDestroy(ctx->ev_free[i]); }
@@ -700,6 +705,81 @@ int pb_fri_fold(pb_ctx_t* ctx, const uint32_t* d_in, size_t log_len, uint32_t sh
 }
 
 // ---------------------------------------------------------------------------------------------------------------------
+// openings: y_k = f_k(zeta) for columns given as evaluations over shift*H (natural order); d_ys: [width][4] Montgomery
+static int eval_at_point_m(pb_ctx* ctx, const uint32_t* d_mat, size_t log_n, size_t width, uint32_t shift_m, bb::E4 zeta_m, uint32_t* d_ys) {
+    const size_t N = (size_t)1 << log_n;
+    if (width == 0) return 0;
+    int rc = ctx->ws_w.ensure(N);
+    if (rc) return rc;
+    // f(zeta) = g(zeta/shift) with g's evaluations over H:  g(z) = (z^N - 1)/N * sum_i g_i * w^i / (z - w^i)
+    const bb::E4 z = bb::e4_scale(zeta_m, bb::inv(shift_m));
+    deep::bary_weights_kernel<<<(unsigned)((N + 255) / 256), 256, 0, ctx->stream>>>(ctx->ws_w.p, (int)log_n, h_root_of_unity_m((int)log_n), z);
+    LAUNCHED(ctx);
+    bb::E4 zn = z;
+    for (size_t i = 0; i < log_n; i++) zn = bb::e4_mul(zn, zn);
+    zn.c[0] = bb::sub(zn.c[0], bb::R1);
+    const bb::E4 pref = bb::e4_scale(zn, bb::inv(h_to_m((uint32_t)(N % bb::P))));
+    const uint32_t rows_per_cta = (uint32_t)std::max<size_t>(deep::EV_THREADS, std::min<size_t>(N, (size_t)1 << 15));
+    const uint32_t splits = (uint32_t)((N + rows_per_cta - 1) / rows_per_cta);
+    rc = ctx->ws_part.ensure(width * splits);
+    if (rc) return rc;
+    dim3 grid((unsigned)((width + deep::EV_COLS - 1) / deep::EV_COLS), splits);
+    deep::eval_partial_kernel<<<grid, deep::EV_THREADS, 0, ctx->stream>>>(d_mat, N, (uint32_t)width, ctx->ws_w.p, ctx->ws_part.p, rows_per_cta);
+    LAUNCHED(ctx);
+    deep::eval_finalize_kernel<<<(unsigned)((width + 127) / 128), 128, 0, ctx->stream>>>(ctx->ws_part.p, (uint32_t)width, splits, pref,
+                                                                                        reinterpret_cast<uint4*>(d_ys));
+    LAUNCHED(ctx);
+    CK(cudaGetLastError());
+    return 0;
+}
+
+// reduced opening over shift*H' (bit-reversed rows) of the columns in `cols`; ys_m: host, [n_cols][4] Montgomery
+static int deep_quotient_m(pb_ctx* ctx, const std::vector<const uint32_t*>& cols, size_t log_m, uint32_t shift_m, bb::E4 zeta_m,
+                           bb::E4 gamma_m, const uint32_t* ys_m, uint32_t* d_out) {
+    const size_t n_cols = cols.size(), M = (size_t)1 << log_m;
+    std::vector<uint2> gp(4 * n_cols);
+    bb::E4 cur = {{bb::R1, 0u, 0u, 0u}}, ysum = {{0u, 0u, 0u, 0u}};
+    for (size_t j = 0; j < n_cols; j++) {
+        for (int l = 0; l < 4; l++) gp[4 * j + l] = bb::shoup_pair(h_from_m(cur.c[l]));
+        bb::E4 y;
+        memcpy(y.c, ys_m + 4 * j, 16);
+        ysum = bb::e4_add(ysum, bb::e4_mul(cur, y));
+        cur = bb::e4_mul(cur, gamma_m);
+    }
+    int rc = ctx->ws_gp.ensure(4 * n_cols);
+    if (rc) return rc;
+    rc = ctx->coltab2.ensure(n_cols);
+    if (rc) return rc;
+    CK(cudaMemcpyAsync(ctx->ws_gp.p, gp.data(), gp.size() * sizeof(uint2), cudaMemcpyHostToDevice, ctx->stream));
+    CK(cudaMemcpyAsync(ctx->coltab2.p, cols.data(), n_cols * sizeof(void*), cudaMemcpyHostToDevice, ctx->stream));
+    deep::deep_quotient_kernel<<<(unsigned)((M + 255) / 256), 256, 0, ctx->stream>>>(ctx->coltab2.p, (uint32_t)n_cols, M, (int)log_m, shift_m,
+                                                                                    h_root_of_unity_m((int)log_m), ctx->ws_gp.p, ysum, zeta_m,
+                                                                                    reinterpret_cast<uint4*>(d_out));
+    LAUNCHED(ctx);
+    CK(cudaGetLastError());
+    return 0;
+}
+
+int pb_eval_at_point(pb_ctx_t* ctx, const uint32_t* d_mat, size_t log_n, size_t width, uint32_t shift, const uint32_t zeta[4], uint32_t* d_ys) {
+    if (!ctx || !d_mat || !zeta || !d_ys) return PB_ERR_INVALID_ARG;
+    if (log_n < 1 || log_n > 27 || shift == 0 || shift >= bb::P) return PB_ERR_UNSUPPORTED;
+    return eval_at_point_m(ctx, d_mat, log_n, width, h_to_m(shift), h_e4_from_canon(zeta), d_ys);
+}
+
+int pb_deep_quotient(pb_ctx_t* ctx, const uint32_t* const* d_mats, const size_t* widths, size_t n_mats, size_t log_m, uint32_t shift,
+                     const uint32_t zeta[4], const uint32_t gamma[4], const uint32_t* d_ys, uint32_t* d_out) {
+    if (!ctx || !d_mats || !widths || !n_mats || !zeta || !gamma || !d_ys || !d_out) return PB_ERR_INVALID_ARG;
+    if (log_m < 1 || log_m > 27 || shift == 0 || shift >= bb::P) return PB_ERR_UNSUPPORTED;
+    std::vector<const uint32_t*> cols;
+    for (size_t i = 0; i < n_mats; i++)
+        for (size_t c = 0; c < widths[i]; c++) cols.push_back(d_mats[i] + (c << log_m));
+    std::vector<uint32_t> ys(4 * cols.size());
+    CK(cudaMemcpyAsync(ys.data(), d_ys, 16 * cols.size(), cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    return deep_quotient_m(ctx, cols, log_m, h_to_m(shift), h_e4_from_canon(zeta), h_e4_from_canon(gamma), ys.data(), d_out);
+}
+
+// ---------------------------------------------------------------------------------------------------------------------
 int pb_prove_segment(pb_ctx_t* ctx, const pb_air_t* a, const uint32_t* trace, size_t log_n, size_t width, uint32_t flags,
                      pb_segment_proof_t* proof) {
     if (!ctx || !a || !trace || !proof) return PB_ERR_INVALID_ARG;
@@ -722,6 +802,7 @@ int pb_prove_segment(pb_ctx_t* ctx, const pb_air_t* a, const uint32_t* trace, si
     Challenger ch;
     ch.k = &ctx->p2;
     uint32_t root_m[8];
+    const uint32_t* d_trace_full = trace;        // device-resident trace (the caller's buffer, or ws_trace in host mode)
 
     if (flags & PB_TRACE_ON_DEVICE) {
         // main trace commit: LDE then Merkle
@@ -739,7 +820,8 @@ int pb_prove_segment(pb_ctx_t* ctx, const pb_air_t* a, const uint32_t* trace, si
         if (const char* e = getenv("PB_PIPE_CHUNK_COLS")) cw = std::max<size_t>(8, ((size_t)atol(e) / 8) * 8);
         cw = std::min<size_t>(width, cw);
         const size_t n_chunks = (width + cw - 1) / cw;
-        RC(ctx->ws_trace.ensure(2 * cw * N));
+        RC(ctx->ws_trace.ensure(width * N));          // whole trace stays resident: it is read again for the openings at zeta
+        d_trace_full = ctx->ws_trace.p;
         RC(ctx->ws_state.ensure(16 * M));
         std::vector<const uint32_t*> cols(width);
         for (size_t c = 0; c < width; c++) cols[c] = ctx->ws_lde.p + c * M;
@@ -751,7 +833,7 @@ int pb_prove_segment(pb_ctx_t* ctx, const pb_air_t* a, const uint32_t* trace, si
         for (size_t k = 0; k < n_chunks; k++) {
             const int b = (int)(k & 1);
             const size_t c0 = k * cw, wk = std::min(cw, width - c0);
-            uint32_t* stage = ctx->ws_trace.p + (size_t)b * cw * N;
+            uint32_t* stage = ctx->ws_trace.p + c0 * N;
             CK(cudaStreamWaitEvent(ctx->copy_stream, ctx->ev_free[b], 0));
             CK(cudaMemcpyAsync(stage, trace + c0 * N, wk * N * 4, cudaMemcpyHostToDevice, ctx->copy_stream));
             CK(cudaEventRecord(ctx->ev_copy[b], ctx->copy_stream));
@@ -793,11 +875,39 @@ int pb_prove_segment(pb_ctx_t* ctx, const pb_air_t* a, const uint32_t* trace, si
     RC(read_root(ctx, ctx->ws_layers.p, log_m, root_m));
     for (int i = 0; i < 8; i++) proof->quotient_root[i] = h_from_m(root_m[i]);
     ch.observe(root_m, 8);
-    bb::E4 gamma = ch.sample_ext();
+    const bb::E4 zeta = ch.sample_ext();
+    for (int i = 0; i < 4; i++) proof->zeta[i] = h_from_m(zeta.c[i]);
 
-    // FRI commit phase on f = Q0 + gamma*Q1
-    fri::combine_chunks_kernel<<<(unsigned)((M + 255) / 256), 256, 0, st>>>(ctx->ws_qlde.p, M, gamma, reinterpret_cast<uint4*>(ctx->ws_f0.p));
-    LAUNCHED(ctx);
+    // openings at zeta: trace columns over H, quotient chunk b over g*w_{2N}^b*H; the opened values are committed as rows of 8
+    // (zero padded to a power of two) and that root is observed
+    const size_t n_open = width + 8;
+    size_t open_rows = 1, log_open_rows = 0;
+    while (open_rows * 8 < 4 * n_open) { open_rows <<= 1; log_open_rows++; }
+    RC(ctx->ws_ys.ensure(8 * open_rows));
+    CK(cudaMemsetAsync(ctx->ws_ys.p, 0, 32 * open_rows, st));
+    {
+        const uint32_t g_c = bb::GEN, gw_c = h_from_m(bb::mul(h_to_m(bb::GEN), h_root_of_unity_m((int)log_n + 1)));
+        RC(eval_at_point_m(ctx, d_trace_full, log_n, width, h_to_m(1u), zeta, ctx->ws_ys.p));
+        RC(eval_at_point_m(ctx, ctx->ws_qnat.p, log_n, 4, h_to_m(g_c), zeta, ctx->ws_ys.p + 4 * width));
+        RC(eval_at_point_m(ctx, ctx->ws_qnat.p + 4 * N, log_n, 4, h_to_m(gw_c), zeta, ctx->ws_ys.p + 4 * (width + 4)));
+    }
+    RC(pb_merkle_commit_rows8(ctx, ctx->ws_ys.p, log_open_rows, ctx->ws_layers.p, nullptr));
+    std::vector<uint32_t> ys_h(4 * n_open);
+    CK(cudaMemcpyAsync(ys_h.data(), ctx->ws_ys.p, 16 * n_open, cudaMemcpyDeviceToHost, st));
+    RC(read_root(ctx, ctx->ws_layers.p, log_open_rows, root_m));
+    for (int i = 0; i < 8; i++) proof->openings_root[i] = h_from_m(root_m[i]);
+    ch.observe(root_m, 8);
+    const bb::E4 gamma = ch.sample_ext();
+    for (int i = 0; i < 4; i++) proof->gamma[i] = h_from_m(gamma.c[i]);
+
+    // FRI commit phase on the reduced opening ro(x) = sum_j gamma^j (f_j(x) - f_j(zeta)) / (x - zeta) over g*H'
+    {
+        std::vector<const uint32_t*> cols(n_open);
+        for (size_t c = 0; c < width; c++) cols[c] = ctx->ws_lde.p + c * M;
+        for (size_t c = 0; c < 8; c++) cols[width + c] = ctx->ws_qlde.p + c * M;
+        RC(deep_quotient_m(ctx, cols, log_m, h_to_m(bb::GEN), zeta, gamma, ys_h.data(), ctx->ws_f0.p));
+    }
+    CK(cudaEventRecord(ctx->ev[8], st));
     uint32_t* f = ctx->ws_f0.p;
     uint32_t* g = ctx->ws_f1.p;
     size_t log_len = log_m;
@@ -824,13 +934,15 @@ int pb_prove_segment(pb_ctx_t* ctx, const pb_air_t* a, const uint32_t* trace, si
     CK(cudaStreamSynchronize(st));
     for (uint32_t i = 0; i < proof->final_len; i++)
         for (int l = 0; l < 4; l++) proof->final_poly[i][l] = h_from_m(fin[4 * i + l]);
-    for (int i = 0; i < 7; i++) cudaEventElapsedTime(&ctx->stage_ms[i], ctx->ev[i], ctx->ev[i + 1]);
-    cudaEventElapsedTime(&ctx->stage_ms[7], ctx->ev[0], ctx->ev[7]);
+    for (int i = 0; i < 6; i++) cudaEventElapsedTime(&ctx->stage_ms[i], ctx->ev[i], ctx->ev[i + 1]);
+    cudaEventElapsedTime(&ctx->stage_ms[6], ctx->ev[6], ctx->ev[8]);     // openings + reduced opening
+    cudaEventElapsedTime(&ctx->stage_ms[7], ctx->ev[8], ctx->ev[7]);     // FRI commit phase
+    cudaEventElapsedTime(&ctx->stage_ms[8], ctx->ev[0], ctx->ev[7]);
 #undef RC
     return 0;
 }
 
-int pb_last_stage_ms(pb_ctx_t* ctx, float ms[8]) {
+int pb_last_stage_ms(pb_ctx_t* ctx, float ms[9]) {
     if (!ctx || !ms) return PB_ERR_INVALID_ARG;
     memcpy(ms, ctx->stage_ms, sizeof ctx->stage_ms);
     return 0;

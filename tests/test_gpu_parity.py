@@ -327,3 +327,46 @@ def test_host_pipeline_with_many_chunks_matches_device_path(ctx, orc, monkeypatc
     assert got == exp
     monkeypatch.setenv("PB_PIPE_CHUNK_COLS", "16")
     assert ctx.prove_segment(air, host.ctypes.data, log_n, mach.width, on_device=False) == exp
+
+
+# ---------------------------------------------------------------- openings + reduced opening
+@pytest.mark.parametrize("log_n,width,shift", [(3, 2, 1), (9, 13, 31), (12, 21, 1234567), (16, 9, 1)])
+def test_eval_at_point_matches_oracle(ctx, orc, log_n, width, shift):
+    rng = np.random.default_rng(61 + log_n)
+    mat = rand_field(rng, (width, 1 << log_n))
+    zeta = rand_field(rng, 4)
+    d = ctx.to_device(mat)
+    d_ys = ctx.alloc(16 * width)
+    ctx.eval_at_point(d.ptr, log_n, width, shift, zeta, d_ys.ptr)
+    got = ctx.to_host(d_ys, (width, 4))
+    assert (got == orc.eval_at_point(mat, shift, zeta)).all()
+
+
+@pytest.mark.parametrize("log_m,widths", [(4, [3]), (10, [7, 4, 4]), (13, [30, 8])])
+def test_deep_quotient_matches_oracle(ctx, orc, log_m, widths):
+    rng = np.random.default_rng(67 + log_m)
+    m = 1 << log_m
+    mats = [rand_field(rng, (w, m)) for w in widths]
+    ys = rand_field(rng, (sum(widths), 4))
+    zeta, gamma = rand_field(rng, 4), rand_field(rng, 4)
+    d_mats = [ctx.to_device(x) for x in mats]
+    d_ys = ctx.to_device(ys)
+    d_out = ctx.alloc(16 * m)
+    ctx.deep_quotient([d.ptr for d in d_mats], widths, log_m, 31, zeta, gamma, d_ys.ptr, d_out.ptr)
+    got = ctx.to_host(d_out, (m, 4))
+    assert (got == orc.deep_quotient(mats, 31, zeta, gamma, ys)).all()
+
+
+def test_reduced_opening_is_low_degree_at_scale(ctx):
+    """FRI's own invariant as a size-independent property (2^17 rows): for ANY trace the reduced opening
+    sum_j gamma^j (f_j(x) - f_j(zeta))/(x - zeta) is a polynomial of degree < N, so after log2(N) folds of the rate-1/2
+    codeword the two surviving evaluations are equal (constant final polynomial)"""
+    mach = _machine().synthetic_machine(24, 6, seed=13)
+    air, bc, spans = _compile(ctx, mach)
+    log_n = 17
+    rng = np.random.default_rng(71)
+    trace = rand_field(rng, (mach.width, 1 << log_n))
+    d = ctx.to_device(trace)
+    got = ctx.prove_segment(air, d.ptr, log_n, mach.width, on_device=True)
+    assert got["final_len"] == 2 and got["final_poly"][0] == got["final_poly"][1]
+    assert got["final_poly"][0] != [0, 0, 0, 0]

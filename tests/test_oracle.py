@@ -249,3 +249,35 @@ def test_tracegen_oracle(orc):
         d = int(out[1, r])
         assert int(out[2, r]) == (int(out[0, r]) * pow(d, P - 2, P)) % P
     assert not out[2, 6:].any()
+
+
+def test_eval_at_point_is_polynomial_evaluation(orc):
+    rng = np.random.default_rng(73)
+    log_n, shift = 6, 31 * 5 % P
+    co = rand_field(rng, 1 << log_n)
+    ev = orc.dft_naive(co, shift)
+    zeta = rand_field(rng, 4)
+
+    def emul(a, b):
+        t = [0] * 7
+        for i in range(4):
+            for j in range(4):
+                t[i + j] = (t[i + j] + int(a[i]) * int(b[j])) % P
+        return [(t[i] + 11 * t[i + 4]) % P if i < 3 else t[i] for i in range(4)]
+
+    acc = [0, 0, 0, 0]
+    for c in co[::-1]:
+        acc = emul(acc, zeta)
+        acc[0] = (acc[0] + int(c)) % P
+    assert orc.eval_at_point(ev[None, :], shift, zeta)[0].tolist() == acc
+
+
+def test_segment_reduced_opening_folds_to_a_constant(orc):
+    """whole-segment invariant of the oracle pipeline: random (unsatisfying) trace, the FRI final polynomial is constant"""
+    from powdr_b200 import machine as M
+    mach = M.synthetic_machine(10, 4, seed=21)
+    bc, spans = M.compile_constraints(mach)
+    trace = rand_field(np.random.default_rng(79), (mach.width, 1 << 7))
+    proof, _ = orc.prove_segment(trace, bc, spans)
+    assert proof["final_len"] == 2 and proof["final_poly"][0] == proof["final_poly"][1]
+    assert proof["n_fri_layers"] == 7
