@@ -128,6 +128,16 @@ typedef struct {
 #define PB_TRACE_ON_DEVICE 1u       /* `trace` is a device pointer (value-only timing); else host memory, copied in */
 int pb_prove_segment(pb_ctx_t* ctx, const pb_air_t* air, const uint32_t* trace, size_t log_n, size_t width, uint32_t flags,
                      pb_segment_proof_t* proof);
+/* ---- query phase (completes SURVEY.md §8f-4): the state of the last pb_prove_segment stays on the device ------------------
+ * pb_query_segment samples n_queries indices from the transcript (sample_bits(log_m) each, continuing after the FRI commit
+ * phase) and gathers, per query (canonical words, pb_query_words of them):
+ *   [ r | trace LDE row (width) | trace path (log_m x 8) | quotient row (8) | quotient path (log_m x 8) |
+ *     per FRI layer i: opened pair row (8), path ((log_m-1-i) x 8) ]
+ * pb_last_openings: the values opened at zeta, [(width + 8)][4] canonical. */
+int pb_query_words(size_t log_n, size_t width, size_t* words_per_query);
+int pb_query_segment(pb_ctx_t* ctx, size_t n_queries, uint32_t* h_out, size_t out_capacity_words);
+int pb_last_openings(pb_ctx_t* ctx, uint32_t* h_ys, size_t capacity_words);
+
 /* per-stage device milliseconds of the last pb_prove_segment: [h2d, lde, merkle, quotient, qlde, qmerkle, open, fri, total] */
 int pb_last_stage_ms(pb_ctx_t* ctx, float ms[9]);
 /* kernels launched by this context since creation (bench.py's gpu_launches) */

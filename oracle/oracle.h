@@ -99,6 +99,16 @@ typedef struct {
 void orc_prove_segment(const uint32_t* trace, unsigned log_n, size_t width, const uint32_t* bc, const orc_span_t* spans,
                        size_t n_constraints, orc_segment_proof_t* proof, double stage_seconds[8]);
 
+/* independent verifier of a segment proof + query openings (layout of pb_query_segment); 0 = accept, else the failed check:
+   1 alpha 2 zeta 3 openings root/gamma 4 beta 5 query index 6 trace path 7 quotient path 8 reduced opening != FRI layer 0
+   9 FRI path 10 fold consistency 11 final polynomial 12 constraint identity at zeta 20 malformed */
+int orc_verify_segment(const uint32_t* bc, const orc_span_t* spans, size_t n_constraints, unsigned log_n, size_t width,
+                       const orc_segment_proof_t* proof, const uint32_t* ys, const uint32_t* queries, size_t n_queries,
+                       int check_constraints);
+
+void orc_prove_segment_q(const uint32_t* trace, unsigned log_n, size_t width, const uint32_t* bc, const orc_span_t* spans,
+                         size_t n_constraints, orc_segment_proof_t* proof, double stage_seconds[8], uint32_t* ys_out,
+                         size_t n_queries, uint32_t* queries_out);
 int orc_num_threads(void);
 #ifdef __cplusplus
 }

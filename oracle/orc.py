@@ -15,7 +15,7 @@ GENERATOR = 31
 
 
 def build(force=False):
-    srcs = [os.path.join(_DIR, f) for f in ("ntt.c", "poseidon2.c", "air.c", "prove.c", "oracle.h", "bb31.h")]
+    srcs = [os.path.join(_DIR, f) for f in ("ntt.c", "poseidon2.c", "air.c", "prove.c", "verify.c", "oracle.h", "bb31.h")]
     if force or not os.path.exists(_SO) or any(os.path.getmtime(s) > os.path.getmtime(_SO) for s in srcs):
         subprocess.check_call(["make", "-C", _DIR, "-s"])
     return _SO
@@ -284,3 +284,50 @@ def prove_segment(trace, bc, spans):
     lib().orc_prove_segment(_p(t), C.c_uint(n.bit_length() - 1), C.c_size_t(w), _p(bc), compile_spans(spans),
                             C.c_size_t(len(spans)), C.byref(proof), st)
     return proof.as_dict(), list(st)[:6]
+
+
+def proof_struct(d):
+    """dict (as returned by prove_segment here or by powdr_b200.Context.prove_segment) -> SegmentProof ctypes struct"""
+    p = SegmentProof()
+    for k in ("trace_root", "quotient_root", "alpha", "zeta", "openings_root", "gamma"):
+        for i, v in enumerate(d[k]):
+            getattr(p, k)[i] = v
+    p.n_fri_layers = d["n_fri_layers"]
+    p.final_len = d["final_len"]
+    for i in range(d["n_fri_layers"]):
+        for j in range(8):
+            p.fri_roots[i][j] = d["fri_roots"][i][j]
+        for j in range(4):
+            p.fri_betas[i][j] = d["fri_betas"][i][j]
+    for i in range(d["final_len"]):
+        for j in range(4):
+            p.final_poly[i][j] = d["final_poly"][i][j]
+    return p
+
+
+def verify_segment(bc, spans, log_n, width, proof, ys, queries, check_constraints=False):
+    """0 = accept; see oracle.h for the failure codes"""
+    bc, ys, q = _u32(bc), _u32(ys), _u32(queries)
+    p = proof_struct(proof)
+    lib().orc_verify_segment.restype = C.c_int
+    return lib().orc_verify_segment(_p(bc), compile_spans(spans), C.c_size_t(len(spans)), C.c_uint(log_n), C.c_size_t(width),
+                                    C.byref(p), _p(ys), _p(q), C.c_size_t(q.shape[0]), C.c_int(1 if check_constraints else 0))
+
+
+def query_words(log_n, width):
+    log_m = log_n + 1
+    return 1 + width + 8 * log_m + 8 + 8 * log_m + sum(8 + 8 * (log_m - 1 - i) for i in range(log_n))
+
+
+def prove_segment_q(trace, bc, spans, n_queries):
+    """-> (proof dict, opened values (width+8, 4), query openings (n_queries, words))"""
+    t, bc = _u32(trace), _u32(bc)
+    w, n = t.shape
+    log_n = n.bit_length() - 1
+    proof = SegmentProof()
+    st = (C.c_double * 8)()
+    ys = np.empty((w + 8, 4), dtype=np.uint32)
+    q = np.empty((n_queries, query_words(log_n, w)), dtype=np.uint32)
+    lib().orc_prove_segment_q(_p(t), C.c_uint(log_n), C.c_size_t(w), _p(bc), compile_spans(spans), C.c_size_t(len(spans)),
+                              C.byref(proof), st, _p(ys), C.c_size_t(n_queries), _p(q))
+    return proof.as_dict(), ys, q

@@ -35,8 +35,40 @@ static void merkle_root_rowmajor(const uint32_t* mat, size_t width, unsigned log
     free(layer);
 }
 
+/* Merkle tree (all layers, node-major) of a row-major matrix; returns malloc'ed [2h-1][8] */
+static uint32_t* merkle_tree_rowmajor(const uint32_t* mat, size_t width, unsigned log_h) {
+    size_t h = (size_t)1 << log_h;
+    uint32_t* t = (uint32_t*)malloc(8 * (2 * h) * sizeof(uint32_t));
+#pragma omp parallel for schedule(static) if (h >= 2048)
+    for (long r = 0; r < (long)h; r++) orc_hash_row(mat + (size_t)r * width, width, t + 8 * (size_t)r);
+    uint32_t* prev = t;
+    for (size_t n = h >> 1; n >= 1; n >>= 1) {
+        uint32_t* cur = prev + 16 * n;
+#pragma omp parallel for schedule(static) if (n >= 2048)
+        for (long j = 0; j < (long)n; j++) orc_compress(prev + 16 * (size_t)j, prev + 16 * (size_t)j + 8, cur + 8 * (size_t)j);
+        prev = cur;
+        if (n == 1) break;
+    }
+    return t;
+}
+
+static void copy_path(const uint32_t* tree, unsigned log_h, size_t idx, uint32_t* out) {
+    for (unsigned k = 0; k < log_h; k++) {
+        size_t level_off = ((size_t)2 << log_h) - ((size_t)2 << (log_h - k));
+        memcpy(out + 8 * k, tree + 8 * (level_off + ((idx >> k) ^ 1)), 32);
+    }
+}
+
 void orc_prove_segment(const uint32_t* trace, unsigned log_n, size_t width, const uint32_t* bc, const orc_span_t* spans,
                        size_t n_constraints, orc_segment_proof_t* proof, double st[8]) {
+    orc_prove_segment_q(trace, log_n, width, bc, spans, n_constraints, proof, st, NULL, 0, NULL);
+}
+
+/* same, and additionally the opened values (ys_out, [(width+8)][4]) and n_queries query openings in the layout of
+   pb_query_segment (see include/powdr_b200.h) */
+void orc_prove_segment_q(const uint32_t* trace, unsigned log_n, size_t width, const uint32_t* bc, const orc_span_t* spans,
+                         size_t n_constraints, orc_segment_proof_t* proof, double st[8], uint32_t* ys_out, size_t n_queries,
+                         uint32_t* queries_out) {
     const unsigned log_blowup = 1;
     size_t n = (size_t)1 << log_n, m = n << log_blowup;
     unsigned log_m = log_n + log_blowup;
@@ -77,9 +109,9 @@ void orc_prove_segment(const uint32_t* trace, unsigned log_n, size_t width, cons
     double t4 = now_s();
     const uint32_t* mats2[2] = {qlde, qlde + 4 * m};
     size_t w2[2] = {4, 4};
-    orc_merkle_commit(mats2, w2, 2, log_m, layers);
-    memcpy(proof->quotient_root, layers + 8 * (2 * m - 2), 32);
-    free(layers);
+    uint32_t* layers_q = (uint32_t*)malloc((2 * m) * 8 * sizeof(uint32_t));
+    orc_merkle_commit(mats2, w2, 2, log_m, layers_q);
+    memcpy(proof->quotient_root, layers_q + 8 * (2 * m - 2), 32);
     double t5 = now_s();
     orc_challenger_observe(&ch, proof->quotient_root, 8);
     orc_challenger_sample_ext(&ch, proof->zeta);
@@ -106,19 +138,21 @@ void orc_prove_segment(const uint32_t* trace, unsigned log_n, size_t width, cons
         size_t w3[3] = {width, 4, 4};
         orc_deep_quotient(mats3, w3, 3, log_m, BB_GENERATOR, proof->zeta, proof->gamma, ys, f);
     }
+    if (ys_out) memcpy(ys_out, ys, 16 * n_open);
     free(ys);
-    free(lde);
-    free(qlde);
     unsigned log_len = log_m;
     uint32_t shift = BB_GENERATOR;
     uint32_t layer_i = 0;
+    uint32_t* words[32];
+    uint32_t* trees[32];
     while (log_len > log_blowup) {                       /* final_poly_len = 1 */
-        merkle_root_rowmajor(f, 8, log_len - 1, proof->fri_roots[layer_i]);
+        words[layer_i] = f;
+        trees[layer_i] = merkle_tree_rowmajor(f, 8, log_len - 1);
+        memcpy(proof->fri_roots[layer_i], trees[layer_i] + 8 * (((size_t)2 << (log_len - 1)) - 2), 32);
         orc_challenger_observe(&ch, proof->fri_roots[layer_i], 8);
         orc_challenger_sample_ext(&ch, proof->fri_betas[layer_i]);
         uint32_t* nf = (uint32_t*)malloc(4 * ((size_t)1 << (log_len - 1)) * sizeof(uint32_t));
         orc_fri_fold(f, log_len, shift, proof->fri_betas[layer_i], nf);
-        free(f);
         f = nf;
         shift = bb_mul(shift, shift);
         log_len--;
@@ -128,6 +162,37 @@ void orc_prove_segment(const uint32_t* trace, unsigned log_n, size_t width, cons
     proof->final_len = 1u << log_len;
     memcpy(proof->final_poly, f, 16 * proof->final_len);
     free(f);
+    /* query phase */
+    if (n_queries && queries_out) {
+        size_t wpq = 1 + width + 8 * log_m + 8 + 8 * log_m;
+        for (unsigned i = 0; i < layer_i; i++) wpq += 8 + 8 * (log_m - 1 - i);
+        for (size_t qi = 0; qi < n_queries; qi++) {
+            uint32_t* o = queries_out + qi * wpq;
+            size_t r = orc_challenger_sample(&ch) & (((size_t)1 << log_m) - 1);
+            *o++ = (uint32_t)r;
+            for (size_t c = 0; c < width; c++) o[c] = lde[c * m + r];
+            o += width;
+            copy_path(layers, log_m, r, o);
+            o += 8 * log_m;
+            for (size_t c = 0; c < 8; c++) o[c] = qlde[c * m + r];
+            o += 8;
+            copy_path(layers_q, log_m, r, o);
+            o += 8 * log_m;
+            for (unsigned i = 0; i < layer_i; i++) {
+                unsigned lh = log_m - 1 - i;
+                size_t j = r >> (i + 1);
+                memcpy(o, words[i] + 8 * j, 32);
+                o += 8;
+                copy_path(trees[i], lh, j, o);
+                o += 8 * lh;
+            }
+        }
+    }
+    for (unsigned i = 0; i < layer_i; i++) { free(words[i]); free(trees[i]); }
+    free(lde);
+    free(qlde);
+    free(layers);
+    free(layers_q);
     double t6 = now_s();
     st[0] = t1 - t0; st[1] = t2 - t1; st[2] = t3 - t2; st[3] = t4 - t3; st[4] = t5 - t4; st[5] = t6 - t5;
 }

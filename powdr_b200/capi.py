@@ -15,7 +15,7 @@ EXPORTS = [
     "pb_ctx_create", "pb_ctx_destroy", "pb_ctx_synchronize", "pb_ctx_set_poseidon2", "pb_host_alloc", "pb_host_free",
     "pb_device_alloc", "pb_device_free", "pb_copy_h2d", "pb_copy_d2h", "pb_memset_zero", "pb_to_monty", "pb_from_monty",
     "pb_lde_batch", "pb_air_compile", "pb_air_free", "pb_air_is_jit", "pb_air_jit_compile_only", "pb_quotient", "pb_constraint_fold", "pb_merkle_commit",
-    "pb_merkle_commit_rows8", "pb_poseidon2_permute", "pb_fri_fold", "pb_eval_at_point", "pb_deep_quotient", "pb_prove_segment", "pb_last_stage_ms",
+    "pb_merkle_commit_rows8", "pb_poseidon2_permute", "pb_fri_fold", "pb_eval_at_point", "pb_deep_quotient", "pb_prove_segment", "pb_query_words", "pb_query_segment", "pb_last_openings", "pb_last_stage_ms",
     "pb_launch_count", "pb_leaf_kernel_profile", "_apc_tracegen", "_apc_apply_derived_expr", "_apc_apply_bus",
 ]
 
@@ -252,6 +252,16 @@ class Context:
         _chk(self.lib.pb_prove_segment(self.h, air.h, C.c_void_p(trace_ptr), C.c_size_t(log_n), C.c_size_t(width),
                                        C.c_uint32(1 if on_device else 0), C.byref(proof)), "pb_prove_segment")
         return proof.as_dict()
+
+    def query_segment(self, log_n, width, n_queries):
+        """-> (n_queries, words_per_query) uint32 array of openings for the last prove_segment, and the opened values (width+8, 4)"""
+        wpq = C.c_size_t()
+        _chk(self.lib.pb_query_words(C.c_size_t(log_n), C.c_size_t(width), C.byref(wpq)), "pb_query_words")
+        out = np.empty((n_queries, wpq.value), dtype=np.uint32)
+        _chk(self.lib.pb_query_segment(self.h, C.c_size_t(n_queries), out.ctypes.data_as(C.c_void_p), C.c_size_t(out.size)), "pb_query_segment")
+        ys = np.empty((width + 8, 4), dtype=np.uint32)
+        _chk(self.lib.pb_last_openings(self.h, ys.ctypes.data_as(C.c_void_p), C.c_size_t(ys.size)), "pb_last_openings")
+        return out, ys
 
     def last_stage_ms(self):
         ms = (C.c_float * 9)()

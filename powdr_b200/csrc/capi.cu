@@ -171,6 +171,16 @@ struct pb_ctx {
     DevBuf<uint4> ws_w, ws_part;          // barycentric weights [N], per-CTA partial sums of the openings
     DevBuf<uint2> ws_gp;                  // Shoup pairs of the gamma powers of the reduced opening
     DevBuf<const uint32_t*> coltab2;
+    DevBuf<uint32_t> ws_layers_q, ws_layers_open, ws_fri_words, ws_fri_trees, ws_qidx, ws_qout;
+    // what pb_query_segment needs from the last pb_prove_segment (everything stays resident on the device)
+    struct {
+        bool valid = false;
+        size_t log_n = 0, log_m = 0, width = 0;
+        uint32_t n_layers = 0;
+        size_t word_off[32] = {0}, tree_off[32] = {0};
+        Challenger ch;                       // transcript state after the FRI commit phase
+        std::vector<uint32_t> ys;            // opened values, Montgomery, [(width + 8)][4]
+    } seg;
     cudaStream_t copy_stream = nullptr;   // H2D chunks of the host-input pipeline
     cudaEvent_t ev_copy[2] = {nullptr}, ev_free[2] = {nullptr};
     cudaEvent_t ev[10] = {nullptr};
@@ -430,6 +440,7 @@ int pb_lde_batch(pb_ctx_t* ctx, const uint32_t* d_trace, size_t log_n, size_t wi
         if (const char* e = getenv("PB_LDE_BATCH")) batch = std::max<size_t>(1, (size_t)atol(e));
     }
     batch = std::min<size_t>(std::min<size_t>(batch, width), 32768);
+    batch = (width + (width + batch - 1) / batch - 1) / ((width + batch - 1) / batch);     // equal-sized batches (no runt batch)
     rc = ctx->tmp.ensure(batch * N); if (rc) return rc;
     rc = ctx->tmp2.ensure(batch * N * cosets); if (rc) return rc;
     const size_t smem_hi = (size_t)4 << (n_hi + log_lc_hi);
@@ -870,9 +881,10 @@ int pb_prove_segment(pb_ctx_t* ctx, const pb_air_t* a, const uint32_t* trace, si
     CK(cudaEventRecord(ctx->ev[5], st));
     const uint32_t* mats2[2] = {ctx->ws_qlde.p, ctx->ws_qlde.p + 4 * M};
     const size_t w2[2] = {4, 4};
-    RC(pb_merkle_commit(ctx, mats2, w2, 2, log_m, ctx->ws_layers.p, nullptr));
+    RC(ctx->ws_layers_q.ensure(8 * (2 * M)));
+    RC(pb_merkle_commit(ctx, mats2, w2, 2, log_m, ctx->ws_layers_q.p, nullptr));
     CK(cudaEventRecord(ctx->ev[6], st));
-    RC(read_root(ctx, ctx->ws_layers.p, log_m, root_m));
+    RC(read_root(ctx, ctx->ws_layers_q.p, log_m, root_m));
     for (int i = 0; i < 8; i++) proof->quotient_root[i] = h_from_m(root_m[i]);
     ch.observe(root_m, 8);
     const bb::E4 zeta = ch.sample_ext();
@@ -891,10 +903,12 @@ int pb_prove_segment(pb_ctx_t* ctx, const pb_air_t* a, const uint32_t* trace, si
         RC(eval_at_point_m(ctx, ctx->ws_qnat.p, log_n, 4, h_to_m(g_c), zeta, ctx->ws_ys.p + 4 * width));
         RC(eval_at_point_m(ctx, ctx->ws_qnat.p + 4 * N, log_n, 4, h_to_m(gw_c), zeta, ctx->ws_ys.p + 4 * (width + 4)));
     }
-    RC(pb_merkle_commit_rows8(ctx, ctx->ws_ys.p, log_open_rows, ctx->ws_layers.p, nullptr));
-    std::vector<uint32_t> ys_h(4 * n_open);
+    RC(ctx->ws_layers_open.ensure(8 * (2 * open_rows)));
+    RC(pb_merkle_commit_rows8(ctx, ctx->ws_ys.p, log_open_rows, ctx->ws_layers_open.p, nullptr));
+    std::vector<uint32_t>& ys_h = ctx->seg.ys;
+    ys_h.assign(4 * n_open, 0u);
     CK(cudaMemcpyAsync(ys_h.data(), ctx->ws_ys.p, 16 * n_open, cudaMemcpyDeviceToHost, st));
-    RC(read_root(ctx, ctx->ws_layers.p, log_open_rows, root_m));
+    RC(read_root(ctx, ctx->ws_layers_open.p, log_open_rows, root_m));
     for (int i = 0; i < 8; i++) proof->openings_root[i] = h_from_m(root_m[i]);
     ch.observe(root_m, 8);
     const bb::E4 gamma = ch.sample_ext();
@@ -905,27 +919,38 @@ int pb_prove_segment(pb_ctx_t* ctx, const pb_air_t* a, const uint32_t* trace, si
         std::vector<const uint32_t*> cols(n_open);
         for (size_t c = 0; c < width; c++) cols[c] = ctx->ws_lde.p + c * M;
         for (size_t c = 0; c < 8; c++) cols[width + c] = ctx->ws_qlde.p + c * M;
-        RC(deep_quotient_m(ctx, cols, log_m, h_to_m(bb::GEN), zeta, gamma, ys_h.data(), ctx->ws_f0.p));
+        // every FRI codeword and every layer tree stays resident (back to back) for the query phase
+        RC(ctx->ws_fri_words.ensure(8 * M + 64));
+        RC(ctx->ws_fri_trees.ensure(8 * (2 * M)));
+        RC(deep_quotient_m(ctx, cols, log_m, h_to_m(bb::GEN), zeta, gamma, ys_h.data(), ctx->ws_fri_words.p));
     }
     CK(cudaEventRecord(ctx->ev[8], st));
-    uint32_t* f = ctx->ws_f0.p;
-    uint32_t* g = ctx->ws_f1.p;
-    size_t log_len = log_m;
+    uint32_t* f = ctx->ws_fri_words.p;
+    size_t log_len = log_m, word_off = 0, tree_off = 0;
     uint32_t shift_m = h_to_m(bb::GEN);
     uint32_t layer = 0;
     while (log_len > log_blowup) {
-        RC(pb_merkle_commit_rows8(ctx, f, log_len - 1, ctx->ws_layers.p, nullptr));
-        RC(read_root(ctx, ctx->ws_layers.p, log_len - 1, root_m));
+        uint32_t* tree = ctx->ws_fri_trees.p + tree_off;
+        ctx->seg.word_off[layer] = word_off;
+        ctx->seg.tree_off[layer] = tree_off;
+        RC(pb_merkle_commit_rows8(ctx, f, log_len - 1, tree, nullptr));
+        RC(read_root(ctx, tree, log_len - 1, root_m));
         for (int i = 0; i < 8; i++) proof->fri_roots[layer][i] = h_from_m(root_m[i]);
         ch.observe(root_m, 8);
         bb::E4 beta = ch.sample_ext();
         for (int i = 0; i < 4; i++) proof->fri_betas[layer][i] = h_from_m(beta.c[i]);
+        uint32_t* g = f + ((size_t)4 << log_len);
         RC(fri_fold_m(ctx, f, log_len, shift_m, beta, g));
-        std::swap(f, g);
+        word_off += (size_t)4 << log_len;
+        tree_off += 8 * (((size_t)2 << (log_len - 1)) - 1);
+        f = g;
         shift_m = bb::mul(shift_m, shift_m);
         log_len--;
         layer++;
     }
+    ctx->seg.valid = true;
+    ctx->seg.log_n = log_n; ctx->seg.log_m = log_m; ctx->seg.width = width; ctx->seg.n_layers = layer;
+    ctx->seg.ch = ch;
     proof->n_fri_layers = layer;
     proof->final_len = 1u << log_len;
     uint32_t fin[8 * 4];
@@ -939,6 +964,52 @@ int pb_prove_segment(pb_ctx_t* ctx, const pb_air_t* a, const uint32_t* trace, si
     cudaEventElapsedTime(&ctx->stage_ms[7], ctx->ev[8], ctx->ev[7]);     // FRI commit phase
     cudaEventElapsedTime(&ctx->stage_ms[8], ctx->ev[0], ctx->ev[7]);
 #undef RC
+    return 0;
+}
+
+// query phase of the last pb_prove_segment: indices from the transcript (sample_bits(log_m) each), openings gathered on the device
+static size_t query_words(size_t log_n, size_t width) {
+    const size_t log_m = log_n + 1, layers = log_n;      // log_blowup 1, final_poly_len 1
+    size_t w = 1 + width + 8 * log_m + 8 + 8 * log_m;
+    for (size_t i = 0; i < layers; i++) w += 8 + 8 * (log_m - 1 - i);
+    return w;
+}
+
+int pb_query_words(size_t log_n, size_t width, size_t* words_per_query) {
+    if (!words_per_query || log_n < 1 || log_n > 24) return PB_ERR_INVALID_ARG;
+    *words_per_query = query_words(log_n, width);
+    return 0;
+}
+
+int pb_query_segment(pb_ctx_t* ctx, size_t n_queries, uint32_t* h_out, size_t out_capacity_words) {
+    if (!ctx || !h_out || !n_queries) return PB_ERR_INVALID_ARG;
+    if (!ctx->seg.valid) return PB_ERR_INVALID_ARG;
+    const size_t wpq = query_words(ctx->seg.log_n, ctx->seg.width);
+    if (out_capacity_words < wpq * n_queries) return PB_ERR_INVALID_ARG;
+    int rc;
+    std::vector<uint32_t> idx(n_queries);
+    Challenger ch = ctx->seg.ch;
+    for (size_t q = 0; q < n_queries; q++) idx[q] = h_from_m(ch.sample()) & (uint32_t)(((size_t)1 << ctx->seg.log_m) - 1);
+    if ((rc = ctx->ws_qidx.ensure(n_queries))) return rc;
+    if ((rc = ctx->ws_qout.ensure(wpq * n_queries))) return rc;
+    CK(cudaMemcpyAsync(ctx->ws_qidx.p, idx.data(), 4 * n_queries, cudaMemcpyHostToDevice, ctx->stream));
+    fri::QueryDesc d;
+    d.lde = ctx->ws_lde.p; d.qlde = ctx->ws_qlde.p; d.tree_t = ctx->ws_layers.p; d.tree_q = ctx->ws_layers_q.p;
+    d.fri_words = ctx->ws_fri_words.p; d.fri_trees = ctx->ws_fri_trees.p;
+    d.m = (size_t)1 << ctx->seg.log_m; d.width = (uint32_t)ctx->seg.width; d.log_m = (int)ctx->seg.log_m; d.n_layers = (int)ctx->seg.n_layers;
+    for (int i = 0; i < 32; i++) { d.word_off[i] = ctx->seg.word_off[i]; d.tree_off[i] = ctx->seg.tree_off[i]; }
+    fri::gather_queries_kernel<<<(unsigned)n_queries, 256, 0, ctx->stream>>>(d, ctx->ws_qidx.p, ctx->ws_qout.p, wpq);
+    LAUNCHED(ctx);
+    CK(cudaGetLastError());
+    CK(cudaMemcpyAsync(h_out, ctx->ws_qout.p, 4 * wpq * n_queries, cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    return 0;
+}
+
+// opened values of the last pb_prove_segment, canonical, [(width + 8)][4]
+int pb_last_openings(pb_ctx_t* ctx, uint32_t* h_ys, size_t capacity_words) {
+    if (!ctx || !h_ys || !ctx->seg.valid || capacity_words < ctx->seg.ys.size()) return PB_ERR_INVALID_ARG;
+    for (size_t i = 0; i < ctx->seg.ys.size(); i++) h_ys[i] = h_from_m(ctx->seg.ys[i]);
     return 0;
 }
 

@@ -33,3 +33,60 @@ __global__ void __launch_bounds__(256) combine_chunks_kernel(const uint32_t* __r
 }
 
 }  // namespace fri
+
+// ---------------- query phase: gather the openings a verifier needs for each sampled index ----------------
+// One CTA per query.  Output (canonical words) per query:
+//   [ r | trace row (W) | trace path (log_m x 8) | quotient row (8) | quotient path (log_m x 8) |
+//     per FRI layer i: pair row (8), path ((log_m-1-i) x 8) ]
+// Merkle trees are node-major with level k at node offset 2^(h+1) - 2^(h-k+1); the sibling of leaf idx at level k is (idx>>k)^1.
+namespace fri {
+
+struct QueryDesc {
+    const uint32_t* lde;        // trace LDE, column-major [W][M]
+    const uint32_t* qlde;       // quotient chunk LDEs, column-major [8][M]
+    const uint32_t* tree_t;     // digest layers of the trace commitment
+    const uint32_t* tree_q;     // digest layers of the quotient commitment
+    const uint32_t* fri_words;  // all FRI codewords back to back (layer i at word_off[i])
+    const uint32_t* fri_trees;  // all FRI layer trees back to back (layer i at tree_off[i], in words)
+    size_t m;
+    uint32_t width;
+    int log_m;
+    int n_layers;
+    size_t word_off[32];
+    size_t tree_off[32];
+};
+
+__device__ __forceinline__ void copy_path(const uint32_t* tree, int log_h, size_t idx, uint32_t* out) {
+    for (int k = 0; k < log_h; k++) {
+        const size_t level_off = ((size_t)2 << log_h) - ((size_t)2 << (log_h - k));
+        const uint32_t* node = tree + 8 * (level_off + ((idx >> k) ^ 1));
+        for (int e = threadIdx.x; e < 8; e += blockDim.x) out[8 * k + e] = bb::from_monty(node[e]);
+    }
+}
+
+__global__ void __launch_bounds__(256) gather_queries_kernel(QueryDesc d, const uint32_t* __restrict__ indices, uint32_t* __restrict__ out,
+                                                             size_t words_per_query) {
+    const size_t r = indices[blockIdx.x];
+    uint32_t* o = out + (size_t)blockIdx.x * words_per_query;
+    if (threadIdx.x == 0) o[0] = (uint32_t)r;
+    o += 1;
+    for (uint32_t c = threadIdx.x; c < d.width; c += blockDim.x) o[c] = bb::from_monty(d.lde[(size_t)c * d.m + r]);
+    o += d.width;
+    copy_path(d.tree_t, d.log_m, r, o);
+    o += 8 * d.log_m;
+    for (uint32_t c = threadIdx.x; c < 8; c += blockDim.x) o[c] = bb::from_monty(d.qlde[(size_t)c * d.m + r]);
+    o += 8;
+    copy_path(d.tree_q, d.log_m, r, o);
+    o += 8 * d.log_m;
+    for (int i = 0; i < d.n_layers; i++) {
+        const int log_h = d.log_m - 1 - i;
+        const size_t j = r >> (i + 1);
+        const uint32_t* row = d.fri_words + d.word_off[i] + 8 * j;
+        for (uint32_t e = threadIdx.x; e < 8; e += blockDim.x) o[e] = bb::from_monty(row[e]);
+        o += 8;
+        copy_path(d.fri_trees + d.tree_off[i], log_h, j, o);
+        o += 8 * log_h;
+    }
+}
+
+}  // namespace fri

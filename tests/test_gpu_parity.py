@@ -370,3 +370,41 @@ def test_reduced_opening_is_low_degree_at_scale(ctx):
     got = ctx.prove_segment(air, d.ptr, log_n, mach.width, on_device=True)
     assert got["final_len"] == 2 and got["final_poly"][0] == got["final_poly"][1]
     assert got["final_poly"][0] != [0, 0, 0, 0]
+
+
+# ---------------------------------------------------------------- query phase + independent verification
+@pytest.mark.parametrize("log_n,width,ncons", [(5, 7, 3), (11, 30, 8)])
+def test_gpu_proof_and_queries_match_oracle_and_verify(ctx, orc, log_n, width, ncons):
+    mach = _machine().synthetic_machine(width, ncons, seed=17)
+    air, bc, spans = _compile(ctx, mach)
+    trace = rand_field(np.random.default_rng(83), (mach.width, 1 << log_n))
+    d = ctx.to_device(trace)
+    proof = ctx.prove_segment(air, d.ptr, log_n, mach.width, on_device=True)
+    queries, ys = ctx.query_segment(log_n, mach.width, 12)
+    exp_proof, exp_ys, exp_q = orc.prove_segment_q(trace, bc, spans, 12)
+    assert proof == exp_proof and (ys == exp_ys).all() and (queries == exp_q).all()
+    assert orc.verify_segment(bc, spans, log_n, mach.width, proof, ys, queries) == 0
+
+
+def test_gpu_proof_of_a_satisfying_trace_verifies_with_the_constraint_identity(ctx, orc):
+    """the reference's own notion of correctness: the GPU engine's proof verifies under the CPU verifier"""
+    from powdr_b200 import machine as M
+    mach = M.SymbolicMachine([["b@0", "*", ["b@0", "-", 1]], [["b@0", "*", "c@1"], "-", "d@2"]])
+    air, bc, spans = _compile(ctx, mach)
+    log_n = 14
+    rng = np.random.default_rng(89)
+    b = rng.integers(0, 2, 1 << log_n).astype(np.uint32)
+    c = rand_field(rng, 1 << log_n)
+    dd = (b.astype(np.uint64) * c % P).astype(np.uint32)
+    trace = np.stack([b, c, dd])
+    dev = ctx.to_device(trace)
+    proof = ctx.prove_segment(air, dev.ptr, log_n, 3, on_device=True)
+    queries, ys = ctx.query_segment(log_n, 3, 30)
+    assert orc.verify_segment(bc, spans, log_n, 3, proof, ys, queries, check_constraints=True) == 0
+    trace[1, 5] = (int(trace[1, 5]) + 1) % P if b[5] else trace[1, 5]
+    trace[2, 9] = (int(trace[2, 9]) + 1) % P
+    dev = ctx.to_device(trace)
+    proof = ctx.prove_segment(air, dev.ptr, log_n, 3, on_device=True)
+    queries, ys = ctx.query_segment(log_n, 3, 30)
+    assert orc.verify_segment(bc, spans, log_n, 3, proof, ys, queries, check_constraints=False) == 0
+    assert orc.verify_segment(bc, spans, log_n, 3, proof, ys, queries, check_constraints=True) == 12

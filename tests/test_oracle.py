@@ -281,3 +281,46 @@ def test_segment_reduced_opening_folds_to_a_constant(orc):
     proof, _ = orc.prove_segment(trace, bc, spans)
     assert proof["final_len"] == 2 and proof["final_poly"][0] == proof["final_poly"][1]
     assert proof["n_fri_layers"] == 7
+
+
+# ---- the oracle's verifier (validity is how the reference itself pins its prover: openvm-riscv/src/lib.rs:337-341) ----
+def _bool_machine():
+    from powdr_b200 import machine as M
+    return M.SymbolicMachine([["b@0", "*", ["b@0", "-", 1]], [["b@0", "*", "c@1"], "-", "d@2"]])
+
+
+def test_verifier_accepts_honest_and_rejects_tampered(orc):
+    from powdr_b200 import machine as M
+    mach = M.synthetic_machine(10, 4, seed=21)
+    bc, spans = M.compile_constraints(mach)
+    trace = rand_field(np.random.default_rng(79), (mach.width, 1 << 7))
+    proof, ys, q = orc.prove_segment_q(trace, bc, spans, 6)
+    assert proof == orc.prove_segment(trace, bc, spans)[0]
+    assert orc.verify_segment(bc, spans, 7, mach.width, proof, ys, q) == 0
+    q2 = q.copy(); q2[2, 5] ^= 1
+    assert orc.verify_segment(bc, spans, 7, mach.width, proof, ys, q2) == 6          # trace row no longer matches its path
+    q3 = q.copy(); q3[0, -3] ^= 1
+    assert orc.verify_segment(bc, spans, 7, mach.width, proof, ys, q3) == 9          # FRI layer path
+    q4 = q.copy(); q4[1, 1 + mach.width + 8 * 8 + 8 + 8 * 8 + 2] ^= 1               # a layer-0 pair value
+    assert orc.verify_segment(bc, spans, 7, mach.width, proof, ys, q4) in (8, 9, 10)
+    ys2 = ys.copy(); ys2[3, 1] = (int(ys2[3, 1]) + 1) % P
+    assert orc.verify_segment(bc, spans, 7, mach.width, proof, ys2, q) == 3          # opened values are bound by the transcript
+    bad = dict(proof); bad["final_poly"] = [[1, 2, 3, 4], [1, 2, 3, 4]]
+    assert orc.verify_segment(bc, spans, 7, mach.width, bad, ys, q) == 11
+
+
+def test_verifier_constraint_identity_on_satisfying_and_unsatisfying_traces(orc):
+    from powdr_b200 import machine as M
+    mach = _bool_machine()
+    bc, spans = M.compile_constraints(mach)
+    rng = np.random.default_rng(5)
+    b = rng.integers(0, 2, 128).astype(np.uint32)
+    c = rand_field(rng, 128)
+    d = (b.astype(np.uint64) * c % P).astype(np.uint32)
+    trace = np.stack([b, c, d])
+    proof, ys, q = orc.prove_segment_q(trace, bc, spans, 5)
+    assert orc.verify_segment(bc, spans, 7, 3, proof, ys, q, check_constraints=True) == 0
+    trace[2, 17] = (int(trace[2, 17]) + 1) % P                                       # one bad cell
+    proof, ys, q = orc.prove_segment_q(trace, bc, spans, 5)
+    assert orc.verify_segment(bc, spans, 7, 3, proof, ys, q, check_constraints=False) == 0    # the PCS part is still sound
+    assert orc.verify_segment(bc, spans, 7, 3, proof, ys, q, check_constraints=True) == 12
