@@ -38,6 +38,9 @@ def parse():
     ap.add_argument("--cpu-sample-log-n", type=int, default=15)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--workload", default="keccak", choices=["keccak", "multichip"],
+                    help="keccak: one APC chip per segment (the BASELINE metric); multichip: 50 independent chips of one segment "
+                         "sharded over the ranks by LPT (BASELINE.json configs[3] shape, strong scaling)")
     return ap.parse_args()
 
 
@@ -266,9 +269,105 @@ def run_native(a):
     ctx.close()
 
 
+def multichip_shapes():
+    """50 synthetic chips shaped like the guest-ecrecover APC set: widths sum to 18508, constraints to 10511
+    (/root/reference/openvm-riscv/src/lib.rs:1332-1339); heights 2^12..2^18 by decreasing width rank (deterministic)."""
+    s = [0xEC0EC0]
+
+    def rnd():
+        s[0] = (s[0] * 6364136223846793005 + 1442695040888963407) & (2**64 - 1)
+        return (s[0] >> 33) / float(1 << 31)
+
+    raw = sorted((2.718281828 ** (4.5 + 1.2 * (rnd() + rnd() + rnd() - 1.5)) for _ in range(50)), reverse=True)
+    tot = sum(raw)
+    widths = [max(8, int(round(x / tot * 18508))) for x in raw]
+    widths[0] += 18508 - sum(widths)
+    cons = [max(2, int(round(w * 10511 / 18508))) for w in widths]
+    logs = [18 - (i * 7) // 50 for i in range(50)]          # widest chips are also the tallest: 2^18 ... 2^12
+    return list(zip(logs, widths, cons))
+
+
+def run_multichip(a):
+    """strong scaling of ONE multi-chip segment: chips are independent until the transcript, so they are sharded by LPT
+    on height*width; each rank proves its chips back to back; one all-gather of the per-chip Merkle caps ends the step."""
+    import torch
+    import powdr_b200
+    from powdr_b200 import machine as M, parallel
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=dev)
+    stream = torch.cuda.current_stream()
+    ctx = powdr_b200.Context(local, stream.cuda_stream)
+    shapes = multichip_shapes()
+    costs = [w * (1 << ln) for ln, w, _ in shapes]
+    plan = parallel.lpt_assign(costs, world)
+    mine = plan[rank]
+    kmax = max(len(p) for p in plan)
+    chips = []
+    for i in mine:
+        ln, w, c = shapes[i]
+        mach = M.synthetic_machine(w, c, seed=0xEC000 + i)
+        bc, spans = M.compile_constraints(mach)
+        air = ctx.air(bc, spans, mach.width)
+        gen = torch.Generator(device=dev)
+        gen.manual_seed(0xEC100 + i)
+        chips.append((ln, mach.width, air, torch.randint(0, P, (mach.width, 1 << ln), dtype=torch.int32, device=dev, generator=gen)))
+    caps = torch.zeros((kmax, 8), dtype=torch.int32, device=dev)
+
+    def step():
+        roots = []
+        for ln, w, air, tr in chips:
+            roots.append(ctx.prove_segment(air, tr.data_ptr(), ln, w, on_device=True)["trace_root"])
+        if roots:
+            caps[:len(roots)].copy_(torch.tensor(roots, dtype=torch.int64).to(torch.int32), non_blocking=True)
+        parallel.all_gather_caps(caps, dist)
+
+    def sync_all():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+            torch.cuda.synchronize()
+
+    for _ in range(a.warmup):
+        step()
+    sync_all()
+    l0 = ctx.launch_count()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record(stream)
+    for _ in range(a.steps):
+        step()
+    e1.record(stream)
+    sync_all()
+    t = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms = float(t.item()) / a.steps
+    if rank == 0:
+        mx, mean = parallel.plan_summary(costs, world)
+        print(json.dumps({
+            "metric": "proof-gen sec for a 50-chip APC segment (ecrecover-shaped), chips sharded over GPUs", "value": ms / 1e3, "unit": "s",
+            "n_gpus": world, "steps": a.steps, "warmup": a.warmup, "ms_per_step": ms, "higher_is_better": False, "scaling": "strong",
+            "vs_baseline": None, "dtype": "u32 (BabyBear, Montgomery)", "data": "synthetic",
+            "config": {"workload": "50 chips, widths sum 18508, constraints sum 10511, heights 2^12..2^18; LPT by height*width",
+                       "lpt_max_over_mean": mx / mean, "chips_per_rank": [len(p) for p in plan]},
+            "gpu_launches": ctx.launch_count() - l0}))
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+    ctx.close()
+
+
 if __name__ == "__main__":
     args = parse()
     if args.impl == "reference":
         run_reference(args)
+    elif args.workload == "multichip":
+        run_multichip(args)
     else:
         run_native(args)
