@@ -255,7 +255,13 @@ int get_twiddles(pb_ctx* ctx, int n, int log_blowup, uint32_t shift, const Twidd
     CK(cudaMemcpyAsync(t.d_inv, inv.data(), N * sizeof(uint2), cudaMemcpyHostToDevice, ctx->stream));
     CK(cudaMemcpyAsync(t.d_fwd, fwd.data(), N * cosets * sizeof(uint2), cudaMemcpyHostToDevice, ctx->stream));
     CK(cudaStreamSynchronize(ctx->stream));
-    if (ctx->tws.size() >= 12) {   // bounded cache
+    // bounded cache: a multi-chip segment cycles through (height, shift) pairs -- 3 shifts per height -- so keep them all
+    // unless the tables get large (FIFO eviction above 64 sets or 4 GiB)
+    auto bytes_of = [](const TwiddleSet& s) { return (((size_t)1 << s.n) * ((size_t)1 + ((size_t)1 << s.log_blowup))) * sizeof(uint2); };
+    size_t total = bytes_of(t);
+    for (auto& s : ctx->tws) total += bytes_of(s);
+    while (!ctx->tws.empty() && (ctx->tws.size() >= 64 || total > ((size_t)4 << 30))) {
+        total -= bytes_of(ctx->tws.front());
         cudaFree(ctx->tws.front().d_inv);
         cudaFree(ctx->tws.front().d_fwd);
         ctx->tws.erase(ctx->tws.begin());
