@@ -38,6 +38,7 @@ def parse():
     ap.add_argument("--cpu-sample-log-n", type=int, default=15)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-sharded", action="store_true", help="skip the one-segment-on-all-GPUs (strong scaling) measurement at N > 1")
     ap.add_argument("--workload", default="keccak", choices=["keccak", "multichip"],
                     help="keccak: one APC chip per segment (the BASELINE metric); multichip: 50 independent chips of one segment "
                          "sharded over the ranks by LPT (BASELINE.json configs[3] shape, strong scaling)")
@@ -228,6 +229,10 @@ def run_native(a):
                "d2h_bytes_per_step": (16 + 4 + 12 * proof["n_fri_layers"] + 4 * proof["final_len"]) * 4 * world,
                "stages_ms": ctx.last_stage_ms()}
 
+    sharded = None
+    if world > 1 and not a.no_sharded:
+        sharded = sharded_segment(a, ctx, air, dist, dev, stream, world, rank)
+
     if rank == 0:
         peaks = {}
         try:
@@ -260,6 +265,8 @@ def run_native(a):
         }
         if e2e:
             out["e2e"] = e2e
+        if sharded:
+            out["one_segment_on_all_gpus"] = sharded
         if world == 1 and not a.no_cpu_baseline:
             out["cpu_baseline"] = cpu_baseline(a, mach, bc, spans)
         print(json.dumps(out))
@@ -267,6 +274,66 @@ def run_native(a):
         dist.barrier()
         dist.destroy_process_group()
     ctx.close()
+
+
+def sharded_segment(a, ctx, air, dist, dev, stream, world, rank):
+    """Strong scaling of ONE segment: the N ranks prove the same segment together (pb_prove_segment_sharded: column-sharded
+    trace in, one all-to-all of folded coefficients, row-sharded LDE / Merkle / quotient / FRI; NCCL through
+    powdr_b200.sharded.TorchComm).  Reported next to the weak-scaling headline; the proof is checked against the
+    single-GPU proof of the same trace on every rank."""
+    import torch
+    from powdr_b200.sharded import TorchComm, shard_columns
+    n, w = 1 << a.log_n, air.width
+    gen = torch.Generator(device=dev)
+    gen.manual_seed(0xB2000000)                                   # the same trace on every rank
+    full = torch.randint(0, P, (w, n), dtype=torch.int32, device=dev, generator=gen)
+    single = ctx.prove_segment(air, full.data_ptr(), a.log_n, w, on_device=True)
+    single_ms = ctx.last_stage_ms()["total"]
+    first, count = shard_columns(w, world, rank)
+    mine = full[first:first + count].clone()
+    del full
+    torch.cuda.empty_cache()
+    comm = TorchComm()
+
+    def sync_all():
+        torch.cuda.synchronize()
+        dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(fn):
+        for _ in range(max(2, min(3, a.warmup))):
+            fn()
+        sync_all()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        t0 = time.time()
+        e0.record(stream)
+        for _ in range(a.steps):
+            pr = fn()
+        e1.record(stream)
+        sync_all()
+        wall = (time.time() - t0) / a.steps
+        t = torch.tensor([max(e0.elapsed_time(e1) / 1e3 / a.steps, wall)], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item()), pr
+
+    sec, proof = timed(lambda: ctx.prove_segment_sharded(air, mine.data_ptr() if count else 0, a.log_n, w, comm, on_device=True))
+    stages = ctx.last_stage_ms()
+    calls, nbytes = comm.calls, comm.bytes
+    ok = torch.tensor([1 if proof == single else 0], dtype=torch.int32, device=dev)
+    dist.all_reduce(ok, op=dist.ReduceOp.MIN)
+    out = {"value": sec, "unit": "s", "scaling": "strong", "single_gpu_s": single_ms / 1e3, "speedup": single_ms / 1e3 / sec,
+           "proof_equals_single_gpu": bool(ok.item()), "stages_ms": stages,
+           "collectives_per_segment": calls // max(1, a.steps + max(2, min(3, a.warmup))),
+           "collective_bytes_per_rank_per_segment": nbytes // max(1, a.steps + max(2, min(3, a.warmup)))}
+    if not a.no_e2e:
+        host = torch.empty((max(1, count), n), dtype=torch.int32, pin_memory=True)
+        if count:
+            host.copy_(mine)
+        torch.cuda.synchronize()
+        esec, eproof = timed(lambda: ctx.prove_segment_sharded(air, host.data_ptr() if count else 0, a.log_n, w, comm, on_device=False))
+        out["e2e"] = {"value": esec, "unit": "s", "h2d_bytes_per_step": 4 * w * n, "proof_equals_single_gpu": eproof == single,
+                      "stages_ms": ctx.last_stage_ms()}
+    return out
 
 
 def multichip_shapes():

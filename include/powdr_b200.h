@@ -26,6 +26,7 @@ extern "C" {
 #define PB_ERR_STACK_DEPTH (-3)   /* expression needs more than 16 stack slots (STACK_CAPACITY, expr_eval.cuh:22) */
 #define PB_ERR_BAD_BYTECODE (-4)
 #define PB_ERR_NO_DEVICE (-5)
+#define PB_ERR_COMM (-6)          /* a caller-supplied collective (pb_comm_t) reported failure */
 
 #define PB_BABYBEAR_P 2013265921u
 #define PB_DIGEST_WORDS 8
@@ -137,6 +138,31 @@ int pb_prove_segment(pb_ctx_t* ctx, const pb_air_t* air, const uint32_t* trace, 
 int pb_query_words(size_t log_n, size_t width, size_t* words_per_query);
 int pb_query_segment(pb_ctx_t* ctx, size_t n_queries, uint32_t* h_out, size_t out_capacity_words);
 int pb_last_openings(pb_ctx_t* ctx, uint32_t* h_ys, size_t capacity_words);
+
+/* ---- one segment across G = 2^g GPUs, one process (and one pb_ctx) per GPU: SURVEY.md §8e ----
+ * The trace is column-sharded on input (rank r holds columns pb_shard_columns(width, G, r)), the LDE and everything after it
+ * is row-sharded (rank r holds rows [r*2N/G, (r+1)*2N/G) of the bit-reversed LDE for ALL columns); one all-to-all of folded
+ * coefficients connects the two (the distributed-FFT transpose), after which only digests, the quotient columns, the opened
+ * values and the tail of the FRI codeword are exchanged.  Collectives are supplied by the caller (NCCL, MPI, a test harness):
+ * both take DEVICE pointers, are called with the context's stream idle, and must return once d_recv is complete.
+ * The resulting proof is bit-identical to pb_prove_segment's on the gathered trace.  (Reference: the stark backend proves a
+ * segment on one device -- /root/reference/openvm/src/lib.rs:69-95 selects one engine per process; this is the north_star's
+ * "trace-column shards partitioned across the GPUs, one all-gather of Merkle caps and FRI fold outputs".) */
+typedef int (*pb_collective_fn)(void* user, const void* d_send, void* d_recv, size_t bytes_per_rank);
+typedef struct pb_comm {
+    int rank, world;                  /* world: 2, 4, 8 or 16 */
+    pb_collective_fn all_gather;      /* d_recv[r * bytes ..] = rank r's d_send[0 .. bytes) */
+    pb_collective_fn all_to_all;      /* d_recv[r * bytes ..] = rank r's d_send[rank * bytes ..) */
+    void* user;
+} pb_comm_t;
+/* the column block of `rank`: first = min(width, rank*ceil(width/world)), count = min(ceil(width/world), width - first) */
+int pb_shard_columns(size_t width, int world, int rank, size_t* first, size_t* count);
+/* rows [blk*2N/world, (blk+1)*2N/world) of pb_lde_batch(.., log_blowup 1, shift)'s result for every column, computed without
+ * the other rows (sub-coset evaluation); d_out column-major [width][2N/world] */
+int pb_lde_shard(pb_ctx_t* ctx, const uint32_t* d_trace, size_t log_n, size_t width, uint32_t shift, int world, int blk, uint32_t* d_out);
+/* trace_cols: this rank's column block [count][2^log_n] (device if PB_TRACE_ON_DEVICE, else host); width: the whole trace's */
+int pb_prove_segment_sharded(pb_ctx_t* ctx, const pb_air_t* air, const uint32_t* trace_cols, size_t log_n, size_t width, uint32_t flags,
+                             const pb_comm_t* comm, pb_segment_proof_t* proof);
 
 /* per-stage device milliseconds of the last pb_prove_segment: [h2d, lde, merkle, quotient, qlde, qmerkle, open, fri, total] */
 int pb_last_stage_ms(pb_ctx_t* ctx, float ms[9]);

@@ -16,6 +16,7 @@ EXPORTS = [
     "pb_device_alloc", "pb_device_free", "pb_copy_h2d", "pb_copy_d2h", "pb_memset_zero", "pb_to_monty", "pb_from_monty",
     "pb_lde_batch", "pb_air_compile", "pb_air_free", "pb_air_is_jit", "pb_air_jit_compile_only", "pb_quotient", "pb_constraint_fold", "pb_merkle_commit",
     "pb_merkle_commit_rows8", "pb_poseidon2_permute", "pb_fri_fold", "pb_eval_at_point", "pb_deep_quotient", "pb_prove_segment", "pb_query_words", "pb_query_segment", "pb_last_openings", "pb_last_stage_ms",
+    "pb_shard_columns", "pb_lde_shard", "pb_prove_segment_sharded",
     "pb_launch_count", "pb_leaf_kernel_profile", "_apc_tracegen", "_apc_apply_derived_expr", "_apc_apply_bus",
 ]
 
@@ -251,6 +252,17 @@ class Context:
         proof = SegmentProof()
         _chk(self.lib.pb_prove_segment(self.h, air.h, C.c_void_p(trace_ptr), C.c_size_t(log_n), C.c_size_t(width),
                                        C.c_uint32(1 if on_device else 0), C.byref(proof)), "pb_prove_segment")
+        return proof.as_dict()
+
+    def lde_shard(self, d_trace_ptr, log_n, width, world, blk, d_out_ptr, shift=31):
+        _chk(self.lib.pb_lde_shard(self.h, C.c_void_p(d_trace_ptr), C.c_size_t(log_n), C.c_size_t(width), C.c_uint32(shift), C.c_int(world),
+                                   C.c_int(blk), C.c_void_p(d_out_ptr)), "pb_lde_shard")
+
+    def prove_segment_sharded(self, air, trace_cols_ptr, log_n, width, comm, on_device=False):
+        """one rank of a multi-GPU segment proof; comm: powdr_b200.sharded.Comm.  trace_cols_ptr: this rank's column block."""
+        proof = SegmentProof()
+        _chk(self.lib.pb_prove_segment_sharded(self.h, air.h, C.c_void_p(trace_cols_ptr or 0), C.c_size_t(log_n), C.c_size_t(width),
+                                               C.c_uint32(1 if on_device else 0), C.byref(comm.c), C.byref(proof)), "pb_prove_segment_sharded")
         return proof.as_dict()
 
     def query_segment(self, log_n, width, n_queries):

@@ -172,6 +172,7 @@ struct pb_ctx {
     DevBuf<uint2> ws_gp;                  // Shoup pairs of the gamma powers of the reduced opening
     DevBuf<const uint32_t*> coltab2;
     DevBuf<uint32_t> ws_layers_q, ws_layers_open, ws_fri_words, ws_fri_trees, ws_qidx, ws_qout;
+    DevBuf<uint32_t> ws_shard_send, ws_shard_recv, ws_shard_coef, ws_gather, ws_gather2;   // multi-GPU segment (shard_api.inl)
     // what pb_query_segment needs from the last pb_prove_segment (everything stays resident on the device)
     struct {
         bool valid = false;
@@ -360,6 +361,7 @@ int pb_ctx_destroy(pb_ctx_t* ctx) {
     ctx->ws_ys.release(); ctx->ws_w.release(); ctx->ws_part.release(); ctx->ws_gp.release(); ctx->coltab2.release();
     ctx->ws_layers_q.release(); ctx->ws_layers_open.release(); ctx->ws_fri_words.release(); ctx->ws_fri_trees.release();
     ctx->ws_qidx.release(); ctx->ws_qout.release();
+    ctx->ws_shard_send.release(); ctx->ws_shard_recv.release(); ctx->ws_shard_coef.release(); ctx->ws_gather.release(); ctx->ws_gather2.release();
     ctx->ws_qnat.release(); ctx->ws_qlde.release(); ctx->ws_f0.release(); ctx->ws_f1.release(); ctx->ws_state.release();
     if (ctx->copy_stream) cudaStreamDestroy(ctx->copy_stream);
     for (int i = 0; i < 2; i++) { if (ctx->ev_copy[i]) cudaEventDestroy(ctx->ev_copy[i]); if (ctx->ev_free[i]) cudaEventDestroy(ctx->ev_free[i]); }
@@ -411,6 +413,101 @@ int pb_from_monty(pb_ctx_t* ctx, uint32_t* d, size_t n) {
 }
 
 // ---------------------------------------------------------------------------------------------------------------------
+// ---------------------------------------------------------------------------------------------------------------------
+// NTT pass geometry and the two halves of the LDE (shared by pb_lde_batch and pb_lde_shard)
+namespace {
+
+struct NttGeom {
+    int n, n_lo, n_hi, log_lc_hi, log_lc_lo;
+    bool fast;                          // compile-time specialised passes (ntt_fast.cuh) cover this geometry
+    size_t smem_hi, smem_lo;
+    ntt::Rounds r_inv_hi, r_fwd_hi, r_inv_lo, r_fwd_lo;
+};
+
+NttGeom make_geom(int n) {
+    NttGeom g{};
+    g.n = n;
+    g.n_lo = n <= 10 ? n : (n + 1) / 2;
+    g.n_hi = n - g.n_lo;
+    g.fast = getenv("PB_LDE_GENERIC") == nullptr && nttf::supported(g.n_hi, g.n_lo);
+    // K1/K3 tile: 2^n_hi rows x 2^log_lc_hi lanes;  K2 tile: 2^n_lo rows x 2^log_lc_lo blocks
+    g.log_lc_hi = g.fast ? nttf::log_lc_of(g.n_hi) : std::min(5, ntt::LOG_TILE_MAX - g.n_hi);
+    g.log_lc_lo = g.fast ? nttf::log_lc_of(g.n_lo) : std::min(5, ntt::LOG_TILE_MAX - g.n_lo);
+    g.smem_hi = (size_t)4 << (g.n_hi + g.log_lc_hi);
+    g.smem_lo = (size_t)4 << (g.n_lo + g.log_lc_lo);
+    auto make_rounds = [](int bits, bool descending) {
+        ntt::Rounds r{};
+        const int nr = (bits + 4) / 5;
+        r.n = nr;
+        int q[ntt::MAX_ROUNDS], b0[ntt::MAX_ROUNDS], acc = 0;
+        for (int i = 0; i < nr; i++) { q[i] = bits / nr + (i < bits % nr ? 1 : 0); b0[i] = acc; acc += q[i]; }
+        for (int i = 0; i < nr; i++) { const int k = descending ? nr - 1 - i : i; r.q[i] = q[k]; r.b0[i] = b0[k]; }
+        return r;
+    };
+    g.r_inv_hi = make_rounds(g.n_hi, true); g.r_fwd_hi = make_rounds(g.n_hi, false);
+    g.r_inv_lo = make_rounds(g.n_lo, true); g.r_fwd_lo = make_rounds(g.n_lo, false);
+    return g;
+}
+
+// Column batch: the passes are integer-pipe bound (ncu: DRAM < 15 % busy), so filling the machine evenly matters more than
+// keeping the intermediates L2-resident.  Measured at 2^20: 4 columns -> 49.7 ms, 37 -> 35.5, 74 -> 34.5.
+// PB_LDE_BATCH overrides for experiments.
+size_t lde_column_batch(size_t N, size_t width) {
+    const size_t tiles_per_col = std::max<size_t>(1, N >> ntt::LOG_TILE_MAX);
+    size_t batch = std::max<size_t>(1, (size_t)148 * 16 / tiles_per_col);
+    if (const char* e = getenv("PB_LDE_BATCH")) batch = std::max<size_t>(1, (size_t)atol(e));
+    batch = std::min<size_t>(std::min<size_t>(batch, width), 32768);
+    return (width + (width + batch - 1) / batch - 1) / ((width + batch - 1) / batch);     // equal-sized batches (no runt batch)
+}
+
+// K1 + K2a: nb natural-order columns (stride N) -> coefficients in bit-reversed slots, scaled by 1/N, in coef (stride N)
+void ntt_inverse_cols(pb_ctx* ctx, const NttGeom& g, const TwiddleSet* tw, const uint32_t* src, unsigned nb, uint32_t* coef) {
+    const size_t N = (size_t)1 << g.n;
+    if (g.n_hi > 0) {
+        dim3 g1((unsigned)(1u << (g.n_lo - g.log_lc_hi)), nb);
+        if (!g.fast || !nttf::launch_strided(true, g.n_hi, g.n_lo, g1, ctx->stream, src, N, coef, N, 0, tw->d_inv))
+            ntt::strided_pass_kernel<true><<<g1, ntt::THREADS, g.smem_hi, ctx->stream>>>(src, N, coef, N, g.n, g.n_lo, g.log_lc_hi, 0,
+                                                                                         tw->d_inv, g.r_inv_hi);
+        LAUNCHED(ctx);
+        src = coef;
+    }
+    const size_t total_blocks = (size_t)nb << g.n_hi;
+    const unsigned gx = (unsigned)((total_blocks + ((size_t)1 << g.log_lc_lo) - 1) >> g.log_lc_lo);
+    if (!g.fast || !nttf::launch_transposed(true, g.n, g.n_lo, dim3(gx), ctx->stream, src, N, coef, 0, total_blocks, tw->d_inv, tw->ninv))
+        ntt::transposed_pass_kernel<true><<<dim3(gx), ntt::THREADS, g.smem_lo, ctx->stream>>>(src, N, coef, g.n, g.n_lo, g.log_lc_lo, 0,
+                                                                                             total_blocks, tw->d_inv, tw->ninv, g.r_inv_lo);
+    LAUNCHED(ctx);
+}
+
+// K2b + K3: coefficients (bit-reversed slots, stride N) -> 2^log_blowup coset evaluations per column, bit-reversed rows,
+// out[col * out_stride + bitrev_b(c) * N + bitrev_n(k)];  scratch holds [nb][cosets][N]
+void ntt_forward_cols(pb_ctx* ctx, const NttGeom& g, const TwiddleSet* tw, int log_blowup, const uint32_t* coef, unsigned nb,
+                      uint32_t* scratch, uint32_t* out, size_t out_stride) {
+    const size_t N = (size_t)1 << g.n;
+    const int cosets = 1 << log_blowup;
+    const size_t total_blocks = (size_t)nb << g.n_hi;
+    const unsigned gx = (unsigned)((total_blocks + ((size_t)1 << g.log_lc_lo) - 1) >> g.log_lc_lo);
+    if (!g.fast || !nttf::launch_transposed(false, g.n, g.n_lo, dim3(gx, 1, (unsigned)cosets), ctx->stream, coef, N, scratch, log_blowup,
+                                            total_blocks, tw->d_fwd, make_uint2(0u, 0u)))
+        ntt::transposed_pass_kernel<false><<<dim3(gx, 1, (unsigned)cosets), ntt::THREADS, g.smem_lo, ctx->stream>>>(
+            coef, N, scratch, g.n, g.n_lo, g.log_lc_lo, log_blowup, total_blocks, tw->d_fwd, make_uint2(0u, 0u), g.r_fwd_lo);
+    LAUNCHED(ctx);
+    if (g.n_hi > 0) {
+        dim3 g3((unsigned)(1u << (g.n_lo - g.log_lc_hi)), nb, (unsigned)cosets);
+        if (!g.fast || !nttf::launch_strided(false, g.n_hi, g.n_lo, g3, ctx->stream, scratch, 0, out, out_stride, log_blowup, tw->d_fwd))
+            ntt::strided_pass_kernel<false><<<g3, ntt::THREADS, g.smem_hi, ctx->stream>>>(scratch, 0, out, out_stride, g.n, g.n_lo, g.log_lc_hi,
+                                                                                          log_blowup, tw->d_fwd, g.r_fwd_hi);
+        LAUNCHED(ctx);
+    } else {
+        const size_t tot = ((size_t)nb * cosets) << g.n;
+        ntt::bitrev_store_kernel<<<(unsigned)((tot + 255) / 256), 256, 0, ctx->stream>>>(scratch, out, out_stride, g.n, log_blowup, nb);
+        LAUNCHED(ctx);
+    }
+}
+
+}  // namespace
+
+
 int pb_lde_batch(pb_ctx_t* ctx, const uint32_t* d_trace, size_t log_n, size_t width, uint32_t log_blowup, uint32_t shift,
                  uint32_t* d_lde) {
     if (!ctx || !d_trace || !d_lde) return PB_ERR_INVALID_ARG;
@@ -422,77 +519,14 @@ int pb_lde_batch(pb_ctx_t* ctx, const uint32_t* d_trace, size_t log_n, size_t wi
     const TwiddleSet* tw;
     int rc = get_twiddles(ctx, n, (int)log_blowup, shift, &tw);
     if (rc) return rc;
-    const int n_lo = n <= 10 ? n : (n + 1) / 2;
-    const int n_hi = n - n_lo;
-    const bool use_fast = getenv("PB_LDE_GENERIC") == nullptr;     // compile-time specialised passes (ntt_fast.cuh) when available
-    const bool fast_geom = use_fast && nttf::supported(n_hi, n_lo);
-    // K1/K3 tile: 2^n_hi rows x 2^log_lc_hi lanes;  K2 tile: 2^n_lo rows x 2^log_lc_lo blocks
-    const int log_lc_hi = fast_geom ? nttf::log_lc_of(n_hi) : std::min(5, ntt::LOG_TILE_MAX - n_hi);
-    const int log_lc_lo = fast_geom ? nttf::log_lc_of(n_lo) : std::min(5, ntt::LOG_TILE_MAX - n_lo);
-    auto make_rounds = [](int bits, bool descending) {
-        ntt::Rounds r{};
-        const int nr = (bits + 4) / 5;
-        r.n = nr;
-        int q[ntt::MAX_ROUNDS], b0[ntt::MAX_ROUNDS], acc = 0;
-        for (int i = 0; i < nr; i++) { q[i] = bits / nr + (i < bits % nr ? 1 : 0); b0[i] = acc; acc += q[i]; }
-        for (int i = 0; i < nr; i++) { const int k = descending ? nr - 1 - i : i; r.q[i] = q[k]; r.b0[i] = b0[k]; }
-        return r;
-    };
-    // Column batch: the passes are integer-pipe bound (ncu: DRAM < 15 % busy), so filling the machine evenly matters more
-    // than keeping the intermediates L2-resident: size the batch so every pass launches a whole number of 148-CTA waves
-    // (one 128 KB-tile CTA per SM).  PB_LDE_BATCH overrides for experiments.
-    size_t batch;
-    {
-        const size_t tiles_per_col = std::max<size_t>(1, N >> ntt::LOG_TILE_MAX);
-        batch = std::max<size_t>(1, (size_t)148 * 16 / tiles_per_col);      // measured at 2^20: 4 -> 49.7 ms, 37 -> 35.5, 74 -> 34.5
-        if (const char* e = getenv("PB_LDE_BATCH")) batch = std::max<size_t>(1, (size_t)atol(e));
-    }
-    batch = std::min<size_t>(std::min<size_t>(batch, width), 32768);
-    batch = (width + (width + batch - 1) / batch - 1) / ((width + batch - 1) / batch);     // equal-sized batches (no runt batch)
+    const NttGeom g = make_geom(n);
+    const size_t batch = lde_column_batch(N, width);
     rc = ctx->tmp.ensure(batch * N); if (rc) return rc;
     rc = ctx->tmp2.ensure(batch * N * cosets); if (rc) return rc;
-    const size_t smem_hi = (size_t)4 << (n_hi + log_lc_hi);
-    const size_t smem_lo = (size_t)4 << (n_lo + log_lc_lo);
-    const ntt::Rounds r_inv_hi = make_rounds(n_hi, true), r_fwd_hi = make_rounds(n_hi, false);
-    const ntt::Rounds r_inv_lo = make_rounds(n_lo, true), r_fwd_lo = make_rounds(n_lo, false);
     for (size_t c0 = 0; c0 < width; c0 += batch) {
         const unsigned nb = (unsigned)std::min(batch, width - c0);
-        const uint32_t* src = d_trace + c0 * N;
-        const bool fast = fast_geom;
-        if (n_hi > 0) {
-            dim3 g1((unsigned)(1u << (n_lo - log_lc_hi)), nb);
-            if (!fast || !nttf::launch_strided(true, n_hi, n_lo, g1, ctx->stream, src, N, ctx->tmp.p, N, (int)log_blowup, tw->d_inv))
-                ntt::strided_pass_kernel<true><<<g1, ntt::THREADS, smem_hi, ctx->stream>>>(src, N, ctx->tmp.p, N, n, n_lo, log_lc_hi,
-                                                                                           (int)log_blowup, tw->d_inv, r_inv_hi);
-            LAUNCHED(ctx);
-            src = ctx->tmp.p;
-        }
-        const size_t total_blocks = (size_t)nb << n_hi;
-        const unsigned gx = (unsigned)((total_blocks + ((size_t)1 << log_lc_lo) - 1) >> log_lc_lo);
-        if (!fast || !nttf::launch_transposed(true, n, n_lo, dim3(gx), ctx->stream, src, N, ctx->tmp.p, (int)log_blowup, total_blocks,
-                                              tw->d_inv, tw->ninv))
-            ntt::transposed_pass_kernel<true><<<dim3(gx), ntt::THREADS, smem_lo, ctx->stream>>>(src, N, ctx->tmp.p, n, n_lo, log_lc_lo,
-                                                                                                (int)log_blowup, total_blocks, tw->d_inv,
-                                                                                                tw->ninv, r_inv_lo);
-        LAUNCHED(ctx);
-        if (!fast || !nttf::launch_transposed(false, n, n_lo, dim3(gx, 1, (unsigned)cosets), ctx->stream, ctx->tmp.p, N, ctx->tmp2.p,
-                                              (int)log_blowup, total_blocks, tw->d_fwd, make_uint2(0u, 0u)))
-            ntt::transposed_pass_kernel<false><<<dim3(gx, 1, (unsigned)cosets), ntt::THREADS, smem_lo, ctx->stream>>>(
-                ctx->tmp.p, N, ctx->tmp2.p, n, n_lo, log_lc_lo, (int)log_blowup, total_blocks, tw->d_fwd, make_uint2(0u, 0u), r_fwd_lo);
-        LAUNCHED(ctx);
-        uint32_t* out = d_lde + c0 * N * cosets;
-        if (n_hi > 0) {
-            dim3 g3((unsigned)(1u << (n_lo - log_lc_hi)), nb, (unsigned)cosets);
-            if (!fast || !nttf::launch_strided(false, n_hi, n_lo, g3, ctx->stream, ctx->tmp2.p, 0, out, N * cosets, (int)log_blowup, tw->d_fwd))
-                ntt::strided_pass_kernel<false><<<g3, ntt::THREADS, smem_hi, ctx->stream>>>(ctx->tmp2.p, 0, out, N * cosets, n, n_lo,
-                                                                                            log_lc_hi, (int)log_blowup, tw->d_fwd, r_fwd_hi);
-            LAUNCHED(ctx);
-        } else {
-            const size_t tot = ((size_t)nb * cosets) << n;
-            ntt::bitrev_store_kernel<<<(unsigned)((tot + 255) / 256), 256, 0, ctx->stream>>>(ctx->tmp2.p, out, N * cosets, n,
-                                                                                             (int)log_blowup, nb);
-            LAUNCHED(ctx);
-        }
+        ntt_inverse_cols(ctx, g, tw, d_trace + c0 * N, nb, ctx->tmp.p);
+        ntt_forward_cols(ctx, g, tw, (int)log_blowup, ctx->tmp.p, nb, ctx->tmp2.p, d_lde + c0 * N * cosets, N * cosets);
     }
     CK(cudaGetLastError());
     return 0;
@@ -701,16 +735,18 @@ int pb_poseidon2_permute(pb_ctx_t* ctx, uint32_t* d_states, size_t n, int reps) 
 }
 
 // ---------------------------------------------------------------------------------------------------------------------
-static int fri_fold_m(pb_ctx* ctx, const uint32_t* d_in, size_t log_len, uint32_t shift_m, bb::E4 beta_m, uint32_t* d_out) {
+// outputs [j0, j0 + n_out) of the folded codeword only when n_out != 0 (d_in / d_out then point at that block: inputs 2*j0.., outputs j0..)
+static int fri_fold_m(pb_ctx* ctx, const uint32_t* d_in, size_t log_len, uint32_t shift_m, bb::E4 beta_m, uint32_t* d_out, size_t j0 = 0,
+                      size_t n_out = 0) {
     int rc = get_fold_table(ctx, (int)log_len);
     if (rc) return rc;
-    const size_t half = (size_t)1 << (log_len - 1);
+    const size_t half = n_out ? n_out : (size_t)1 << (log_len - 1);
     const uint32_t two_inv = bb::inv(h_to_m(2));
     const uint32_t c = bb::mul(two_inv, bb::inv(shift_m));          // (2*shift)^-1
     bb::E4 beta_c = bb::e4_scale(beta_m, c);
     // table prefix property: w_L^{-bitrev_{logL-1}(j)} for a shorter layer is the prefix of the longer layer's table
     fri::fold_kernel<<<(unsigned)((half + 255) / 256), 256, 0, ctx->stream>>>(reinterpret_cast<const uint4*>(d_in),
-                                                                              reinterpret_cast<uint4*>(d_out), half, ctx->d_fold_tab,
+                                                                              reinterpret_cast<uint4*>(d_out), half, ctx->d_fold_tab + j0,
                                                                               beta_c, two_inv);
     LAUNCHED(ctx);
     CK(cudaGetLastError());
@@ -754,8 +790,9 @@ static int eval_at_point_m(pb_ctx* ctx, const uint32_t* d_mat, size_t log_n, siz
 
 // reduced opening over shift*H' (bit-reversed rows) of the columns in `cols`; ys_m: host, [n_cols][4] Montgomery
 static int deep_quotient_m(pb_ctx* ctx, const std::vector<const uint32_t*>& cols, size_t log_m, uint32_t shift_m, bb::E4 zeta_m,
-                           bb::E4 gamma_m, const uint32_t* ys_m, uint32_t* d_out) {
-    const size_t n_cols = cols.size(), M = (size_t)1 << log_m;
+                           bb::E4 gamma_m, const uint32_t* ys_m, uint32_t* d_out, size_t row0 = 0, size_t n_rows = 0) {
+    // rows [row0, row0 + n_rows) of the domain only (n_rows = 0: all of it); cols[] then point at that row block
+    const size_t n_cols = cols.size(), M = n_rows ? n_rows : (size_t)1 << log_m;
     std::vector<uint2> gp(4 * n_cols);
     bb::E4 cur = {{bb::R1, 0u, 0u, 0u}}, ysum = {{0u, 0u, 0u, 0u}};
     for (size_t j = 0; j < n_cols; j++) {
@@ -771,7 +808,7 @@ static int deep_quotient_m(pb_ctx* ctx, const std::vector<const uint32_t*>& cols
     if (rc) return rc;
     CK(cudaMemcpyAsync(ctx->ws_gp.p, gp.data(), gp.size() * sizeof(uint2), cudaMemcpyHostToDevice, ctx->stream));
     CK(cudaMemcpyAsync(ctx->coltab2.p, cols.data(), n_cols * sizeof(void*), cudaMemcpyHostToDevice, ctx->stream));
-    deep::deep_quotient_kernel<<<(unsigned)((M + 255) / 256), 256, 0, ctx->stream>>>(ctx->coltab2.p, (uint32_t)n_cols, M, (int)log_m, shift_m,
+    deep::deep_quotient_kernel<<<(unsigned)((M + 255) / 256), 256, 0, ctx->stream>>>(ctx->coltab2.p, (uint32_t)n_cols, M, (int)log_m, row0, shift_m,
                                                                                     h_root_of_unity_m((int)log_m), ctx->ws_gp.p, ysum, zeta_m,
                                                                                     reinterpret_cast<uint4*>(d_out));
     LAUNCHED(ctx);
@@ -1078,5 +1115,7 @@ int _apc_apply_bus(const uint32_t* d_output, int num_apc_calls, const uint32_t* 
         sz0, sz1, bitwise_bus_id, d_bitwise_hist);
     return (int)cudaGetLastError();
 }
+
+#include "shard_api.inl"
 
 }  // extern "C"

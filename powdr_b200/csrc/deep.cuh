@@ -116,8 +116,9 @@ __global__ void eval_finalize_kernel(const uint4* __restrict__ partial, uint32_t
 }
 
 // reduced opening over the LDE domain (bit-reversed rows).  gp[j*4+l] = Shoup pair of limb l of gamma^j (canonical), so
-// gamma^j * f_j costs four 8-cycle constant products; `cols` has one base pointer per opened column.
-__global__ void __launch_bounds__(256) deep_quotient_kernel(const uint32_t* const* __restrict__ cols, uint32_t n_cols, size_t m, int log_m,
+// gamma^j * f_j costs four 8-cycle constant products; `cols` has one base pointer per opened column.  The m rows passed
+// are rows [row0, row0 + m) of the 2^log_m-row domain (row0 = 0, m = 2^log_m for the whole domain).
+__global__ void __launch_bounds__(256) deep_quotient_kernel(const uint32_t* const* __restrict__ cols, uint32_t n_cols, size_t m, int log_m, size_t row0,
                                                             uint32_t shift_m, uint32_t omega_m, const uint2* __restrict__ gp,
                                                             bb::E4 ysum, bb::E4 zeta, uint4* __restrict__ out) {
     const size_t r = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -133,7 +134,7 @@ __global__ void __launch_bounds__(256) deep_quotient_kernel(const uint32_t* cons
         a3 = bb::add(a3, bb::mul_shoup(f, make_uint2(g23.z, g23.w)));
     }
     bb::E4 acc = {{bb::sub(a0, ysum.c[0]), bb::sub(a1, ysum.c[1]), bb::sub(a2, ysum.c[2]), bb::sub(a3, ysum.c[3])}};
-    const uint32_t x = bb::mul(shift_m, bb::pow(omega_m, (uint64_t)(__brev((uint32_t)r) >> (32 - log_m))));
+    const uint32_t x = bb::mul(shift_m, bb::pow(omega_m, (uint64_t)(__brev((uint32_t)(row0 + r)) >> (32 - log_m))));
     bb::E4 d = {{bb::sub(x, zeta.c[0]), bb::neg(zeta.c[1]), bb::neg(zeta.c[2]), bb::neg(zeta.c[3])}};
     const bb::E4 v = bb::e4_mul(acc, e4_inv(d));
     out[r] = make_uint4(v.c[0], v.c[1], v.c[2], v.c[3]);

@@ -1,0 +1,380 @@
+// One segment across G = 2^g GPUs (north_star "trace-column shards partitioned across the GPUs").
+// Included by capi.cu inside its extern "C" block (uses its file-local helpers).
+//
+// Decomposition.  Input: the trace is COLUMN-sharded (rank r holds columns [r*per, (r+1)*per), per = ceil(W/G)).  Output
+// of stage 1: the LDE is ROW-sharded: rank r holds rows [r*Ms, (r+1)*Ms) of the bit-reversed 2N-row LDE, Ms = 2N/G, for
+// ALL columns -- which is what Merkle leaf hashing, constraint evaluation, the reduced opening and FRI folding need,
+// because each of them is per-row (or per adjacent row pair).  A contiguous block of bit-reversed rows is a sub-coset:
+// rows of block (c, h) (c = coset, h = block inside the coset, G1 = G/2 blocks per coset) are the points
+//     s' * <w_N^G1>,   s' = shift * w_2N^c * w_N^k0,   k0 = bitrev_{g-1}(h)
+// and a polynomial restricted to that sub-coset is the size-N/G1 polynomial  b_r = sum_q lambda^q a_{r + q N/G1},
+// lambda = s'^(N/G1).  With the coefficients in bit-reversed slots (what the inverse passes leave), a_{r + q N/G1} are G1
+// ADJACENT slots, so the fold is a streaming kernel.  Hence:
+//   inverse NTT of my columns  ->  fold for every destination block  ->  ONE all-to-all (the distributed-FFT transpose,
+//   2N*W*4 bytes in total)  ->  forward NTT of size N/G1 on my block, all columns.
+// After that only digests (32 B per rank and tree), the 8 quotient columns, the opened values and the tail of the FRI
+// codeword cross GPUs.  The collectives are caller-supplied callbacks (pb_comm_t): NCCL via torch.distributed in
+// bench.py, a barrier + staging copy in the single-GPU thread tests.  The library itself links no communication library.
+//
+// The transcript, and therefore the proof, is identical to pb_prove_segment's on the same trace (tests/test_gpu_sharded.py).
+
+namespace shard {
+
+struct FoldParams { uint32_t lam[16][8]; };     // lam[s][q] = lambda_s^q (Montgomery), s < n_out <= 16, q < G1 <= 8
+
+// out[s * shard_stride + col * Np + p] = sum_q lam[s][q] * coef[col * N + p * G1 + bitrev_g1(q)]
+__global__ void __launch_bounds__(256) coef_fold_kernel(const uint32_t* __restrict__ coef, size_t n_cols, int n, int g1, int n_out, FoldParams P,
+                                                        uint32_t* __restrict__ out, size_t shard_stride) {
+    const int np = n - g1;
+    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= (n_cols << np)) return;
+    const size_t col = i >> np, p = i & (((size_t)1 << np) - 1);
+    const uint32_t* a = coef + (col << n) + (p << g1);
+    uint32_t v[8];
+    const int G1 = 1 << g1;
+    for (int q = 0; q < G1; q++) v[q] = __ldg(a + ntt::brev((uint32_t)q, g1));
+    for (int s = 0; s < n_out; s++) {
+        uint32_t acc = v[0];
+        for (int q = 1; q < G1; q++) acc = bb::add(acc, bb::mul(v[q], P.lam[s][q]));
+        out[(size_t)s * shard_stride + i] = acc;
+    }
+}
+
+__global__ void __launch_bounds__(256) scale_kernel(uint32_t* __restrict__ a, size_t n, uint32_t k) {
+    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) a[i] = bb::mul(a[i], k);
+}
+
+}  // namespace shard
+
+namespace {
+
+struct ShardGeom {
+    int g, g1, G, G1;
+    size_t N, Ms;        // Ms = rows per block = N >> g1 = 2N >> g
+    int np;              // log2(Ms)
+};
+
+inline bool make_shard_geom(size_t log_n, int world, ShardGeom* s) {
+    int g = 0;
+    while ((1 << g) < world) g++;
+    if ((1 << g) != world || g < 1 || g > 4 || log_n < (size_t)g + 3) return false;
+    s->g = g; s->g1 = g - 1; s->G = world; s->G1 = world / 2;
+    s->N = (size_t)1 << log_n; s->Ms = s->N >> s->g1; s->np = (int)log_n - s->g1;
+    return true;
+}
+
+// s' (Montgomery) of block `blk` of the LDE with base shift `shift_m` (log_blowup 1)
+inline uint32_t block_shift_m(const ShardGeom& s, size_t log_n, uint32_t shift_m, int blk) {
+    const int c = blk >> s.g1, h = blk & (s.G1 - 1);
+    uint32_t k0 = 0;
+    for (int b = 0; b < s.g1; b++) k0 |= ((h >> b) & 1u) << (s.g1 - 1 - b);
+    uint32_t sp = bb::mul(shift_m, bb::pow(h_root_of_unity_m((int)log_n + 1), (uint64_t)c));
+    return bb::mul(sp, bb::pow(h_root_of_unity_m((int)log_n), (uint64_t)k0));
+}
+
+inline void fold_params_for(const ShardGeom& s, size_t log_n, uint32_t shift_m, int first_blk, int n_blk, shard::FoldParams* P) {
+    memset(P, 0, sizeof *P);
+    for (int i = 0; i < n_blk; i++) {
+        const uint32_t lam = bb::pow(block_shift_m(s, log_n, shift_m, first_blk + i), (uint64_t)s.Ms);
+        uint32_t x = bb::R1;
+        for (int q = 0; q < s.G1; q++) { P->lam[i][q] = x; x = bb::mul(x, lam); }
+    }
+}
+
+// inverse NTT of `w` natural-order columns (stride N), then the fold for blocks [first_blk, first_blk + n_blk):
+// out[(b - first_blk) * shard_stride + col * Ms + p]
+int inverse_and_fold(pb_ctx* ctx, const ShardGeom& s, const uint32_t* d_cols, size_t log_n, size_t w, uint32_t shift, int first_blk, int n_blk,
+                     uint32_t* out, size_t shard_stride) {
+    if (w == 0) return 0;
+    const TwiddleSet* tw;
+    int rc = get_twiddles(ctx, (int)log_n, 1, bb::GEN, &tw);       // only the (shift independent) inverse table is used
+    if (rc) return rc;
+    const NttGeom g = make_geom((int)log_n);
+    const size_t batch = lde_column_batch(s.N, w);
+    rc = ctx->tmp.ensure(batch * s.N);
+    if (rc) return rc;
+    shard::FoldParams P;
+    fold_params_for(s, log_n, h_to_m(shift), first_blk, n_blk, &P);
+    for (size_t c0 = 0; c0 < w; c0 += batch) {
+        const unsigned nb = (unsigned)std::min(batch, w - c0);
+        ntt_inverse_cols(ctx, g, tw, d_cols + c0 * s.N, nb, ctx->tmp.p);
+        const size_t tot = (size_t)nb << s.np;
+        shard::coef_fold_kernel<<<(unsigned)((tot + 255) / 256), 256, 0, ctx->stream>>>(ctx->tmp.p, nb, (int)log_n, s.g1, n_blk, P,
+                                                                                       out + c0 * s.Ms, shard_stride);
+        LAUNCHED(ctx);
+    }
+    CK(cudaGetLastError());
+    return 0;
+}
+
+// forward NTT (size Ms, one coset with shift s' of block blk) of `w` folded coefficient columns (stride Ms) -> out (stride Ms)
+int forward_block(pb_ctx* ctx, const ShardGeom& s, const uint32_t* d_coef, size_t log_n, size_t w, uint32_t shift, int blk, uint32_t* out) {
+    if (w == 0) return 0;
+    const uint32_t sp = h_from_m(block_shift_m(s, log_n, h_to_m(shift), blk));
+    const TwiddleSet* tw;
+    int rc = get_twiddles(ctx, s.np, 0, sp, &tw);
+    if (rc) return rc;
+    const NttGeom g = make_geom(s.np);
+    const size_t batch = lde_column_batch(s.Ms, w);
+    rc = ctx->tmp2.ensure(batch * s.Ms);
+    if (rc) return rc;
+    for (size_t c0 = 0; c0 < w; c0 += batch) {
+        const unsigned nb = (unsigned)std::min(batch, w - c0);
+        ntt_forward_cols(ctx, g, tw, 0, d_coef + c0 * s.Ms, nb, ctx->tmp2.p, out + c0 * s.Ms, s.Ms);
+    }
+    CK(cudaGetLastError());
+    return 0;
+}
+
+inline void host_compress(const P2Host& k, const uint32_t l[8], const uint32_t r[8], uint32_t out[8]) {
+    uint32_t st[16];
+    memcpy(st, l, 32);
+    memcpy(st + 8, r, 32);
+    host_permute(st, k);
+    memcpy(out, st, 32);
+}
+
+// all ranks' subtree roots (device, Montgomery) -> the root of the whole tree (host, Montgomery)
+int combine_roots(pb_ctx* ctx, const pb_comm_t* comm, const uint32_t* d_my_root, uint32_t root_m[8]) {
+    int rc = ctx->ws_gather.ensure(8 * (size_t)comm->world);
+    if (rc) return rc;
+    CK(cudaStreamSynchronize(ctx->stream));
+    rc = comm->all_gather(comm->user, d_my_root, ctx->ws_gather.p, 32);
+    if (rc) return PB_ERR_COMM;
+    uint32_t nodes[16][8];
+    CK(cudaMemcpyAsync(nodes, ctx->ws_gather.p, 32 * (size_t)comm->world, cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    for (int n = comm->world; n > 1; n >>= 1)
+        for (int i = 0; i < n / 2; i++) {
+            uint32_t t[8];
+            host_compress(ctx->p2, nodes[2 * i], nodes[2 * i + 1], t);
+            memcpy(nodes[i], t, 32);
+        }
+    memcpy(root_m, nodes[0], 32);
+    return 0;
+}
+
+inline const uint32_t* root_ptr(const uint32_t* d_layers, size_t log_h) { return d_layers + 8 * (((size_t)2 << log_h) - 2); }
+
+}  // namespace
+
+int pb_shard_columns(size_t width, int world, int rank, size_t* first, size_t* count) {
+    if (world < 1 || rank < 0 || rank >= world || !first || !count) return PB_ERR_INVALID_ARG;
+    const size_t per = (width + (size_t)world - 1) / (size_t)world;
+    *first = std::min(width, (size_t)rank * per);
+    *count = std::min(per, width - *first);
+    return 0;
+}
+
+// rows [blk * Ms, (blk + 1) * Ms) of pb_lde_batch(..., log_blowup 1, shift)'s output, every column, computed without the rest:
+// d_out column-major [width][Ms].  (All columns are inverse-transformed here; the multi-GPU prover shares that work instead.)
+int pb_lde_shard(pb_ctx_t* ctx, const uint32_t* d_trace, size_t log_n, size_t width, uint32_t shift, int world, int blk, uint32_t* d_out) {
+    if (!ctx || !d_trace || !d_out) return PB_ERR_INVALID_ARG;
+    ShardGeom s;
+    if (log_n > 24 || shift == 0 || shift >= bb::P || !make_shard_geom(log_n, world, &s) || blk < 0 || blk >= world) return PB_ERR_UNSUPPORTED;
+    if (width == 0) return 0;
+    int rc = ctx->ws_shard_coef.ensure(width * s.Ms);
+    if (rc) return rc;
+    rc = inverse_and_fold(ctx, s, d_trace, log_n, width, shift, blk, 1, ctx->ws_shard_coef.p, 0);
+    if (rc) return rc;
+    return forward_block(ctx, s, ctx->ws_shard_coef.p, log_n, width, shift, blk, d_out);
+}
+
+int pb_prove_segment_sharded(pb_ctx_t* ctx, const pb_air_t* a, const uint32_t* trace_cols, size_t log_n, size_t width, uint32_t flags,
+                             const pb_comm_t* comm, pb_segment_proof_t* proof) {
+    if (!ctx || !a || !proof || !comm || !comm->all_gather || !comm->all_to_all) return PB_ERR_INVALID_ARG;
+    if (log_n < 1 || log_n > 24 || width == 0 || width != a->width) return PB_ERR_INVALID_ARG;
+    ShardGeom s;
+    if (!make_shard_geom(log_n, comm->world, &s) || comm->rank < 0 || comm->rank >= comm->world) return PB_ERR_UNSUPPORTED;
+    const int G = s.G, rho = comm->rank;
+    const size_t N = s.N, Ms = s.Ms, log_m = log_n + 1, log_ms = (size_t)s.np;
+    const size_t per = (width + (size_t)G - 1) / (size_t)G;
+    size_t c_first, w_my;
+    pb_shard_columns(width, G, rho, &c_first, &w_my);
+    if (w_my && !trace_cols) return PB_ERR_INVALID_ARG;
+    int rc;
+    memset(proof, 0, sizeof *proof);
+    cudaStream_t st = ctx->stream;
+    ctx->seg.valid = false;
+#define RC(x) do { rc = (x); if (rc) return rc; } while (0)
+#define COMM(fn, send, recv, bytes) do { CK(cudaStreamSynchronize(st)); if (comm->fn(comm->user, (send), (recv), (bytes))) return PB_ERR_COMM; } while (0)
+    CK(cudaEventRecord(ctx->ev[0], st));
+    RC(ctx->ws_shard_send.ensure((size_t)G * per * Ms));
+    RC(ctx->ws_shard_recv.ensure((size_t)G * per * Ms));
+    RC(ctx->ws_lde.ensure(width * Ms));
+    RC(ctx->ws_layers.ensure(8 * (2 * Ms)));
+    RC(ctx->ws_layers_q.ensure(8 * (2 * Ms)));
+    RC(ctx->ws_q.ensure(8 * N));
+    RC(ctx->ws_qnat.ensure(8 * N));
+    RC(ctx->ws_qlde.ensure(8 * Ms));
+    RC(ctx->ws_shard_coef.ensure(std::max((size_t)G * 4 * Ms, 4 * 2 * N)));
+    RC(ctx->ws_f0.ensure(4 * 2 * N));
+    RC(ctx->ws_f1.ensure(4 * 2 * N));
+    Challenger ch;
+    ch.k = &ctx->p2;
+    uint32_t root_m[8];
+
+    // ---- stage 0/1: (copy,) inverse NTT of my columns, fold for every block, all-to-all, forward NTT of my block ----
+    const uint32_t* d_my = trace_cols;
+    if (!(flags & PB_TRACE_ON_DEVICE) && w_my) {
+        RC(ctx->ws_trace.ensure(w_my * N));
+        CK(cudaMemcpyAsync(ctx->ws_trace.p, trace_cols, w_my * N * 4, cudaMemcpyHostToDevice, st));
+        d_my = ctx->ws_trace.p;
+    }
+    CK(cudaEventRecord(ctx->ev[1], st));
+    if (w_my < per)      // pad columns of the last ranks: defined contents, never read back
+        for (int b = 0; b < G; b++) CK(cudaMemsetAsync(ctx->ws_shard_send.p + ((size_t)b * per + w_my) * Ms, 0, (per - w_my) * Ms * 4, st));
+    RC(inverse_and_fold(ctx, s, d_my, log_n, w_my, bb::GEN, 0, G, ctx->ws_shard_send.p, per * Ms));
+    COMM(all_to_all, ctx->ws_shard_send.p, ctx->ws_shard_recv.p, per * Ms * 4);
+    // recv = [source rank][per][Ms]: global column j = source * per + i, so the first `width` columns are the real ones
+    RC(forward_block(ctx, s, ctx->ws_shard_recv.p, log_n, width, bb::GEN, rho, ctx->ws_lde.p));
+    CK(cudaEventRecord(ctx->ev[2], st));
+
+    // ---- stage 3a: Merkle subtree over my rows; the G subtree roots are the nodes of level log_ms ----
+    {
+        const uint32_t* mats1[1] = {ctx->ws_lde.p};
+        RC(pb_merkle_commit(ctx, mats1, &width, 1, log_ms, ctx->ws_layers.p, nullptr));
+    }
+    CK(cudaEventRecord(ctx->ev[3], st));
+    RC(combine_roots(ctx, comm, root_ptr(ctx->ws_layers.p, log_ms), root_m));
+    for (int i = 0; i < 8; i++) proof->trace_root[i] = h_from_m(root_m[i]);
+    ch.observe(root_m, 8);
+    const bb::E4 alpha = ch.sample_ext();
+    for (int i = 0; i < 4; i++) proof->alpha[i] = h_from_m(alpha.c[i]);
+
+    // ---- stage 2: quotient values on my rows (all in chunk c = rho >> g1), gathered so that every rank holds both chunks ----
+    {
+        uint32_t* q_my = ctx->ws_shard_coef.p;                 // [4][Ms]
+        uint32_t* q_all = ctx->ws_f0.p;                        // [G][4][Ms]  (ws_f0 is free until FRI)
+        RC(pb_constraint_fold(ctx, a, ctx->ws_lde.p, Ms, proof->alpha, q_my));
+        const uint32_t sn = bb::pow(h_to_m(bb::GEN), (uint64_t)1 << log_n);
+        const uint32_t zinv = (rho >> s.g1) ? bb::inv(bb::sub(bb::neg(sn), bb::R1)) : bb::inv(bb::sub(sn, bb::R1));
+        shard::scale_kernel<<<(unsigned)((4 * Ms + 255) / 256), 256, 0, st>>>(q_my, 4 * Ms, zinv);
+        LAUNCHED(ctx);
+        CK(cudaEventRecord(ctx->ev[4], st));
+        COMM(all_gather, q_my, q_all, 4 * Ms * 4);
+        for (int b = 0; b < G; b++) {
+            const size_t c = (size_t)(b >> s.g1), h = (size_t)(b & (s.G1 - 1));
+            for (size_t l = 0; l < 4; l++)
+                CK(cudaMemcpyAsync(ctx->ws_q.p + (c * 4 + l) * N + h * Ms, q_all + ((size_t)b * 4 + l) * Ms, Ms * 4, cudaMemcpyDeviceToDevice, st));
+        }
+        const size_t tot = 8 * N;
+        ntt::bitrev_rows_kernel<<<(unsigned)((tot + 255) / 256), 256, 0, st>>>(ctx->ws_q.p, ctx->ws_qnat.p, (int)log_n, 8);
+        LAUNCHED(ctx);
+        // quotient chunk LDEs: every rank has the 8 columns, so each computes only its own block of rows
+        const uint32_t w2n_inv = h_from_m(bb::inv(h_root_of_unity_m((int)log_n + 1)));
+        RC(inverse_and_fold(ctx, s, ctx->ws_qnat.p, log_n, 4, 1u, rho, 1, ctx->ws_shard_coef.p, 0));
+        RC(forward_block(ctx, s, ctx->ws_shard_coef.p, log_n, 4, 1u, rho, ctx->ws_qlde.p));
+        RC(inverse_and_fold(ctx, s, ctx->ws_qnat.p + 4 * N, log_n, 4, w2n_inv, rho, 1, ctx->ws_shard_coef.p, 0));
+        RC(forward_block(ctx, s, ctx->ws_shard_coef.p, log_n, 4, w2n_inv, rho, ctx->ws_qlde.p + 4 * Ms));
+    }
+    CK(cudaEventRecord(ctx->ev[5], st));
+    {
+        const uint32_t* mats2[2] = {ctx->ws_qlde.p, ctx->ws_qlde.p + 4 * Ms};
+        const size_t w2[2] = {4, 4};
+        RC(pb_merkle_commit(ctx, mats2, w2, 2, log_ms, ctx->ws_layers_q.p, nullptr));
+    }
+    CK(cudaEventRecord(ctx->ev[6], st));
+    RC(combine_roots(ctx, comm, root_ptr(ctx->ws_layers_q.p, log_ms), root_m));
+    for (int i = 0; i < 8; i++) proof->quotient_root[i] = h_from_m(root_m[i]);
+    ch.observe(root_m, 8);
+    const bb::E4 zeta = ch.sample_ext();
+    for (int i = 0; i < 4; i++) proof->zeta[i] = h_from_m(zeta.c[i]);
+
+    // ---- openings at zeta: my trace columns, gathered; the 8 quotient columns on every rank ----
+    const size_t n_open = width + 8;
+    size_t open_rows = 1, log_open_rows = 0;
+    while (open_rows * 8 < 4 * n_open) { open_rows <<= 1; log_open_rows++; }
+    RC(ctx->ws_ys.ensure(std::max(8 * open_rows, 4 * ((size_t)G * per + 8))));
+    RC(ctx->ws_gather2.ensure(4 * per + 4 * (size_t)G * per));
+    {
+        uint32_t* ys_my = ctx->ws_gather2.p;                    // [per][4]
+        uint32_t* ys_all = ctx->ws_gather2.p + 4 * per;        // [G*per][4]
+        CK(cudaMemsetAsync(ys_my, 0, 16 * per, st));
+        if (w_my) RC(eval_at_point_m(ctx, d_my, log_n, w_my, h_to_m(1u), zeta, ys_my));
+        COMM(all_gather, ys_my, ys_all, 16 * per);
+        CK(cudaMemsetAsync(ctx->ws_ys.p, 0, 32 * open_rows, st));
+        CK(cudaMemcpyAsync(ctx->ws_ys.p, ys_all, 16 * width, cudaMemcpyDeviceToDevice, st));
+        const uint32_t g_c = bb::GEN, gw_c = h_from_m(bb::mul(h_to_m(bb::GEN), h_root_of_unity_m((int)log_n + 1)));
+        RC(eval_at_point_m(ctx, ctx->ws_qnat.p, log_n, 4, h_to_m(g_c), zeta, ctx->ws_ys.p + 4 * width));
+        RC(eval_at_point_m(ctx, ctx->ws_qnat.p + 4 * N, log_n, 4, h_to_m(gw_c), zeta, ctx->ws_ys.p + 4 * (width + 4)));
+    }
+    RC(ctx->ws_layers_open.ensure(8 * (2 * open_rows)));
+    RC(pb_merkle_commit_rows8(ctx, ctx->ws_ys.p, log_open_rows, ctx->ws_layers_open.p, nullptr));
+    std::vector<uint32_t>& ys_h = ctx->seg.ys;
+    ys_h.assign(4 * n_open, 0u);
+    CK(cudaMemcpyAsync(ys_h.data(), ctx->ws_ys.p, 16 * n_open, cudaMemcpyDeviceToHost, st));
+    RC(read_root(ctx, ctx->ws_layers_open.p, log_open_rows, root_m));
+    for (int i = 0; i < 8; i++) proof->openings_root[i] = h_from_m(root_m[i]);
+    ch.observe(root_m, 8);
+    const bb::E4 gamma = ch.sample_ext();
+    for (int i = 0; i < 4; i++) proof->gamma[i] = h_from_m(gamma.c[i]);
+
+    // ---- reduced opening on my rows ----
+    uint32_t* f = ctx->ws_f0.p;
+    uint32_t* f_next = ctx->ws_f1.p;
+    {
+        std::vector<const uint32_t*> cols(n_open);
+        for (size_t c = 0; c < width; c++) cols[c] = ctx->ws_lde.p + c * Ms;
+        for (size_t c = 0; c < 8; c++) cols[width + c] = ctx->ws_qlde.p + c * Ms;
+        RC(deep_quotient_m(ctx, cols, log_m, h_to_m(bb::GEN), zeta, gamma, ys_h.data(), f, (size_t)rho * Ms, Ms));
+    }
+    CK(cudaEventRecord(ctx->ev[8], st));
+
+    // ---- FRI commit phase: fold partners are adjacent, so a row block folds locally; per layer only the subtree root travels.
+    //      Below 2^SMALL entries per rank the codeword is gathered once and the remaining layers run replicated. ----
+    RC(ctx->ws_fri_trees.ensure(8 * (2 * std::max<size_t>(Ms, (size_t)1 << 12))));
+    size_t log_len = log_m;
+    uint32_t shift_m = h_to_m(bb::GEN);
+    uint32_t layer = 0;
+    bool sharded = true;
+    constexpr size_t SMALL = 6;
+    while (log_len > 1) {
+        if (sharded && log_len - (size_t)s.g < SMALL) {
+            const size_t loc = (size_t)1 << (log_len - s.g);
+            COMM(all_gather, f, f_next, 16 * loc);
+            std::swap(f, f_next);
+            sharded = false;
+        }
+        uint32_t* tree = ctx->ws_fri_trees.p;
+        if (sharded) {
+            const size_t log_rows = log_len - 1 - (size_t)s.g, loc_out = (size_t)1 << log_rows;
+            RC(pb_merkle_commit_rows8(ctx, f, log_rows, tree, nullptr));
+            RC(combine_roots(ctx, comm, root_ptr(tree, log_rows), root_m));
+            for (int i = 0; i < 8; i++) proof->fri_roots[layer][i] = h_from_m(root_m[i]);
+            ch.observe(root_m, 8);
+            const bb::E4 beta = ch.sample_ext();
+            for (int i = 0; i < 4; i++) proof->fri_betas[layer][i] = h_from_m(beta.c[i]);
+            RC(fri_fold_m(ctx, f, log_len, shift_m, beta, f_next, (size_t)rho * loc_out, loc_out));
+        } else {
+            RC(pb_merkle_commit_rows8(ctx, f, log_len - 1, tree, nullptr));
+            RC(read_root(ctx, tree, log_len - 1, root_m));
+            for (int i = 0; i < 8; i++) proof->fri_roots[layer][i] = h_from_m(root_m[i]);
+            ch.observe(root_m, 8);
+            const bb::E4 beta = ch.sample_ext();
+            for (int i = 0; i < 4; i++) proof->fri_betas[layer][i] = h_from_m(beta.c[i]);
+            RC(fri_fold_m(ctx, f, log_len, shift_m, beta, f_next));
+        }
+        std::swap(f, f_next);
+        shift_m = bb::mul(shift_m, shift_m);
+        log_len--;
+        layer++;
+    }
+    if (sharded) return PB_ERR_UNSUPPORTED;      // unreachable: make_shard_geom bounds log_n from below
+    proof->n_fri_layers = layer;
+    proof->final_len = 1u << log_len;
+    uint32_t fin[8 * 4];
+    CK(cudaMemcpyAsync(fin, f, 16 * proof->final_len, cudaMemcpyDeviceToHost, st));
+    CK(cudaEventRecord(ctx->ev[7], st));
+    CK(cudaStreamSynchronize(st));
+    for (uint32_t i = 0; i < proof->final_len; i++)
+        for (int l = 0; l < 4; l++) proof->final_poly[i][l] = h_from_m(fin[4 * i + l]);
+    for (int i = 0; i < 6; i++) cudaEventElapsedTime(&ctx->stage_ms[i], ctx->ev[i], ctx->ev[i + 1]);
+    cudaEventElapsedTime(&ctx->stage_ms[6], ctx->ev[6], ctx->ev[8]);
+    cudaEventElapsedTime(&ctx->stage_ms[7], ctx->ev[8], ctx->ev[7]);
+    cudaEventElapsedTime(&ctx->stage_ms[8], ctx->ev[0], ctx->ev[7]);
+#undef COMM
+#undef RC
+    return 0;
+}

@@ -109,3 +109,31 @@ def test_jit_codegen_compiles_for_sm100a_without_a_device():
     sp1 = (Span * 1)()
     sp1[0].off, sp1[0].len = 0, 2
     assert lib.pb_air_jit_compile_only(bad.ctypes.data_as(C.c_void_p), C.c_size_t(2), sp1, C.c_size_t(1), C.c_uint32(3), C.byref(sz)) == -4
+
+
+def test_shard_columns_partition():
+    """pb_shard_columns: contiguous blocks of ceil(W/G) columns, trailing ranks may be short or empty; no GPU needed"""
+    from powdr_b200.sharded import shard_columns
+    for width, world in [(2022, 8), (2022, 2), (12, 8), (5, 8), (256, 4), (1, 2)]:
+        blocks = [shard_columns(width, world, r) for r in range(world)]
+        per = -(-width // world)
+        assert all(c <= per for _, c in blocks)
+        cols = [c for f, n in blocks for c in range(f, f + n)]
+        assert cols == list(range(width))
+
+
+def test_comm_struct_wraps_python_callables():
+    from powdr_b200.sharded import Comm, PbComm
+    calls = []
+
+    class Rec(Comm):
+        def all_gather(self, send, recv, nbytes):
+            calls.append(("ag", send, recv, nbytes))
+
+        def all_to_all(self, send, recv, nbytes):
+            raise RuntimeError("boom")
+
+    c = Rec(1, 4)
+    assert isinstance(c.c, PbComm) and c.c.rank == 1 and c.c.world == 4
+    assert c.c.all_gather(None, 16, 32, 8) == 0 and calls == [("ag", 16, 32, 8)]
+    assert c.c.all_to_all(None, 0, 0, 0) == 1 and isinstance(c.error, RuntimeError)     # exceptions never cross into C
