@@ -324,12 +324,14 @@ int pb_prove_segment_sharded(pb_ctx_t* ctx, const pb_air_t* a, const uint32_t* t
 
     // ---- FRI commit phase: fold partners are adjacent, so a row block folds locally; per layer only the subtree root travels.
     //      Below 2^SMALL entries per rank the codeword is gathered once and the remaining layers run replicated. ----
-    RC(ctx->ws_fri_trees.ensure(8 * (2 * std::max<size_t>(Ms, (size_t)1 << 12))));
-    size_t log_len = log_m;
-    uint32_t shift_m = h_to_m(bb::GEN);
     uint32_t layer = 0;
     bool sharded = true;
-    constexpr size_t SMALL = 6;
+    RC(ctx->ws_fri_trees.ensure(8 * (2 * N)));
+    size_t log_len = log_m;
+    uint32_t shift_m = h_to_m(bb::GEN);
+    // every sharded layer costs one (latency-bound) root exchange, a replicated layer of 2^k entries costs microseconds: switch early
+    size_t SMALL = 14;
+    if (const char* e = getenv("PB_SHARD_FRI_SMALL")) SMALL = std::min<size_t>(24, std::max<size_t>(2, (size_t)atol(e)));
     while (log_len > 1) {
         if (sharded && log_len - (size_t)s.g < SMALL) {
             const size_t loc = (size_t)1 << (log_len - s.g);

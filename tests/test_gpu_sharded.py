@@ -71,3 +71,17 @@ def test_more_ranks_than_columns(ctx):
     assert trace.shape[0] < 8
     for p in prove_segment_threads(8, trace, bc, spans):
         assert p == single
+
+
+@pytest.mark.parametrize("small", ["2", "5", "24"])
+def test_fri_shard_to_replicated_switch_point_does_not_change_the_proof(ctx, monkeypatch, small):
+    """PB_SHARD_FRI_SMALL moves the layer at which the FRI codeword is gathered: 2 = fold sharded down to 4 entries per rank
+    (a root exchange per layer), 24 = gather immediately"""
+    from powdr_b200.sharded import prove_segment_threads
+    bc, spans, trace = _segment(10, 4, 11, seed=5)
+    air = ctx.air(bc, spans, trace.shape[0])
+    d_trace = ctx.to_device(trace)
+    single = ctx.prove_segment(air, d_trace.ptr, 11, trace.shape[0], on_device=True)
+    monkeypatch.setenv("PB_SHARD_FRI_SMALL", small)
+    for p in prove_segment_threads(4, trace, bc, spans):
+        assert p == single
