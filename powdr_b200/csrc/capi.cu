@@ -875,7 +875,13 @@ int pb_prove_segment(pb_ctx_t* ctx, const pb_air_t* a, const uint32_t* trace, si
         size_t cw = std::max<size_t>(8, ((((size_t)256 << 20) / (4 * N)) / 8) * 8);     // ~256 MB per chunk, multiple of the sponge rate
         if (const char* e = getenv("PB_PIPE_CHUNK_COLS")) cw = std::max<size_t>(8, ((size_t)atol(e) / 8) * 8);
         cw = std::min<size_t>(width, cw);
-        const size_t n_chunks = (width + cw - 1) / cw;
+        // ramp: the first copy has nothing to hide behind, so start with small chunks (8, 16, 32, ... columns) and double up to cw
+        std::vector<size_t> chunk_c0, chunk_w;
+        for (size_t c0 = 0, wk = 8; c0 < width; c0 += chunk_w.back(), wk = std::min(cw, 2 * wk)) {
+            chunk_c0.push_back(c0);
+            chunk_w.push_back(std::min(wk, width - c0));
+        }
+        const size_t n_chunks = chunk_w.size();
         RC(ctx->ws_trace.ensure(width * N));          // whole trace stays resident: it is read again for the openings at zeta
         d_trace_full = ctx->ws_trace.p;
         RC(ctx->ws_state.ensure(16 * M));
@@ -888,7 +894,7 @@ int pb_prove_segment(pb_ctx_t* ctx, const pb_air_t* a, const uint32_t* trace, si
         CK(cudaEventRecord(ctx->ev_free[1], st));
         for (size_t k = 0; k < n_chunks; k++) {
             const int b = (int)(k & 1);
-            const size_t c0 = k * cw, wk = std::min(cw, width - c0);
+            const size_t c0 = chunk_c0[k], wk = chunk_w[k];
             uint32_t* stage = ctx->ws_trace.p + c0 * N;
             CK(cudaStreamWaitEvent(ctx->copy_stream, ctx->ev_free[b], 0));
             CK(cudaMemcpyAsync(stage, trace + c0 * N, wk * N * 4, cudaMemcpyHostToDevice, ctx->copy_stream));
