@@ -6,6 +6,8 @@
 // library itself links against nothing but cudart; when either is missing, or PB_AIR_NO_JIT is set, the interpreter
 // kernel (still CUDA) is used instead.
 #pragma once
+#include <algorithm>
+#include <unordered_map>
 #include <cuda.h>
 #include <dlfcn.h>
 #include <nvrtc.h>
@@ -82,13 +84,40 @@ inline std::string generate(const std::vector<uint32_t>& code, const std::vector
     std::string src = PRELUDE;
     struct Val { bool lit; uint32_t mont; std::string name; };
     char buf[256];
-    const size_t GROUP_OPS = 600;
-    size_t k = 0, n_groups = 0, vid = 0;
+    const size_t GROUP_OPS = 600, GROUP_COLS = 32;
+    size_t k = 0, n_groups = 0, vid = 0, group_end = 0;
     while (k < spans.size()) {
         snprintf(buf, sizeof buf, "__device__ __noinline__ uint4 g%zu(const u32* __restrict__ b, u64 m, const uint4* __restrict__ ap, uint4 acc) {\n", n_groups);
         src += buf;
+        // A group = consecutive constraints that together read at most GROUP_COLS distinct columns.  Their loads are hoisted to
+        // the top of the function as volatile asm (kept in order, nothing to wait for), so one thread has that many loads in
+        // flight before the first use: ncu r01c showed the load-at-use version 90 % stalled on long_scoreboard at 54 % of HBM.
+        std::unordered_map<uint32_t, size_t> hoisted;
+        {
+            size_t ops_la = 0, k1 = k;
+            while (k1 < spans.size()) {
+                std::vector<uint32_t> fresh_cols;
+                for (uint32_t ip = spans[k1].off; ip < spans[k1].off + spans[k1].len; ip++) {
+                    const uint32_t w = code[ip];
+                    if ((w >> 28) == air::OP_PUSH_APC && !hoisted.count(w & 0x0fffffffu) &&
+                        std::find(fresh_cols.begin(), fresh_cols.end(), w & 0x0fffffffu) == fresh_cols.end())
+                        fresh_cols.push_back(w & 0x0fffffffu);
+                }
+                if (k1 > k && (ops_la + spans[k1].len > GROUP_OPS || hoisted.size() + fresh_cols.size() > GROUP_COLS)) break;
+                for (uint32_t c : fresh_cols)
+                    if (hoisted.size() < GROUP_COLS) {
+                        const size_t id = hoisted.size();
+                        hoisted[c] = id;
+                        snprintf(buf, sizeof buf, " u32 c%zu; asm volatile(\"ld.global.nc.u32 %%0, [%%1];\" : \"=r\"(c%zu) : \"l\"(b + %uull * m));\n", id, id, c);
+                        src += buf;
+                    }
+                ops_la += spans[k1].len;
+                k1++;
+            }
+            group_end = k1;
+        }
         size_t ops = 0;
-        while (k < spans.size() && (ops == 0 || ops + spans[k].len <= GROUP_OPS)) {
+        while (k < group_end) {
             std::vector<Val> st;
             for (uint32_t ip = spans[k].off; ip < spans[k].off + spans[k].len; ip++) {
                 const uint32_t w = code[ip], op = w >> 28, arg = w & 0x0fffffffu;
@@ -96,10 +125,16 @@ inline std::string generate(const std::vector<uint32_t>& code, const std::vector
                 auto as_str = [&](const Val& v) { return v.lit ? lit_str(v) : v.name; };
                 auto fresh = [&]() { snprintf(buf, sizeof buf, "v%zu", vid++); return std::string(buf); };
                 if (op == air::OP_PUSH_APC) {
-                    Val v{false, 0, fresh()};
-                    snprintf(buf, sizeof buf, " u32 %s = __ldg(b + %uull * m);\n", v.name.c_str(), arg);
-                    src += buf;
-                    st.push_back(v);
+                    auto h = hoisted.find(arg);
+                    if (h != hoisted.end()) {
+                        snprintf(buf, sizeof buf, "c%zu", h->second);
+                        st.push_back(Val{false, 0, buf});
+                    } else {
+                        Val v{false, 0, fresh()};
+                        snprintf(buf, sizeof buf, " u32 %s = __ldg(b + %uull * m);\n", v.name.c_str(), arg);
+                        src += buf;
+                        st.push_back(v);
+                    }
                 } else if (op == air::OP_PUSH_CONST) {
                     st.push_back(Val{true, pool[arg], ""});
                 } else if (op == air::OP_ADD || op == air::OP_SUB || op == air::OP_MUL) {
@@ -201,6 +236,11 @@ inline int build(const std::vector<uint32_t>& code, const std::vector<air::Span>
     a.GetCUBIN(prog, cubin.data());
     a.DestroyProgram(&prog);
     if (cubin_out) *cubin_out = cubin;
+    if (const char* dump = getenv("PB_AIR_JIT_DUMP")) {       // debugging aid: <path>.cu and <path>.cubin (cuobjdump -sass / -res-usage)
+        const std::string base = dump;
+        if (FILE* f = fopen((base + ".cu").c_str(), "w")) { fwrite(src.data(), 1, src.size(), f); fclose(f); }
+        if (FILE* f = fopen((base + ".cubin").c_str(), "wb")) { fwrite(cubin.data(), 1, cubin.size(), f); fclose(f); }
+    }
     if (!out) return 0;
     if (a.ModuleLoadData(&out->mod, cubin.data()) != CUDA_SUCCESS) return 6;
     if (a.ModuleGetFunction(&out->fn, out->mod, "pbq") != CUDA_SUCCESS) { a.ModuleUnload(out->mod); out->mod = nullptr; return 7; }

@@ -169,7 +169,7 @@ struct pb_ctx {
     // pb_prove_segment workspace
     DevBuf<uint32_t> ws_trace, ws_lde, ws_layers, ws_q, ws_qnat, ws_qlde, ws_f0, ws_f1, ws_state, ws_ys;
     DevBuf<uint4> ws_w, ws_part;          // barycentric weights [N], per-CTA partial sums of the openings
-    DevBuf<uint2> ws_gp;                  // Shoup pairs of the gamma powers of the reduced opening
+    DevBuf<uint2> ws_gp;                  // gamma powers of the reduced opening, canonical (one uint4 per column)
     DevBuf<const uint32_t*> coltab2;
     DevBuf<uint32_t> ws_layers_q, ws_layers_open, ws_fri_words, ws_fri_trees, ws_qidx, ws_qout;
     DevBuf<uint32_t> ws_shard_send, ws_shard_recv, ws_shard_coef, ws_gather, ws_gather2;   // multi-GPU segment (shard_api.inl)
@@ -793,23 +793,38 @@ static int deep_quotient_m(pb_ctx* ctx, const std::vector<const uint32_t*>& cols
                            bb::E4 gamma_m, const uint32_t* ys_m, uint32_t* d_out, size_t row0 = 0, size_t n_rows = 0) {
     // rows [row0, row0 + n_rows) of the domain only (n_rows = 0: all of it); cols[] then point at that row block
     const size_t n_cols = cols.size(), M = n_rows ? n_rows : (size_t)1 << log_m;
-    std::vector<uint2> gp(4 * n_cols);
+    if (n_cols == 0) return PB_ERR_INVALID_ARG;
+    std::vector<uint4> gs(n_cols);
     bb::E4 cur = {{bb::R1, 0u, 0u, 0u}}, ysum = {{0u, 0u, 0u, 0u}};
     for (size_t j = 0; j < n_cols; j++) {
-        for (int l = 0; l < 4; l++) gp[4 * j + l] = bb::shoup_pair(h_from_m(cur.c[l]));
+        uint32_t c[4];
+        for (int l = 0; l < 4; l++) c[l] = h_from_m(cur.c[l]);
+        gs[j] = make_uint4(c[0], c[1], c[2], c[3]);
         bb::E4 y;
         memcpy(y.c, ys_m + 4 * j, 16);
         ysum = bb::e4_add(ysum, bb::e4_mul(cur, y));
         cur = bb::e4_mul(cur, gamma_m);
     }
-    int rc = ctx->ws_gp.ensure(4 * n_cols);
+    // runs of equally spaced columns
+    deep::DeepSegs segs{};
+    for (size_t j = 0; j < n_cols;) {
+        if (segs.n == deep::DQ_MAX_SEGS) return PB_ERR_UNSUPPORTED;
+        size_t k = j + 1;
+        const ptrdiff_t st = k < n_cols ? cols[k] - cols[j] : 0;
+        while (k < n_cols && st > 0 && cols[k] - cols[k - 1] == st) k++;
+        if (st <= 0) k = j + 1;
+        segs.base[segs.n] = cols[j];
+        segs.stride[segs.n] = st > 0 ? (size_t)st : 0;
+        segs.count[segs.n] = (uint32_t)(k - j);
+        segs.n++;
+        j = k;
+    }
+    int rc = ctx->ws_gp.ensure(2 * n_cols);          // uint2 elements: one uint4 per column
     if (rc) return rc;
-    rc = ctx->coltab2.ensure(n_cols);
-    if (rc) return rc;
-    CK(cudaMemcpyAsync(ctx->ws_gp.p, gp.data(), gp.size() * sizeof(uint2), cudaMemcpyHostToDevice, ctx->stream));
-    CK(cudaMemcpyAsync(ctx->coltab2.p, cols.data(), n_cols * sizeof(void*), cudaMemcpyHostToDevice, ctx->stream));
-    deep::deep_quotient_kernel<<<(unsigned)((M + 255) / 256), 256, 0, ctx->stream>>>(ctx->coltab2.p, (uint32_t)n_cols, M, (int)log_m, row0, shift_m,
-                                                                                    h_root_of_unity_m((int)log_m), ctx->ws_gp.p, ysum, zeta_m,
+    CK(cudaMemcpyAsync(ctx->ws_gp.p, gs.data(), gs.size() * sizeof(uint4), cudaMemcpyHostToDevice, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));           // gs is a host temporary
+    deep::deep_quotient_kernel<<<(unsigned)((M + 255) / 256), 256, 0, ctx->stream>>>(segs, M, (int)log_m, row0, shift_m, h_root_of_unity_m((int)log_m),
+                                                                                    reinterpret_cast<const uint4*>(ctx->ws_gp.p), ysum, zeta_m,
                                                                                     reinterpret_cast<uint4*>(d_out));
     LAUNCHED(ctx);
     CK(cudaGetLastError());
