@@ -57,7 +57,13 @@ BB_HD int32_t smul(int32_t a, int32_t b) {
     int32_t lo, hi;
     asm("mul.wide.s32 %0, %1, %2;" : "=l"(t) : "r"(a), "r"(b));
     asm("mov.b64 {%0, %1}, %2;" : "=r"(lo), "=r"(hi) : "l"(t));
+#ifdef PB_V_PINV_SHIFT
+    // experiment: p^-1 mod 2^32 = 2^31 + 2^27 + 1, so lo * p^-1 is two shift-adds on the ALU pipe instead of an IMAD
+    const uint32_t ulo = (uint32_t)lo;
+    int32_t m = (int32_t)(ulo + (ulo << 27) + (ulo << 31));
+#else
     int32_t m = (int32_t)((uint32_t)lo * PINV);
+#endif
 #ifdef PB_V_SMUL_PIN
     return __viaddmin_s32(hi, -__mulhi(m, (int32_t)P), 0x7fffffff);   // experiment: pin the subtraction to the ALU pipe
 #else

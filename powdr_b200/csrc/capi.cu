@@ -183,6 +183,8 @@ struct pb_ctx {
         std::vector<uint32_t> ys;            // opened values, Montgomery, [(width + 8)][4]
     } seg;
     cudaStream_t copy_stream = nullptr;   // H2D chunks of the host-input pipeline
+    cudaStream_t lde_streams[8] = {nullptr};   // PB_LDE_STREAMS experiment
+    cudaEvent_t lde_join[8] = {nullptr}, lde_fork = nullptr;
     cudaEvent_t ev_copy[2] = {nullptr}, ev_free[2] = {nullptr};
     cudaEvent_t ev[10] = {nullptr};
     float stage_ms[9] = {0};               // h2d, lde, merkle, quotient, qlde, qmerkle, open(+deep), fri, total
@@ -296,18 +298,17 @@ int merkle_upper(pb_ctx* ctx, uint32_t* d_layers, size_t log_h) {
     size_t n = (size_t)1 << log_h;
     uint32_t* prev = d_layers;
     while (n > 1) {
-        size_t parents = n >> 1;
-        uint32_t* next = prev + 8 * n;
         if (n <= 1024) {
             p2::compress_tail_kernel<<<1, 512, 0, ctx->stream>>>(reinterpret_cast<uint4*>(prev), (uint32_t)n);
             LAUNCHED(ctx);
             break;
         }
-        p2::compress_layer_kernel<<<(unsigned)((parents + 255) / 256), 256, 0, ctx->stream>>>(
-            reinterpret_cast<const uint4*>(prev), reinterpret_cast<uint4*>(next), parents);
+        // up to 10 levels per launch, leaving at least 1024 nodes for the single-CTA tail
+        int kb = 0;
+        while (kb < 10 && (n >> (kb + 1)) >= 1024) kb++;
+        p2::compress_block_kernel<<<(unsigned)(n >> kb), 256, 0, ctx->stream>>>(reinterpret_cast<uint4*>(prev), n, kb);
         LAUNCHED(ctx);
-        prev = next;
-        n = parents;
+        for (int l = 0; l < kb; l++) { prev += 8 * n; n >>= 1; }
     }
     CK(cudaGetLastError());
     return 0;
@@ -521,13 +522,39 @@ int pb_lde_batch(pb_ctx_t* ctx, const uint32_t* d_trace, size_t log_n, size_t wi
     if (rc) return rc;
     const NttGeom g = make_geom(n);
     const size_t batch = lde_column_batch(N, width);
-    rc = ctx->tmp.ensure(batch * N); if (rc) return rc;
-    rc = ctx->tmp2.ensure(batch * N * cosets); if (rc) return rc;
-    for (size_t c0 = 0; c0 < width; c0 += batch) {
-        const unsigned nb = (unsigned)std::min(batch, width - c0);
-        ntt_inverse_cols(ctx, g, tw, d_trace + c0 * N, nb, ctx->tmp.p);
-        ntt_forward_cols(ctx, g, tw, (int)log_blowup, ctx->tmp.p, nb, ctx->tmp2.p, d_lde + c0 * N * cosets, N * cosets);
+    // PB_LDE_STREAMS > 1 (experiment): small column batches round-robin over several streams, so the four passes of different
+    // batches overlap and the intermediates of the batches in flight can stay in L2
+    int n_streams = 1;
+    if (const char* e = getenv("PB_LDE_STREAMS")) n_streams = std::min(8, std::max(1, atoi(e)));
+    rc = ctx->tmp.ensure((size_t)n_streams * batch * N); if (rc) return rc;
+    rc = ctx->tmp2.ensure((size_t)n_streams * batch * N * cosets); if (rc) return rc;
+    cudaStream_t main_stream = ctx->stream;
+    if (n_streams > 1) {
+        for (int i = 0; i < n_streams; i++)
+            if (!ctx->lde_streams[i]) {
+                CK(cudaStreamCreateWithFlags(&ctx->lde_streams[i], cudaStreamNonBlocking));
+                CK(cudaEventCreateWithFlags(&ctx->lde_join[i], cudaEventDisableTiming));
+            }
+        if (!ctx->lde_fork) CK(cudaEventCreateWithFlags(&ctx->lde_fork, cudaEventDisableTiming));
+        CK(cudaEventRecord(ctx->lde_fork, main_stream));
+        for (int i = 0; i < n_streams; i++) CK(cudaStreamWaitEvent(ctx->lde_streams[i], ctx->lde_fork, 0));
     }
+    size_t k = 0;
+    for (size_t c0 = 0; c0 < width; c0 += batch, k++) {
+        const unsigned nb = (unsigned)std::min(batch, width - c0);
+        const size_t sidx = k % (size_t)n_streams;
+        if (n_streams > 1) ctx->stream = ctx->lde_streams[sidx];
+        uint32_t* t1 = ctx->tmp.p + sidx * batch * N;
+        uint32_t* t2 = ctx->tmp2.p + sidx * batch * N * cosets;
+        ntt_inverse_cols(ctx, g, tw, d_trace + c0 * N, nb, t1);
+        ntt_forward_cols(ctx, g, tw, (int)log_blowup, t1, nb, t2, d_lde + c0 * N * cosets, N * cosets);
+    }
+    ctx->stream = main_stream;
+    if (n_streams > 1)
+        for (int i = 0; i < n_streams; i++) {
+            CK(cudaEventRecord(ctx->lde_join[i], ctx->lde_streams[i]));
+            CK(cudaStreamWaitEvent(main_stream, ctx->lde_join[i], 0));
+        }
     CK(cudaGetLastError());
     return 0;
 }

@@ -253,6 +253,34 @@ __global__ void __launch_bounds__(512) compress_tail_kernel(uint4* layer, uint32
     }
 }
 
+// kb tree levels per launch: CTA b reduces nodes [b << kb, (b + 1) << kb) of the level at `level` (n nodes) to one node,
+// writing every intermediate level at its place in the node-major layer array (level l+1 follows level l).  A thread reads
+// back only what its own CTA wrote, so __syncthreads() orders the global traffic.  Cuts the launches of a 2^21-leaf tree
+// from 12 to 3 (FRI commits 20 trees per segment, so launch latency was most of that phase).
+__global__ void __launch_bounds__(256) compress_block_kernel(uint4* level, size_t n, int kb) {
+    uint4* lvl = level;
+    size_t nn = n, off = (size_t)blockIdx.x << kb;
+    uint32_t cnt = 1u << kb;
+    for (int l = 0; l < kb; l++) {
+        uint4* next = lvl + 2 * nn;
+        const uint32_t m = cnt >> 1;
+        const size_t q0 = off >> 1;
+        for (uint32_t j = threadIdx.x; j < m; j += blockDim.x) {
+            const uint4* pr = lvl + 4 * (q0 + j);
+            uint4 a = pr[0], b = pr[1], c = pr[2], d = pr[3];
+            uint32_t s[16] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w, c.x, c.y, c.z, c.w, d.x, d.y, d.z, d.w};
+            permute(s);
+            next[2 * (q0 + j)] = make_uint4(s[0], s[1], s[2], s[3]);
+            next[2 * (q0 + j) + 1] = make_uint4(s[4], s[5], s[6], s[7]);
+        }
+        __syncthreads();
+        lvl = next;
+        nn >>= 1;
+        cnt = m;
+        off = q0;
+    }
+}
+
 // single permutation per thread on [n][16] states -- used by tests and the throughput micro-benchmark
 #ifndef PB_V_MINBLOCKS
 #define PB_V_MINBLOCKS 1

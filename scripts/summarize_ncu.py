@@ -39,9 +39,13 @@ def rep(path):
                     e[base] = float(d[k].replace(",", ""))
                 except Exception:
                     e[base] = d[k]
-        if "dram__bytes_read.sum" in e and "dram__bytes_write.sum" in e:
-            e["dram_bytes_total"] = e["dram__bytes_read.sum"] + e["dram__bytes_write.sum"]
         e["units"] = {k: rows[1][hdr.index(k)] for k in hdr if k in e and k in KEYS}
+        if "dram__bytes_read.sum" in e and "dram__bytes_write.sum" in e:       # ncu picks a unit per column: normalise to bytes
+            scale = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9, "Tbyte": 1e12}
+            rd = e["dram__bytes_read.sum"] * scale.get(e["units"].get("dram__bytes_read.sum"), 1.0)
+            wr = e["dram__bytes_write.sum"] * scale.get(e["units"].get("dram__bytes_write.sum"), 1.0)
+            e["dram_bytes_total"] = rd + wr
+            e["dram_bytes_read"], e["dram_bytes_write"] = rd, wr
         res.append(e)
     return res
 
