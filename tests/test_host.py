@@ -137,3 +137,27 @@ def test_comm_struct_wraps_python_callables():
     assert isinstance(c.c, PbComm) and c.c.rank == 1 and c.c.world == 4
     assert c.c.all_gather(None, 16, 32, 8) == 0 and calls == [("ag", 16, 32, 8)]
     assert c.c.all_to_all(None, 0, 0, 0) == 1 and isinstance(c.error, RuntimeError)     # exceptions never cross into C
+
+
+def test_header_is_plain_c_and_cxx(tmp_path):
+    """include/powdr_b200.h is the drop-in boundary: it must compile as C99 and as C++ with nothing but the standard headers"""
+    import subprocess
+    hdr = os.path.join(ROOT, "include")
+    c = tmp_path / "t.c"
+    c.write_text('#include "powdr_b200.h"\nint main(void) { pb_segment_proof_t p; pb_comm_t c; (void)p; (void)c; return PB_ERR_COMM == -6 ? 0 : 1; }\n')
+    subprocess.check_call(["/usr/bin/gcc", "-std=c99", "-Wall", "-Werror", "-pedantic", "-fsyntax-only", "-I", hdr, str(c)])
+    cc = tmp_path / "t.cc"
+    cc.write_text(c.read_text())
+    subprocess.check_call(["/usr/bin/g++", "-std=c++17", "-Wall", "-Werror", "-fsyntax-only", "-I", hdr, str(cc)])
+
+
+def test_product_never_imports_the_oracle():
+    """oracle/ is test infrastructure: nothing under powdr_b200/ (python or CUDA) may reference it"""
+    pkg = os.path.join(ROOT, "powdr_b200")
+    for dirpath, _, files in os.walk(pkg):
+        if "_lib" in dirpath or "__pycache__" in dirpath:
+            continue
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".inl", ".h")):
+                txt = open(os.path.join(dirpath, f), errors="replace").read()
+                assert "import oracle" not in txt and "from oracle" not in txt and "oracle/" not in txt.replace("the oracle/", ""), f
