@@ -12,6 +12,7 @@ memory (H2D inside the timed region, proof read back).  Inputs (8.5 GB/segment) 
 needed between iterations.  torch is plumbing only: device memory, the stream, events and torch.distributed/NCCL.
 """
 import argparse
+import math
 import json
 import os
 import subprocess
@@ -259,6 +260,14 @@ def run_native(a):
                          "unit": "GB/s", "frac": achieved / peak, "traffic": traffic, "launches_timed": n_leaf,
                          "avg_launch_ms": leaf_ms / max(1, n_leaf), "peak_source": "MEASURED_PEAKS.json" if peaks else "fallback",
                          "note": "integer-ALU-bound kernel (~22 mulmod per byte); HBM fraction is reported as the contract asks"},
+            # the same kernel against the roof that actually binds it: the integer multiplier pipe.  One Poseidon2 permutation
+            # is 564 Montgomery products (10 pipe cycles each) + 117 constant products (8 cycles) = 657.6 Montgomery-product
+            # equivalents; peak = 12.6 products/clk/SM measured by scripts/microbench.cu (profiles/r01_microbench.txt)
+            "roofline_integer": (lambda perms, peak_i: {"bound": "imad pipe", "achieved": perms * 657.6 / (leaf_ms / 1e3) / 1e12 if leaf_ms > 0 else 0.0,
+                                                        "peak": peak_i / 1e12, "unit": "T mulmod/s",
+                                                        "frac": (perms * 657.6 / (leaf_ms / 1e3)) / peak_i if leaf_ms > 0 else 0.0})(
+                (leaf_bytes / (4.0 * ww + 32.0)) * math.ceil(ww / 8.0) if n_leaf else 0.0,
+                12.6 * 148 * (clocks or {}).get("sm_mhz", 1965.0) * 1e6),
             "stages_ms": stage_ms,
             "stage_roofline_frac": {k: (alg[k] / 1e9) / (stage_ms[k] / 1e3) / peak for k in alg if stage_ms.get(k, 0) > 0},
             "segments_per_s": world / (ms_per_step / 1e3),
