@@ -153,6 +153,7 @@ def run_native(a):
     dist = None
     if world > 1:
         import torch.distributed as dist
+        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")     # NCCL's version banner goes to stdout by default: keep stdout = the JSON line
         dist.init_process_group("nccl", device_id=dev)
 
     stream = torch.cuda.current_stream()
@@ -377,6 +378,7 @@ def run_multichip(a):
     dist = None
     if world > 1:
         import torch.distributed as dist
+        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")     # NCCL's version banner goes to stdout by default: keep stdout = the JSON line
         dist.init_process_group("nccl", device_id=dev)
     stream = torch.cuda.current_stream()
     ctx = powdr_b200.Context(local, stream.cuda_stream)
