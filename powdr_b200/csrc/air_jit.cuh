@@ -7,6 +7,8 @@
 // kernel (still CUDA) is used instead.
 #pragma once
 #include <algorithm>
+#include <atomic>
+#include <thread>
 #include <unordered_map>
 #include <cuda.h>
 #include <dlfcn.h>
@@ -61,8 +63,10 @@ inline Api& api() {
 }
 
 struct Kernel {
-    CUmodule mod = nullptr;
-    CUfunction fn = nullptr;
+    // the AIR's constraints are split into chunks, one module each (compiled in parallel: ptxas time grows faster than linearly
+    // with the size of a module); chunk c adds its constraints' contribution to the running fold
+    std::vector<CUmodule> mods;
+    std::vector<CUfunction> fns;
 };
 
 static const char* PRELUDE = R"(
@@ -80,12 +84,19 @@ __device__ __forceinline__ uint4 fold(uint4 acc, u32 c, uint4 w) {
 )";
 
 // packed program (air.cuh encoding) -> CUDA C.  Literals stay symbolic so constant operands become Shoup products.
-inline std::string generate(const std::vector<uint32_t>& code, const std::vector<air::Span>& spans, const std::vector<uint32_t>& pool) {
+inline std::string generate(const std::vector<uint32_t>& code, const std::vector<air::Span>& spans_all, const std::vector<uint32_t>& pool,
+                            size_t k_begin, size_t k_end) {
+    // constraints [k_begin, k_end) only; alpha-power indices stay global
+    struct SpanView {
+        const std::vector<air::Span>& v; size_t e;
+        size_t size() const { return e; }
+        const air::Span& operator[](size_t i) const { return v[i]; }
+    } spans{spans_all, k_end};
     std::string src = PRELUDE;
     struct Val { bool lit; uint32_t mont; std::string name; };
     char buf[256];
     const size_t GROUP_OPS = 600, GROUP_COLS = 32;
-    size_t k = 0, n_groups = 0, vid = 0, group_end = 0;
+    size_t k = k_begin, n_groups = 0, vid = 0, group_end = 0;
     while (k < spans.size()) {
         snprintf(buf, sizeof buf, "__device__ __noinline__ uint4 g%zu(const u32* __restrict__ b, u64 m, const uint4* __restrict__ ap, uint4 acc) {\n", n_groups);
         src += buf;
@@ -183,17 +194,20 @@ inline std::string generate(const std::vector<uint32_t>& code, const std::vector
     }
     src += R"(
 extern "C" __global__ void __launch_bounds__(256) pbq(const u32* __restrict__ mat, u64 m, int log_n, const uint4* __restrict__ ap,
-                                                       u32 zinv0, u32 zinv1, u32* __restrict__ out, int apply_zinv) {
+                                                       u32 zinv0, u32 zinv1, u32* __restrict__ out, int apply_zinv,
+                                                       const u32* __restrict__ raw_in, u32* __restrict__ raw_out) {
     const u64 r = (u64)blockIdx.x * 256ull + threadIdx.x;
     if (r >= m) return;
     const u32* b = mat + r;
     uint4 acc = make_uint4(0u, 0u, 0u, 0u);
+    if (raw_in) acc = make_uint4(raw_in[r], raw_in[m + r], raw_in[2 * m + r], raw_in[3 * m + r]);      // fold of the earlier chunks
 )";
     for (size_t g = 0; g < n_groups; g++) {
         snprintf(buf, sizeof buf, "    acc = g%zu(b, m, ap, acc);\n", g);
         src += buf;
     }
     src += R"(
+    if (raw_out) { raw_out[r] = acc.x; raw_out[m + r] = acc.y; raw_out[2 * m + r] = acc.z; raw_out[3 * m + r] = acc.w; return; }
     if (apply_zinv) {
         const u64 n = 1ull << log_n, chunk = r >> log_n, j = r & (n - 1);
         const u32 z = chunk ? zinv1 : zinv0;
@@ -207,14 +221,9 @@ extern "C" __global__ void __launch_bounds__(256) pbq(const u32* __restrict__ ma
     return src;
 }
 
-// returns 0 and fills `out` on success; non-zero when the JIT path is unavailable (caller keeps the interpreter)
-inline int build(const std::vector<uint32_t>& code, const std::vector<air::Span>& spans, const std::vector<uint32_t>& pool, Kernel* out,
-                 std::vector<char>* cubin_out = nullptr) {
-    if (getenv("PB_AIR_NO_JIT")) return 1;
-    if (code.size() > 400000) return 2;                        // keep compile time bounded; huge AIRs stay on the interpreter
+// one chunk: source -> cubin (thread-safe: distinct NVRTC programs)
+inline int compile_chunk(const std::string& src, std::vector<char>& cubin) {
     Api& a = api();
-    if (!a.nvrtc_ok || (out && !a.ok)) return 3;
-    const std::string src = generate(code, spans, pool);
     nvrtcProgram prog;
     if (a.CreateProgram(&prog, src.c_str(), "pb_air.cu", 0, nullptr, nullptr) != NVRTC_SUCCESS) return 4;
     const char* opts[] = {"--gpu-architecture=sm_100a", "-std=c++17", "-lineinfo"};
@@ -232,32 +241,93 @@ inline int build(const std::vector<uint32_t>& code, const std::vector<air::Span>
     }
     size_t sz = 0;
     a.GetCUBINSize(prog, &sz);
-    std::vector<char> cubin(sz);
+    cubin.resize(sz);
     a.GetCUBIN(prog, cubin.data());
     a.DestroyProgram(&prog);
-    if (cubin_out) *cubin_out = cubin;
-    if (const char* dump = getenv("PB_AIR_JIT_DUMP")) {       // debugging aid: <path>.cu and <path>.cubin (cuobjdump -sass / -res-usage)
-        const std::string base = dump;
-        if (FILE* f = fopen((base + ".cu").c_str(), "w")) { fwrite(src.data(), 1, src.size(), f); fclose(f); }
-        if (FILE* f = fopen((base + ".cubin").c_str(), "wb")) { fwrite(cubin.data(), 1, cubin.size(), f); fclose(f); }
-    }
-    if (!out) return 0;
-    if (a.ModuleLoadData(&out->mod, cubin.data()) != CUDA_SUCCESS) return 6;
-    if (a.ModuleGetFunction(&out->fn, out->mod, "pbq") != CUDA_SUCCESS) { a.ModuleUnload(out->mod); out->mod = nullptr; return 7; }
     return 0;
 }
 
+// returns 0 and fills `out` on success; non-zero when the JIT path is unavailable (caller keeps the interpreter).
+// Measured (8 shared cores): one module for a 41 k-word AIR (3771 constraints) took 537 s in ptxas; 4 k-word chunks compiled
+// on all host threads bring key generation back to seconds (the running fold crosses chunks through a [4][rows] buffer,
+// +1 % traffic for the keccak shape).
+inline int build(const std::vector<uint32_t>& code, const std::vector<air::Span>& spans, const std::vector<uint32_t>& pool, Kernel* out,
+                 size_t* cubin_bytes = nullptr) {
+    if (getenv("PB_AIR_NO_JIT")) return 1;
+    if (code.size() > 1000000) return 2;                       // keep compile time bounded; huge AIRs stay on the interpreter
+    Api& a = api();
+    if (!a.nvrtc_ok || (out && !a.ok)) return 3;
+    size_t chunk_words = 2000;      // keccak shape (7.2 k words): 4 modules, 2.7 s instead of 7.8 s; sha256 shape: 13 s; 141 k-word pre-opt machine: 30 s
+    if (const char* e = getenv("PB_AIR_JIT_CHUNK")) chunk_words = std::max<size_t>(100, (size_t)atol(e));
+    std::vector<size_t> bounds{0};
+    for (size_t k = 0, w = 0; k < spans.size(); k++) {
+        if (w > 0 && w + spans[k].len > chunk_words) { bounds.push_back(k); w = 0; }
+        w += spans[k].len;
+    }
+    bounds.push_back(spans.size());
+    const size_t n_chunks = bounds.size() - 1;
+    std::vector<std::vector<char>> cubins(n_chunks);
+    std::vector<int> rcs(n_chunks, 0);
+    std::atomic<size_t> next{0};
+    auto worker = [&]() {
+        for (size_t c = next.fetch_add(1); c < n_chunks; c = next.fetch_add(1)) {
+            const std::string src = generate(code, spans, pool, bounds[c], bounds[c + 1]);
+            rcs[c] = compile_chunk(src, cubins[c]);
+            if (const char* dump = getenv("PB_AIR_JIT_DUMP")) {       // debugging aid: <path>.<chunk>.cu / .cubin (cuobjdump -sass / -res-usage)
+                const std::string base = std::string(dump) + "." + std::to_string(c);
+                if (FILE* f = fopen((base + ".cu").c_str(), "w")) { fwrite(src.data(), 1, src.size(), f); fclose(f); }
+                if (FILE* f = fopen((base + ".cubin").c_str(), "wb")) { fwrite(cubins[c].data(), 1, cubins[c].size(), f); fclose(f); }
+            }
+        }
+    };
+    size_t n_threads = std::min<size_t>(n_chunks, std::max(1u, std::thread::hardware_concurrency()));
+    if (const char* e = getenv("PB_AIR_JIT_THREADS")) n_threads = std::min<size_t>(n_chunks, std::max<size_t>(1, (size_t)atol(e)));
+    std::vector<std::thread> pool_threads;
+    for (size_t t = 1; t < n_threads; t++) pool_threads.emplace_back(worker);
+    worker();
+    for (auto& t : pool_threads) t.join();
+    size_t total = 0;
+    for (size_t c = 0; c < n_chunks; c++) {
+        if (rcs[c]) return rcs[c];
+        total += cubins[c].size();
+    }
+    if (cubin_bytes) *cubin_bytes = total;
+    if (!out) return 0;
+    for (size_t c = 0; c < n_chunks; c++) {
+        CUmodule mod = nullptr;
+        CUfunction fn = nullptr;
+        if (a.ModuleLoadData(&mod, cubins[c].data()) != CUDA_SUCCESS || a.ModuleGetFunction(&fn, mod, "pbq") != CUDA_SUCCESS) {
+            if (mod) a.ModuleUnload(mod);
+            for (CUmodule m2 : out->mods) a.ModuleUnload(m2);
+            out->mods.clear();
+            out->fns.clear();
+            return 6;
+        }
+        out->mods.push_back(mod);
+        out->fns.push_back(fn);
+    }
+    return 0;
+}
+
+// raw: [4][m] scratch for the running fold between chunks (needed only when the kernel has more than one chunk)
 inline int launch(const Kernel& k, cudaStream_t st, const uint32_t* mat, unsigned long long m, int log_n, const uint32_t* ap, uint32_t zinv0,
-                  uint32_t zinv1, uint32_t* out, int apply_zinv) {
-    void* args[] = {(void*)&mat, (void*)&m, (void*)&log_n, (void*)&ap, (void*)&zinv0, (void*)&zinv1, (void*)&out, (void*)&apply_zinv};
-    CUresult rc = api().LaunchKernel(k.fn, (unsigned)((m + 255) / 256), 1, 1, 256, 1, 1, 0, (CUstream)st, args, nullptr);
-    return rc == CUDA_SUCCESS ? 0 : 700 + (int)rc;
+                  uint32_t zinv1, uint32_t* out, int apply_zinv, uint32_t* raw) {
+    if (k.fns.size() > 1 && !raw) return 699;
+    for (size_t c = 0; c < k.fns.size(); c++) {
+        const uint32_t* raw_in = c > 0 ? raw : nullptr;
+        uint32_t* raw_out = c + 1 < k.fns.size() ? raw : nullptr;
+        void* args[] = {(void*)&mat, (void*)&m, (void*)&log_n, (void*)&ap, (void*)&zinv0, (void*)&zinv1, (void*)&out, (void*)&apply_zinv,
+                        (void*)&raw_in, (void*)&raw_out};
+        CUresult rc = api().LaunchKernel(k.fns[c], (unsigned)((m + 255) / 256), 1, 1, 256, 1, 1, 0, (CUstream)st, args, nullptr);
+        if (rc != CUDA_SUCCESS) return 700 + (int)rc;
+    }
+    return 0;
 }
 
 inline void destroy(Kernel& k) {
-    if (k.mod) api().ModuleUnload(k.mod);
-    k.mod = nullptr;
-    k.fn = nullptr;
+    for (CUmodule m : k.mods) api().ModuleUnload(m);
+    k.mods.clear();
+    k.fns.clear();
 }
 
 }  // namespace airjit

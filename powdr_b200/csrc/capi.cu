@@ -173,6 +173,7 @@ struct pb_ctx {
     DevBuf<const uint32_t*> coltab2;
     DevBuf<uint32_t> ws_layers_q, ws_layers_open, ws_fri_words, ws_fri_trees, ws_qidx, ws_qout;
     DevBuf<uint32_t> ws_shard_send, ws_shard_recv, ws_shard_coef, ws_gather, ws_gather2;   // multi-GPU segment (shard_api.inl)
+    DevBuf<uint32_t> ws_qraw;             // running constraint fold between the chunks of a JIT-compiled AIR, [4][rows]
     // what pb_query_segment needs from the last pb_prove_segment (everything stays resident on the device)
     struct {
         bool valid = false;
@@ -362,7 +363,7 @@ int pb_ctx_destroy(pb_ctx_t* ctx) {
     ctx->ws_ys.release(); ctx->ws_w.release(); ctx->ws_part.release(); ctx->ws_gp.release(); ctx->coltab2.release();
     ctx->ws_layers_q.release(); ctx->ws_layers_open.release(); ctx->ws_fri_words.release(); ctx->ws_fri_trees.release();
     ctx->ws_qidx.release(); ctx->ws_qout.release();
-    ctx->ws_shard_send.release(); ctx->ws_shard_recv.release(); ctx->ws_shard_coef.release(); ctx->ws_gather.release(); ctx->ws_gather2.release();
+    ctx->ws_qraw.release(); ctx->ws_shard_send.release(); ctx->ws_shard_recv.release(); ctx->ws_shard_coef.release(); ctx->ws_gather.release(); ctx->ws_gather2.release();
     ctx->ws_qnat.release(); ctx->ws_qlde.release(); ctx->ws_f0.release(); ctx->ws_f1.release(); ctx->ws_state.release();
     if (ctx->copy_stream) cudaStreamDestroy(ctx->copy_stream);
     for (int i = 0; i < 2; i++) { if (ctx->ev_copy[i]) cudaEventDestroy(ctx->ev_copy[i]); if (ctx->ev_free[i]) cudaEventDestroy(ctx->ev_free[i]); }
@@ -611,9 +612,9 @@ int pb_air_jit_compile_only(const uint32_t* bc, size_t n_words, const pb_expr_sp
     std::vector<air::Span> spans;
     int rc = pack_program(bc, n_words, cons, n_constraints, width, code, pool, spans);
     if (rc) return rc;
-    std::vector<char> cubin;
-    rc = airjit::build(code, spans, pool, nullptr, &cubin);
-    if (cubin_bytes) *cubin_bytes = cubin.size();
+    size_t total = 0;
+    rc = airjit::build(code, spans, pool, nullptr, &total);
+    if (cubin_bytes) *cubin_bytes = total;
     return rc ? PB_ERR_UNSUPPORTED : 0;
 }
 
@@ -676,7 +677,8 @@ int pb_quotient(pb_ctx_t* ctx, const pb_air_t* a, const uint32_t* d_lde, size_t 
     const uint32_t zinv0 = bb::inv(bb::sub(sn, bb::R1)), zinv1 = bb::inv(bb::sub(bb::neg(sn), bb::R1));
     const size_t m = (size_t)2 << log_n;
     if (a->jit_ok) {
-        rc = airjit::launch(a->jit, ctx->stream, d_lde, m, (int)log_n, a->d_alpha_pows, zinv0, zinv1, d_q, 1);
+        if (a->jit.fns.size() > 1) { rc = ctx->ws_qraw.ensure(4 * m); if (rc) return rc; }
+        rc = airjit::launch(a->jit, ctx->stream, d_lde, m, (int)log_n, a->d_alpha_pows, zinv0, zinv1, d_q, 1, ctx->ws_qraw.p);
         LAUNCHED(ctx);
         return rc;
     }
@@ -693,7 +695,8 @@ int pb_constraint_fold(pb_ctx_t* ctx, const pb_air_t* a, const uint32_t* d_mat, 
     int rc = upload_alpha_pows(ctx, a, h_e4_from_canon(alpha));
     if (rc) return rc;
     if (a->jit_ok) {
-        rc = airjit::launch(a->jit, ctx->stream, d_mat, height, 0, a->d_alpha_pows, 0u, 0u, d_out, 0);
+        if (a->jit.fns.size() > 1) { rc = ctx->ws_qraw.ensure(4 * height); if (rc) return rc; }
+        rc = airjit::launch(a->jit, ctx->stream, d_mat, height, 0, a->d_alpha_pows, 0u, 0u, d_out, 0, ctx->ws_qraw.p);
         LAUNCHED(ctx);
         return rc;
     }

@@ -4,6 +4,9 @@ reference-derived fixtures and the oracle for the generated vectors):  python te
 
   single_div_nondet.machine.json   machine section of /root/reference/autoprecompiles/tests/single_div_nondet.json.gz
   wasm_register_reuse.machine.json machine section of .../wasm_register_reuse.json.gz
+  apc_reth_op_bug.machine.json.gz  machine section of .../apc_reth_op_bug.json.gz: a real PRE-optimisation APC (5869 columns,
+                                   9168 constraints, 3117 bus interactions) -- the large-AIR case for the compiler, the
+                                   interpreter and the chunked JIT
   apc_snapshots.json               the 62 optimized machines of /root/reference/openvm-riscv/tests/apc_snapshots/**
                                    re-serialised in the reference JSON expression schema (constraints + bus interactions)
   fixture_stats.json               sizes/degree histograms of the big reference fixtures (keccak/sha256/ecrecover ...)
@@ -41,6 +44,9 @@ def main():
         for name in ("single_div_nondet", "wasm_register_reuse"):
             doc = json.load(gzip.open(os.path.join(REF, "autoprecompiles/tests/%s.json.gz" % name), "rt"))
             dump(name + ".machine.json", {"machine": doc["machine"], "bus_map": doc.get("bus_map")})
+        doc = json.load(gzip.open(os.path.join(REF, "autoprecompiles/tests/apc_reth_op_bug.json.gz"), "rt"))
+        with gzip.GzipFile(os.path.join(HERE, "apc_reth_op_bug.machine.json.gz"), "wb", mtime=0) as f:      # 5869 columns, 9168 constraints
+            f.write(json.dumps({"machine": doc["machine"], "bus_map": doc.get("bus_map")}, separators=(",", ":")).encode())
         snaps = {}
         for p in sorted(glob.glob(os.path.join(REF, "openvm-riscv/tests/apc_snapshots/*/*.txt"))):
             mach = M.SymbolicMachine.from_snapshot_text(open(p).read())

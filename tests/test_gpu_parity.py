@@ -408,3 +408,28 @@ def test_gpu_proof_of_a_satisfying_trace_verifies_with_the_constraint_identity(c
     queries, ys = ctx.query_segment(log_n, 3, 30)
     assert orc.verify_segment(bc, spans, log_n, 3, proof, ys, queries, check_constraints=False) == 0
     assert orc.verify_segment(bc, spans, log_n, 3, proof, ys, queries, check_constraints=True) == 12
+
+
+def test_large_preopt_fixture_jit_chunks_and_interpreter_agree_with_oracle(ctx, orc, monkeypatch):
+    """apc_reth_op_bug (5869 columns, 9168 constraints): the JIT splits it into ~70 modules whose kernels pass the running fold
+    through a scratch buffer; the interpreter is the other CUDA path.  Both must equal the oracle on random rows."""
+    path = os.path.join(GOLDEN, "apc_reth_op_bug.machine.json.gz")
+    mach = _machine().SymbolicMachine.from_json_file(path)
+    bc, spans = _machine().compile_constraints(mach)
+    rng = np.random.default_rng(31)
+    h = 200
+    mat = rand_field(rng, (mach.width, h))
+    alpha = rand_field(rng, 4)
+    exp = orc.constraint_fold(bc, spans, mat, alpha)
+    d = ctx.to_device(mat)
+    d_out = ctx.alloc(16 * h)
+    air = ctx.air(bc, spans, mach.width)
+    assert air.is_jit
+    ctx.constraint_fold(air, d.ptr, h, alpha, d_out.ptr)
+    assert (ctx.to_host(d_out, (4, h)) == exp).all()
+    monkeypatch.setenv("PB_AIR_NO_JIT", "1")
+    interp = ctx.air(bc, spans, mach.width)
+    assert not interp.is_jit
+    d_out.zero()
+    ctx.constraint_fold(interp, d.ptr, h, alpha, d_out.ptr)
+    assert (ctx.to_host(d_out, (4, h)) == exp).all()

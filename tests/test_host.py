@@ -161,3 +161,25 @@ def test_product_never_imports_the_oracle():
             if f.endswith((".py", ".cu", ".cuh", ".inl", ".h")):
                 txt = open(os.path.join(dirpath, f), errors="replace").read()
                 assert "import oracle" not in txt and "from oracle" not in txt and "oracle/" not in txt.replace("the oracle/", ""), f
+
+
+def test_chunked_jit_compiles_a_9168_constraint_machine_in_parallel():
+    """the real pre-optimisation fixture is 141 k bytecode words: as one NVRTC module that took 11 minutes, as 2 k-word chunks on
+    all host threads it must stay a key-generation-time cost (seconds to tens of seconds)"""
+    import ctypes as C
+    import time
+    import powdr_b200
+    from powdr_b200 import machine as M
+    from powdr_b200.capi import Span
+    mach = M.SymbolicMachine.from_json_file(os.path.join(GOLDEN, "apc_reth_op_bug.machine.json.gz"))
+    bc, spans = M.compile_constraints(mach)
+    bc = np.ascontiguousarray(bc, dtype=np.uint32)
+    sp = (Span * len(spans))()
+    for i, (o, l) in enumerate(spans):
+        sp[i].off, sp[i].len = o, l
+    lib = powdr_b200.load_library()
+    n = C.c_size_t()
+    t0 = time.time()
+    rc = lib.pb_air_jit_compile_only(bc.ctypes.data_as(C.c_void_p), C.c_size_t(bc.size), sp, C.c_size_t(len(spans)), C.c_uint32(mach.width), C.byref(n))
+    assert rc == 0 and n.value > 1 << 20
+    assert time.time() - t0 < 300

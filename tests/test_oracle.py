@@ -324,3 +324,34 @@ def test_verifier_constraint_identity_on_satisfying_and_unsatisfying_traces(orc)
     proof, ys, q = orc.prove_segment_q(trace, bc, spans, 5)
     assert orc.verify_segment(bc, spans, 7, 3, proof, ys, q, check_constraints=False) == 0    # the PCS part is still sound
     assert orc.verify_segment(bc, spans, 7, 3, proof, ys, q, check_constraints=True) == 12
+
+
+def test_large_preopt_fixture_against_python_evaluator(orc):
+    """apc_reth_op_bug: a real pre-optimisation APC (5869 columns, 9168 constraints, degree <= 3).  Sizes as recorded from the
+    reference fixture; 300 sampled constraints evaluated directly on the expression trees must equal the bytecode path."""
+    from powdr_b200 import machine as M
+    mach = M.SymbolicMachine.from_json_file(os.path.join(GOLDEN, "apc_reth_op_bug.machine.json.gz"))
+    st = load("fixture_stats.json")["apc_reth_op_bug"]
+    assert (mach.width, len(mach.constraints), len(mach.bus_interactions)) == (st["columns"], st["constraints"], st["bus_interactions"]) == (5869, 9168, 3117)
+    hist = [0, 0, 0, 0]
+    for c in mach.constraints:
+        hist[M.degree(c)] += 1
+    assert hist == st["degree_hist"]
+    bc, spans = M.compile_constraints(mach)
+    rng = np.random.default_rng(43)
+    mat = rand_field(rng, (mach.width, 2))
+
+    def ev(e, r):
+        if isinstance(e, int):
+            return e % P
+        if isinstance(e, str):
+            return int(mat[mach.col_of(e), r])
+        if len(e) == 2:
+            return (-ev(e[1], r)) % P
+        a, b = ev(e[0], r), ev(e[2], r)
+        return (a + b) % P if e[1] == "+" else (a - b) % P if e[1] == "-" else (a * b) % P
+
+    for k in rng.choice(len(mach.constraints), size=300, replace=False):
+        o, l = spans[k]
+        got = orc.constraint_fold(bc[o:o + l], [(0, l)], mat, [1, 0, 0, 0])[0]
+        assert got.tolist() == [ev(mach.constraints[k], r) for r in range(2)], k
