@@ -329,6 +329,22 @@ def test_host_pipeline_with_many_chunks_matches_device_path(ctx, orc, monkeypatc
     assert ctx.prove_segment(air, host.ctypes.data, log_n, mach.width, on_device=False) == exp
 
 
+def test_host_pipeline_ramped_schedule_with_ragged_tail(ctx, orc, monkeypatch):
+    """wide traces use the ramp-up / ramp-down chunk schedule (8, 16, 32, cw..., 32, 16, 8 + width % 8): 150 columns with
+    8-column chunks = 3 + 4 + 3 chunks, the last one 14 columns wide"""
+    mach = _machine().synthetic_machine(150, 12, seed=13)
+    air, bc, spans = _compile(ctx, mach)
+    rng = np.random.default_rng(67)
+    log_n = 8
+    trace = rand_field(rng, (mach.width, 1 << log_n))
+    exp, _ = orc.prove_segment(trace, bc, spans)
+    from powdr_b200.capi import R_MOD_P
+    host = ((trace.astype(np.uint64) * np.uint64(R_MOD_P)) % np.uint64(P)).astype(np.uint32)
+    monkeypatch.setenv("PB_PIPE_CHUNK_COLS", "8")
+    assert mach.width >= 4 * 8 + 112 and mach.width % 8 != 0
+    assert ctx.prove_segment(air, host.ctypes.data, log_n, mach.width, on_device=False) == exp
+
+
 # ---------------------------------------------------------------- openings + reduced opening (SURVEY §8f-4)
 @pytest.mark.parametrize("log_n,width,shift", [(3, 2, 1), (9, 13, 31), (12, 21, 1234567), (16, 9, 1)])
 def test_eval_at_point_matches_oracle(ctx, orc, log_n, width, shift):
