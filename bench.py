@@ -77,7 +77,12 @@ class ClockSampler:
 
     def _read(self):
         for line in self.proc.stdout:
-            self.rows.append([x.strip() for x in line.split(",")])
+            self.rows.append((time.time(), [x.strip() for x in line.split(",")]))
+
+    def mark(self):
+        """start of the timed region (the sampler is started before the warm-up steps: nvidia-smi needs ~0.5 s to deliver its
+        first sample, longer than a short timed region)"""
+        self.t_mark = time.time()
 
     def stop(self):
         if not self.proc:
@@ -87,8 +92,13 @@ class ClockSampler:
             self.proc.wait(timeout=2)
         except Exception:
             pass
+        t_mark = getattr(self, "t_mark", 0.0)
+        timed = [r for t, r in self.rows if t >= t_mark]
+        window = "timed region"
+        if not timed:                                   # region shorter than the sampling latency: the warm-up steps ran the same load
+            timed, window = [r for _, r in self.rows], "warm-up + timed region"
         sm, mx, reasons = [], None, set()
-        for r in self.rows:
+        for r in timed:
             try:
                 sm.append(float(r[0]))
                 mx = float(r[1])
@@ -98,7 +108,7 @@ class ClockSampler:
             except Exception:
                 pass
         sm.sort()
-        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": mx, "reasons": sorted(reasons), "samples": len(sm)}
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": mx, "reasons": sorted(reasons), "samples": len(sm), "window": window}
 
 
 def cpu_baseline(a, mach, bc, spans):
@@ -180,16 +190,17 @@ def run_native(a):
             dist.barrier()
             torch.cuda.synchronize()
 
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
     for _ in range(a.warmup):
         step_device()
     sync_all()
     ctx.leaf_kernel_profile()                                  # reset
     launches0 = ctx.launch_count()
-    sampler = ClockSampler(local)
-    if rank == 0:
-        sampler.start()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     sync_all()
+    sampler.mark()
     e0.record(stream)
     for _ in range(a.steps):
         proof = step_device()
@@ -268,7 +279,7 @@ def run_native(a):
                                                         "peak": peak_i / 1e12, "unit": "T mulmod/s",
                                                         "frac": (perms * 657.6 / (leaf_ms / 1e3)) / peak_i if leaf_ms > 0 else 0.0})(
                 (leaf_bytes / (4.0 * ww + 32.0)) * math.ceil(ww / 8.0) if n_leaf else 0.0,
-                12.6 * 148 * (clocks or {}).get("sm_mhz", 1965.0) * 1e6),
+                12.6 * 148 * ((clocks or {}).get("sm_mhz") or 1965.0) * 1e6),
             "stages_ms": stage_ms,
             "stage_roofline_frac": {k: (alg[k] / 1e9) / (stage_ms[k] / 1e3) / peak for k in alg if stage_ms.get(k, 0) > 0},
             "segments_per_s": world / (ms_per_step / 1e3),
