@@ -237,8 +237,8 @@ def run_native(a):
         te = torch.tensor([max(ems / 1e3 / a.steps, wall)], dtype=torch.float64, device=dev)
         if world > 1:
             dist.all_reduce(te, op=dist.ReduceOp.MAX)
-        assert p2 == proof or world > 1 or True
         e2e = {"value": float(te.item()) / world, "unit": "s", "h2d_bytes_per_step": 4 * w * n * world,
+               "proof_equals_device_path": p2 == proof,           # same trace through the host-input pipeline: same proof
                "d2h_bytes_per_step": (16 + 4 + 12 * proof["n_fri_layers"] + 4 * proof["final_len"]) * 4 * world,
                "stages_ms": ctx.last_stage_ms()}
 
