@@ -449,3 +449,34 @@ def test_large_preopt_fixture_jit_chunks_and_interpreter_agree_with_oracle(ctx, 
     d_out.zero()
     ctx.constraint_fold(interp, d.ptr, h, alpha, d_out.ptr)
     assert (ctx.to_host(d_out, (4, h)) == exp).all()
+
+
+def test_plain_c_client_produces_the_same_commitments(ctx, orc, tmp_path):
+    """examples/abi_demo.c (gcc, no Python in the loop) proves a satisfying 3-column trace from host memory; the Python binding
+    and the oracle must produce the same roots, and the FRI final polynomial is a constant"""
+    import subprocess
+    from test_host import _build_abi_demo
+    log_n = 10
+    r = subprocess.run([_build_abi_demo(tmp_path), str(log_n)], capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0, r.stderr
+    out = {ln.split()[0]: ln.split()[1:] for ln in r.stdout.strip().splitlines()}
+    n = 1 << log_n
+    s, mask = 88172645463325252, (1 << 64) - 1
+    trace = np.zeros((3, n), dtype=np.uint32)
+    for row in range(n):
+        s ^= (s << 13) & mask
+        s ^= s >> 7
+        s ^= (s << 17) & mask
+        a, b = s % 3, (s >> 8) % P
+        trace[:, row] = [a, b, a * b % P]
+    A, B, Cc = "a@0", "b@1", "c@2"
+    from powdr_b200 import machine as M
+    mach = M.SymbolicMachine([[[A, "*", B], "-", Cc], [[A, "*", [A, "-", 1]], "*", [A, "-", 2]]], [], [])
+    assert mach.width == 3
+    bc, spans = M.compile_constraints(mach)
+    exp, _ = orc.prove_segment(trace, bc, spans)
+    assert [int(x) for x in out["trace_root"]] == exp["trace_root"]
+    assert [int(x) for x in out["quotient_root"]] == exp["quotient_root"]
+    fin = [int(x) for x in out["fri_layers"][4:]]
+    assert int(out["fri_layers"][0]) == exp["n_fri_layers"] and fin == [v for row in exp["final_poly"][:exp["final_len"]] for v in row]
+    assert fin[:4] == fin[4:8]                    # constant final polynomial: the quotient of a satisfying trace is low degree

@@ -183,3 +183,24 @@ def test_chunked_jit_compiles_a_9168_constraint_machine_in_parallel():
     rc = lib.pb_air_jit_compile_only(bc.ctypes.data_as(C.c_void_p), C.c_size_t(bc.size), sp, C.c_size_t(len(spans)), C.c_uint32(mach.width), C.byref(n))
     assert rc == 0 and n.value > 1 << 20
     assert time.time() - t0 < 300
+
+
+def _build_abi_demo(tmp_path):
+    import subprocess
+    exe = str(tmp_path / "abi_demo")
+    lib_dir = os.path.join(ROOT, "powdr_b200", "_lib")
+    subprocess.check_call(["/usr/bin/gcc", "-std=c99", "-O2", "-Wall", "-Wextra", "-Werror", "-pedantic", "-I", os.path.join(ROOT, "include"),
+                           os.path.join(ROOT, "examples", "abi_demo.c"), "-L", lib_dir, "-lpowdr_b200", "-Wl,-rpath," + lib_dir, "-o", exe])
+    return exe
+
+
+def test_plain_c_client_links_and_fails_loudly_without_a_gpu(tmp_path):
+    """examples/abi_demo.c uses nothing but the header and the .so; without a device pb_ctx_create must return PB_ERR_NO_DEVICE"""
+    import subprocess
+    import powdr_b200
+    powdr_b200.load_library()
+    r = subprocess.run([_build_abi_demo(tmp_path), "6"], capture_output=True, text=True, timeout=120)
+    if r.returncode != 0:
+        assert "pb_ctx_create" in r.stderr and "-> -5" in r.stderr, r.stderr
+    else:                                   # a GPU is present where this CPU suite runs: the demo must then succeed
+        assert "trace_root" in r.stdout
