@@ -81,3 +81,104 @@ def test_two_ranks_gather_caps_gloo():
             w, lh = shapes[i]
             mat = np.random.default_rng(1000 + i).integers(0, orc.P, size=(w, 1 << lh), dtype=np.uint32)
             assert (a0[r, slot].astype(np.uint32) == orc.merkle_commit([mat])[-1][0]).all()
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# One segment on several ranks (pb_prove_segment_sharded, csrc/shard_api.inl), restated with the oracle's arithmetic and REAL
+# torch.distributed collectives (gloo): column-sharded trace -> fold per destination block -> all-to-all -> sub-coset
+# evaluation of my row block -> subtree root -> all-gather of roots -> top of the tree.  The GPU library is exercised by
+# tests/test_gpu_sharded.py; this is the CPU check of the decomposition and of the data flow between ranks.
+def _bitrev(x, bits):
+    r = 0
+    for i in range(bits):
+        r = (r << 1) | ((x >> i) & 1)
+    return r
+
+
+def _sharded_worker(rank, world, port, ret):
+    sys.path.insert(0, ROOT)
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    import torch
+    import torch.distributed as dist
+    from oracle import orc
+    from powdr_b200.sharded import shard_columns
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    P = orc.P
+    log_n, width = 6, 5
+    n = 1 << log_n
+    g = world.bit_length() - 1
+    g1, G1 = g - 1, world // 2
+    n_blk = n // G1                       # rows per block = 2n / world
+    log_blk = log_n - g1
+    trace = np.random.default_rng(77).integers(0, P, size=(width, n), dtype=np.uint32)      # same on every rank
+    first, count = shard_columns(width, world, rank)
+    per = -(-width // world)
+
+    def root_of_unity(bits):              # taken from the oracle itself: evaluations of the polynomial x over the subgroup
+        e = np.zeros(1 << bits, dtype=np.uint32)
+        e[1] = 1
+        return int(orc.dft_naive(e, 1)[1]) if bits else 1
+
+    w_n, w_2n = root_of_unity(log_n), root_of_unity(log_n + 1)
+
+    def block_shift(blk):
+        c, h = blk >> g1, blk & (G1 - 1)
+        return orc.GENERATOR * pow(w_2n, c, P) * pow(w_n, _bitrev(h, g1), P) % P
+
+    # 1. inverse transform of MY columns, fold for every destination block
+    send = np.zeros((world, per, n_blk), dtype=np.int64)
+    for i in range(count):
+        a = orc.intt(trace[first + i]).astype(object)          # natural-order coefficients
+        for blk in range(world):
+            lam = pow(block_shift(blk), n_blk, P)
+            b = [sum(int(a[r + q * n_blk]) * pow(lam, q, P) for q in range(G1)) % P for r in range(n_blk)]
+            send[blk, i] = b
+    # 2. all-to-all (gloo has no all_to_all: gather every rank's send buffer and keep the slices addressed to me)
+    gathered = [torch.zeros((world, per, n_blk), dtype=torch.int64) for _ in range(world)]
+    dist.all_gather(gathered, torch.from_numpy(send))
+    recv = np.stack([gathered[src][rank].numpy() for src in range(world)]).reshape(world * per, n_blk)[:width]
+    # 3. evaluate every column on my sub-coset, rows in bit-reversed order
+    sp = block_shift(rank)
+    block = np.zeros((width, n_blk), dtype=np.uint32)
+    for c in range(width):
+        ev = orc.dft_naive(recv[c].astype(np.uint32), sp)
+        for m in range(n_blk):
+            block[c, _bitrev(m, log_blk)] = ev[m]
+    # 4. subtree root, all-gather, top of the tree
+    my_root = orc.merkle_commit([block])[-1][0]
+    roots = [torch.zeros(8, dtype=torch.int64) for _ in range(world)]
+    dist.all_gather(roots, torch.from_numpy(my_root.astype(np.int64)))
+    nodes = [r.numpy().astype(np.uint32) for r in roots]
+    while len(nodes) > 1:
+        nodes = [orc.compress(nodes[2 * i], nodes[2 * i + 1]) for i in range(len(nodes) // 2)]
+    ret[rank] = (block, nodes[0])
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("world", [2, 4])
+def test_sharded_commit_data_flow_gloo(world):
+    import torch.multiprocessing as mp
+    sys.path.insert(0, ROOT)
+    from oracle import orc
+    orc.build()
+    port = _free_port()
+    mgr = mp.Manager()
+    ret = mgr.dict()
+    ctx = mp.get_context("spawn")
+    procs = [ctx.Process(target=_sharded_worker, args=(r, world, port, ret)) for r in range(world)]
+    for p in procs:
+        p.start()
+    for p in procs:
+        p.join(timeout=180)
+        assert p.exitcode == 0
+    trace = np.random.default_rng(77).integers(0, orc.P, size=(5, 64), dtype=np.uint32)
+    lde = orc.lde_batch(trace, 1, orc.GENERATOR)
+    ms = lde.shape[1] // world
+    root = orc.merkle_commit([lde])[-1][0]
+    for r in range(world):
+        block, top = ret[r]
+        assert (block == lde[:, r * ms:(r + 1) * ms]).all(), "rank %d: row block is not the sub-coset evaluation" % r
+        assert (top == root).all(), "rank %d: combined root differs from the single-process commitment" % r
