@@ -355,3 +355,38 @@ def test_large_preopt_fixture_against_python_evaluator(orc):
         o, l = spans[k]
         got = orc.constraint_fold(bc[o:o + l], [(0, l)], mat, [1, 0, 0, 0])[0]
         assert got.tolist() == [ev(mach.constraints[k], r) for r in range(2)], k
+
+
+def test_c_oracle_matches_an_independent_python_poseidon2(orc):
+    """two restatements that share only the constants file: oracle/poseidon2.c and tests/py_poseidon2.py (pure Python integers)"""
+    import py_poseidon2 as pp
+    rng = np.random.default_rng(71)
+    for _ in range(5):
+        st = rand_field(rng, 16)
+        assert orc.poseidon2_permute(st).tolist() == pp.permute(st)
+    assert orc.poseidon2_permute(np.zeros(16, dtype=np.uint32)).tolist() == pp.permute([0] * 16)
+    for width in (1, 7, 8, 9, 16, 23):
+        row = rand_field(rng, width)
+        assert orc.hash_row(row).tolist() == pp.hash_row(row), width
+    l, r = rand_field(rng, 8), rand_field(rng, 8)
+    assert orc.compress(l, r).tolist() == pp.compress(l, r)
+    mat = rand_field(rng, (5, 8))                       # 8 rows of 5 columns
+    assert orc.merkle_commit([mat])[-1][0].tolist() == pp.merkle_root(mat.T.tolist())
+
+
+def test_c_oracle_challenger_and_dft_match_independent_python(orc):
+    import py_poseidon2 as pp
+    rng = np.random.default_rng(73)
+    a, b = orc.Challenger(), pp.DuplexChallenger()
+    for n_obs, n_samp in [(8, 4), (3, 1), (0, 9), (11, 2), (16, 8), (1, 1)]:
+        v = rand_field(rng, n_obs)
+        a.observe(v)
+        b.observe(v.tolist())
+        assert [a.sample() for _ in range(n_samp)] == [b.sample() for _ in range(n_samp)]
+    # the O(n^2) DFT the NTT tests lean on, against Python integers; the 8th root of unity is 31^((p-1)/8)
+    co = rand_field(rng, 8)
+    w = int(orc.dft_naive(np.array([0, 1, 0, 0, 0, 0, 0, 0], dtype=np.uint32), 1)[1])
+    assert pow(w, 8, P) == 1 and pow(w, 4, P) == P - 1
+    for shift in (1, 31):
+        exp = [sum(int(c) * pow(shift * pow(w, i, P) % P, k, P) for k, c in enumerate(co)) % P for i in range(8)]
+        assert orc.dft_naive(co, shift).tolist() == exp
