@@ -204,3 +204,22 @@ def test_plain_c_client_links_and_fails_loudly_without_a_gpu(tmp_path):
         assert "pb_ctx_create" in r.stderr and "-> -5" in r.stderr, r.stderr
     else:                                   # a GPU is present where this CPU suite runs: the demo must then succeed
         assert "trace_root" in r.stdout
+
+
+def test_bench_reference_arm_prints_one_contract_line():
+    """`bench.py --impl reference` (the CPU restatement timed on the host cores) needs no GPU and must print exactly one JSON line
+    with the contract's keys"""
+    import json
+    import subprocess
+    import sys
+    r = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--steps", "1", "--warmup", "1", "--log-n", "12",
+                        "--width", "24", "--constraints", "5", "--cpu-sample-log-n", "8"], capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0, r.stderr[-2000:]
+    lines = [ln for ln in r.stdout.splitlines() if ln.strip()]
+    assert len(lines) == 1
+    d = json.loads(lines[0])
+    for k in ("impl", "metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per_step", "higher_is_better", "scaling", "vs_baseline", "dtype",
+              "data", "config", "cpu_baseline", "e2e"):
+        assert k in d, k
+    assert d["impl"] == "reference" and d["higher_is_better"] is False and d["value"] > 0
+    assert d["cpu_baseline"]["kind"] == "port" and d["e2e"]["h2d_bytes_per_step"] == 0 and d["e2e"]["value"] == d["value"]
