@@ -223,3 +223,29 @@ def test_bench_reference_arm_prints_one_contract_line():
         assert k in d, k
     assert d["impl"] == "reference" and d["higher_is_better"] is False and d["value"] > 0
     assert d["cpu_baseline"]["kind"] == "port" and d["e2e"]["h2d_bytes_per_step"] == 0 and d["e2e"]["value"] == d["value"]
+
+
+def test_entry_points_reject_null_arguments_before_touching_the_device():
+    """error behaviour of the boundary (cuda_abi.rs convention: an int comes back, nothing aborts): every compute entry point
+    returns PB_ERR_INVALID_ARG for null handles / pointers -- checked here without a GPU"""
+    import ctypes as C
+    import powdr_b200
+    lib = powdr_b200.load_library()
+    z, n0 = C.c_void_p(0), C.c_size_t(0)
+    four = (C.c_uint32 * 4)(1, 2, 3, 4)
+    INVALID = -1
+    assert lib.pb_lde_batch(z, z, C.c_size_t(4), C.c_size_t(1), C.c_uint32(1), C.c_uint32(31), z) == INVALID
+    assert lib.pb_quotient(z, z, z, C.c_size_t(4), C.c_uint32(1), C.c_uint32(31), four, z) == INVALID
+    assert lib.pb_constraint_fold(z, z, z, C.c_size_t(4), four, z) == INVALID
+    assert lib.pb_merkle_commit(z, z, z, n0, C.c_size_t(3), z, z) == INVALID
+    assert lib.pb_merkle_commit_rows8(z, z, C.c_size_t(3), z, z) == INVALID
+    assert lib.pb_fri_fold(z, z, C.c_size_t(4), C.c_uint32(31), four, z) == INVALID
+    assert lib.pb_eval_at_point(z, z, C.c_size_t(4), C.c_size_t(1), C.c_uint32(1), four, z) == INVALID
+    assert lib.pb_deep_quotient(z, z, z, n0, C.c_size_t(4), C.c_uint32(31), four, four, z, z) == INVALID
+    assert lib.pb_prove_segment(z, z, z, C.c_size_t(4), C.c_size_t(1), C.c_uint32(0), z) == INVALID
+    assert lib.pb_prove_segment_sharded(z, z, z, C.c_size_t(4), C.c_size_t(1), C.c_uint32(0), z, z) == INVALID
+    assert lib.pb_lde_shard(z, z, C.c_size_t(6), C.c_size_t(1), C.c_uint32(31), C.c_int(2), C.c_int(0), z) == INVALID
+    assert lib.pb_poseidon2_permute(z, z, n0, C.c_int(1)) == INVALID
+    first, count = C.c_size_t(), C.c_size_t()
+    assert lib.pb_shard_columns(C.c_size_t(10), C.c_int(4), C.c_int(4), C.byref(first), C.byref(count)) == INVALID      # rank out of range
+    assert lib.pb_query_words(C.c_size_t(10), C.c_size_t(3), z) == INVALID
