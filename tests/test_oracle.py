@@ -390,3 +390,42 @@ def test_c_oracle_challenger_and_dft_match_independent_python(orc):
     for shift in (1, 31):
         exp = [sum(int(c) * pow(shift * pow(w, i, P) % P, k, P) for k, c in enumerate(co)) % P for i in range(8)]
         assert orc.dft_naive(co, shift).tolist() == exp
+
+
+def test_size_independent_properties_of_the_oracle(orc):
+    """linearity of the LDE and of the FRI fold, and sensitivity of the Merkle root -- the properties the GPU tests rely on at sizes
+    the oracle cannot reach quickly"""
+    from hypothesis import given, settings, strategies as st
+
+    @settings(max_examples=12, deadline=None)
+    @given(st.integers(1, 7), st.integers(0, 2**32 - 1), st.integers(0, P - 1), st.integers(1, P - 1))
+    def lde_is_linear(log_n, seed, k, shift):
+        rng = np.random.default_rng(seed)
+        a, b = rand_field(rng, (1, 1 << log_n)), rand_field(rng, (1, 1 << log_n))
+        comb = ((a.astype(np.uint64) * np.uint64(k) + b) % np.uint64(P)).astype(np.uint32)
+        la, lb, lc = (orc.lde_batch(x, 1, shift)[0].astype(np.uint64) for x in (a, b, comb))
+        assert (lc == (la * np.uint64(k) + lb) % np.uint64(P)).all()
+
+    @settings(max_examples=12, deadline=None)
+    @given(st.integers(2, 8), st.integers(0, 2**32 - 1))
+    def fold_is_affine_in_beta(log_len, seed):
+        rng = np.random.default_rng(seed)
+        f = rand_field(rng, (1 << log_len, 4))
+        b0 = orc.fri_fold(f, 31, [0, 0, 0, 0]).astype(np.int64)
+        b1 = orc.fri_fold(f, 31, [1, 0, 0, 0]).astype(np.int64)
+        b5 = orc.fri_fold(f, 31, [5, 0, 0, 0]).astype(np.int64)
+        assert ((b0 + 5 * (b1 - b0)) % P == b5).all()
+
+    @settings(max_examples=8, deadline=None)
+    @given(st.integers(1, 5), st.integers(1, 20), st.integers(0, 2**32 - 1))
+    def merkle_root_binds_every_element(log_h, width, seed):
+        rng = np.random.default_rng(seed)
+        m = rand_field(rng, (width, 1 << log_h))
+        root = orc.merkle_commit([m])[-1][0].copy()
+        c, r = int(rng.integers(width)), int(rng.integers(1 << log_h))
+        m[c, r] = (int(m[c, r]) + 1) % P
+        assert (orc.merkle_commit([m])[-1][0] != root).any()
+
+    lde_is_linear()
+    fold_is_affine_in_beta()
+    merkle_root_binds_every_element()
