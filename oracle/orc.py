@@ -16,6 +16,7 @@ GENERATOR = 31
 
 def build(force=False):
     srcs = [os.path.join(_DIR, f) for f in ("ntt.c", "poseidon2.c", "air.c", "prove.c", "verify.c", "oracle.h", "bb31.h")]
+    srcs.append(os.path.join(os.path.dirname(_DIR), "include", "pb_poseidon2_constants.h"))
     if force or not os.path.exists(_SO) or any(os.path.getmtime(s) > os.path.getmtime(_SO) for s in srcs):
         subprocess.check_call(["make", "-C", _DIR, "-s"])
     return _SO

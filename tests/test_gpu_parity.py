@@ -85,6 +85,17 @@ def test_poseidon2_permutation(ctx, orc):
     assert (got == exp).all()
 
 
+def test_poseidon2_plonky3_kat(ctx):
+    """CUDA permutation against Plonky3's unit-test vector of default_babybear_poseidon2_16 (input 0..15); provenance of the
+    expected words in tests/test_oracle.py::test_poseidon2_plonky3_default_known_answer"""
+    exp = [1906786279, 1737026427, 1959749225, 700325316, 1638050605, 1021608788, 1726691001, 1761127344, 1552405120, 417318995,
+           36799261, 1215172152, 614923223, 1300746575, 957311597, 304856115]
+    st = np.arange(16, dtype=np.uint32).reshape(1, 16)
+    d = ctx.to_device(st)
+    ctx.poseidon2_permute(d.ptr, 1, 1)
+    assert ctx.to_host(d, st.shape)[0].tolist() == exp
+
+
 def test_poseidon2_custom_constants_generic_diagonal():
     """pb_ctx_set_poseidon2 with arbitrary constants takes the generic (all-Shoup) internal layer; own context so the
     session-wide constants stay untouched"""
