@@ -162,3 +162,40 @@ void orc_deep_quotient(const uint32_t* const* mats, const size_t* widths, size_t
     }
     free(gp);
 }
+
+/* reduced opening over several (column group, point) pairs:
+   ro[r] = sum_g ( sum_{j in g} gamma^j * (f_j[r] - y_j) ) / (x_r - z_g),  j = the column's global index in `cols` (= its exponent).
+   cols[j]: one column of height 2^log_m (bit-reversed rows over shift*H'); ys: [n_cols][4]; zs: [n_groups][4]; out [m][4]. */
+void orc_deep_quotient_groups(const uint32_t* const* cols, const uint32_t* group_of_col, size_t n_cols, const uint32_t* zs, size_t n_groups,
+                              unsigned log_m, uint32_t shift, const uint32_t gamma[4], const uint32_t* ys, uint32_t* out) {
+    const size_t m = (size_t)1 << log_m;
+    bb4_t g = {{gamma[0], gamma[1], gamma[2], gamma[3]}};
+    bb4_t* gp = (bb4_t*)malloc((n_cols ? n_cols : 1) * sizeof(bb4_t));
+    bb4_t* ysum = (bb4_t*)calloc(n_groups, sizeof(bb4_t));
+    bb4_t cur = bb4_from_base(1);
+    for (size_t j = 0; j < n_cols; j++) {
+        gp[j] = cur;
+        bb4_t y;
+        memcpy(y.c, ys + 4 * j, 16);
+        ysum[group_of_col[j]] = bb4_add(ysum[group_of_col[j]], bb4_mul(cur, y));
+        cur = bb4_mul(cur, g);
+    }
+    const uint32_t w = bb_root_of_unity(log_m);
+#pragma omp parallel for schedule(static)
+    for (long r = 0; r < (long)m; r++) {
+        const uint32_t x = bb_mul(shift, bb_pow(w, bitrev32((uint32_t)r, log_m)));
+        bb4_t total = bb4_from_base(0);
+        for (size_t q = 0; q < n_groups; q++) {
+            bb4_t acc = bb4_from_base(0);
+            for (size_t j = 0; j < n_cols; j++)
+                if (group_of_col[j] == q) acc = bb4_add(acc, bb4_scale(gp[j], cols[j][(size_t)r]));
+            acc = bb4_sub(acc, ysum[q]);
+            bb4_t d = bb4_from_base(x), z;
+            memcpy(z.c, zs + 4 * q, 16);
+            d = bb4_sub(d, z);
+            total = bb4_add(total, bb4_mul(acc, bb4_inv(d)));
+        }
+        memcpy(out + 4 * (size_t)r, total.c, 16);
+    }
+    free(gp); free(ysum);
+}

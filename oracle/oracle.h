@@ -82,33 +82,79 @@ void orc_apc_apply_bus(const uint32_t* out, int num_apc_calls, const uint32_t* b
                        uint32_t tuple2_bus_id, uint32_t* tuple2_hist, uint32_t sz0, uint32_t sz1,
                        uint32_t bitwise_bus_id, uint32_t* bitwise_hist);
 
-/* ---- whole segment (the metric's unit of work): commit trace, quotient, commit quotient, FRI commit phase ---- */
+/* ---- LogUp / bus-interaction argument (logup.c) ---- */
+int orc_logup_chunks(const uint32_t* ibc, const orc_span_t* isp, const orc_interaction_t* ints, size_t n_ints, unsigned max_degree,
+                     uint32_t* chunk_start /* n_ints + 1 entries */);
+void orc_logup_perm_trace(const uint32_t* trace, unsigned log_n, const uint32_t* ibc, const orc_span_t* isp, const orc_interaction_t* ints,
+                          size_t n_ints, const uint32_t* chunk_start, size_t n_chunks, const uint32_t alpha_lu[4], const uint32_t beta_lu[4],
+                          uint32_t* perm /* [4*(n_chunks+1)][N] */, uint32_t cumsum[4]);
+void orc_logup_fold(const uint32_t* lde, const uint32_t* perm_lde, unsigned log_n, uint32_t shift, const uint32_t* ibc, const orc_span_t* isp,
+                    const orc_interaction_t* ints, size_t n_ints, const uint32_t* chunk_start, size_t n_chunks, const uint32_t alpha_lu[4],
+                    const uint32_t beta_lu[4], const uint32_t cumsum[4], const uint32_t alpha[4], uint32_t* acc4 /* [4][2N] in/out */);
+/* reduced opening over several (column group, point) pairs -- see ntt.c */
+void orc_deep_quotient_groups(const uint32_t* const* cols, const uint32_t* group_of_col, size_t n_cols, const uint32_t* zs, size_t n_groups,
+                              unsigned log_m, uint32_t shift, const uint32_t gamma[4], const uint32_t* ys, uint32_t* out);
+
+/* ---- whole segment (the metric's unit of work), transcript v2 ----
+   main commit -> [LogUp challenges, permutation trace commit, cumulative sum] -> alpha -> quotient commit -> zeta ->
+   openings (every opened value observed) -> gamma -> FRI commit phase -> final polynomial observed -> proof-of-work -> queries */
+typedef struct {
+    const uint32_t* bc; const orc_span_t* spans; size_t n_constraints;                              /* polynomial identities */
+    const uint32_t* ibc; const orc_span_t* ispans; const orc_interaction_t* ints; size_t n_ints;   /* bus interactions (may be 0) */
+} orc_air_t;
+typedef struct {
+    uint32_t n_queries, pow_bits;
+    int fast;             /* 1: AVX-512 primitives of fast.c where available */
+    int cheat_opening;    /* test hook: a dishonest prover that claims main_col0(zeta) + 1 -- its reduced opening is not a polynomial */
+} orc_params_t;
 typedef struct {
     uint32_t trace_root[8];
-    uint32_t quotient_root[8];
+    uint32_t logup_alpha[4], logup_beta[4];   /* zero when the AIR has no interactions */
+    uint32_t perm_root[8];
+    uint32_t cumulative_sum[4];
     uint32_t alpha[4];
+    uint32_t quotient_root[8];
     uint32_t zeta[4];              /* out-of-domain opening point */
-    uint32_t openings_root[8];     /* Merkle root (rows of 8, zero padded to a power of two) over the opened values */
     uint32_t gamma[4];             /* batching challenge of the reduced opening */
     uint32_t n_fri_layers;
     uint32_t fri_roots[32][8];
     uint32_t fri_betas[32][4];
-    uint32_t final_poly[8][4];     /* last layer (length 2^(log_blowup + log_final_poly_len) <= 8) */
+    uint32_t final_poly[8][4];     /* last layer (length 2^log_blowup): evaluations of the constant final polynomial */
     uint32_t final_len;
+    uint32_t pow_witness;
+    uint32_t pow_bits, n_queries, perm_width;
 } orc_segment_proof_t;
-void orc_prove_segment(const uint32_t* trace, unsigned log_n, size_t width, const uint32_t* bc, const orc_span_t* spans,
-                       size_t n_constraints, orc_segment_proof_t* proof, double stage_seconds[8]);
+/* opened values ys: [(width + 2*perm_width + 8)][4] = main at zeta | perm at zeta | perm at zeta*w | quotient chunks at zeta.
+   query layout (words): [ r | main row | main path | perm row | perm path (both absent when perm_width = 0) | quotient row (8) |
+   quotient path | per FRI layer: pair (8), path ] */
+size_t orc_num_opened(size_t width, size_t perm_width);
+size_t orc_query_words(unsigned log_n, size_t width, size_t perm_width);
+size_t orc_perm_width(const orc_air_t* air);
+/* stage_seconds[10]: lde, merkle, logup_gen, logup_commit, quotient, quotient_commit, openings, fri_commit, pow, query */
+void orc_prove_segment(const uint32_t* trace, unsigned log_n, size_t width, const orc_air_t* air, const orc_params_t* prm,
+                       orc_segment_proof_t* proof, double stage_seconds[10], uint32_t* ys_out, uint32_t* queries_out);
+/* independent verifier; 0 = accept, else the failed check:
+   1 logup challenges 2 alpha 3 zeta 4 gamma 5 beta 6 proof of work 7 query index 8 main path 9 perm path 10 quotient path
+   11 reduced opening != FRI layer 0 12 FRI path 13 fold consistency 14 final polynomial value 15 final polynomial not constant
+   16 constraint identity at zeta 20 malformed */
+int orc_verify_segment(const orc_air_t* air, unsigned log_n, size_t width, const orc_segment_proof_t* proof, const uint32_t* ys,
+                       const uint32_t* queries, int check_constraints);
+/* proof-of-work grinding on a challenger state: smallest witness w with (observe(w); sample() & (2^bits - 1)) == 0 */
+uint32_t orc_grind(const orc_challenger_t* c, unsigned bits);
 
-/* independent verifier of a segment proof + query openings (layout of pb_query_segment); 0 = accept, else the failed check:
-   1 alpha 2 zeta 3 openings root/gamma 4 beta 5 query index 6 trace path 7 quotient path 8 reduced opening != FRI layer 0
-   9 FRI path 10 fold consistency 11 final polynomial 12 constraint identity at zeta 20 malformed */
-int orc_verify_segment(const uint32_t* bc, const orc_span_t* spans, size_t n_constraints, unsigned log_n, size_t width,
-                       const orc_segment_proof_t* proof, const uint32_t* ys, const uint32_t* queries, size_t n_queries,
-                       int check_constraints);
-
-void orc_prove_segment_q(const uint32_t* trace, unsigned log_n, size_t width, const uint32_t* bc, const orc_span_t* spans,
-                         size_t n_constraints, orc_segment_proof_t* proof, double stage_seconds[8], uint32_t* ys_out,
-                         size_t n_queries, uint32_t* queries_out);
+/* ---- AVX-512 Montgomery implementations of the heavy primitives (fast.c), same semantics ---- */
+int orcf_available(void);
+void orcf_lde_batch(const uint32_t* trace, unsigned log_n, size_t width, unsigned log_blowup, uint32_t shift, uint32_t* lde);
+void orcf_merkle_commit(const uint32_t* const* mats, const size_t* widths, size_t n_mats, unsigned log_h, uint32_t* digest_layers);
+void orcf_constraint_fold(const uint32_t* bc, const orc_span_t* spans, size_t n_constraints, const uint32_t* mat, size_t height,
+                          const uint32_t alpha[4], uint32_t* out4);
+void orcf_quotient(const uint32_t* bc, const orc_span_t* spans, size_t n_constraints, const uint32_t* lde, unsigned log_n,
+                   unsigned log_blowup, uint32_t shift, const uint32_t alpha[4], uint32_t* quotient);
+void orcf_eval_at_point(const uint32_t* mat, unsigned log_n, size_t width, uint32_t shift, const uint32_t zeta[4], uint32_t* out);
+void orcf_deep_quotient(const uint32_t* const* mats, const size_t* widths, size_t n_mats, unsigned log_m, uint32_t shift,
+                        const uint32_t zeta[4], const uint32_t gamma[4], const uint32_t* ys, uint32_t* out);
+void orcf_deep_quotient_groups(const uint32_t* const* cols, const uint32_t* group_of_col, size_t n_cols, const uint32_t* zs, size_t n_groups,
+                               unsigned log_m, uint32_t shift, const uint32_t gamma[4], const uint32_t* ys, uint32_t* out);
 int orc_num_threads(void);
 #ifdef __cplusplus
 }

@@ -15,7 +15,7 @@ GENERATOR = 31
 
 
 def build(force=False):
-    srcs = [os.path.join(_DIR, f) for f in ("ntt.c", "poseidon2.c", "air.c", "prove.c", "verify.c", "oracle.h", "bb31.h")]
+    srcs = [os.path.join(_DIR, f) for f in ("ntt.c", "poseidon2.c", "air.c", "prove.c", "verify.c", "fast.c", "logup.c", "oracle.h", "bb31.h")]
     srcs.append(os.path.join(os.path.dirname(_DIR), "include", "pb_poseidon2_constants.h"))
     if force or not os.path.exists(_SO) or any(os.path.getmtime(s) > os.path.getmtime(_SO) for s in srcs):
         subprocess.check_call(["make", "-C", _DIR, "-s"])
@@ -43,20 +43,74 @@ class Interaction(C.Structure):
 
 
 class SegmentProof(C.Structure):
-    _fields_ = [("trace_root", C.c_uint32 * 8), ("quotient_root", C.c_uint32 * 8), ("alpha", C.c_uint32 * 4),
-                ("zeta", C.c_uint32 * 4), ("openings_root", C.c_uint32 * 8), ("gamma", C.c_uint32 * 4),
+    _fields_ = [("trace_root", C.c_uint32 * 8), ("logup_alpha", C.c_uint32 * 4), ("logup_beta", C.c_uint32 * 4),
+                ("perm_root", C.c_uint32 * 8), ("cumulative_sum", C.c_uint32 * 4), ("alpha", C.c_uint32 * 4),
+                ("quotient_root", C.c_uint32 * 8), ("zeta", C.c_uint32 * 4), ("gamma", C.c_uint32 * 4),
                 ("n_fri_layers", C.c_uint32), ("fri_roots", (C.c_uint32 * 8) * 32), ("fri_betas", (C.c_uint32 * 4) * 32),
-                ("final_poly", (C.c_uint32 * 4) * 8), ("final_len", C.c_uint32)]
+                ("final_poly", (C.c_uint32 * 4) * 8), ("final_len", C.c_uint32), ("pow_witness", C.c_uint32),
+                ("pow_bits", C.c_uint32), ("n_queries", C.c_uint32), ("perm_width", C.c_uint32)]
+    VEC = ("trace_root", "logup_alpha", "logup_beta", "perm_root", "cumulative_sum", "alpha", "quotient_root", "zeta", "gamma")
+    SCALAR = ("n_fri_layers", "final_len", "pow_witness", "pow_bits", "n_queries", "perm_width")
 
     def as_dict(self):
         n = self.n_fri_layers
-        return {
-            "trace_root": list(self.trace_root), "quotient_root": list(self.quotient_root), "alpha": list(self.alpha),
-            "zeta": list(self.zeta), "openings_root": list(self.openings_root), "gamma": list(self.gamma),
-            "n_fri_layers": int(n), "fri_roots": [list(self.fri_roots[i]) for i in range(n)],
-            "fri_betas": [list(self.fri_betas[i]) for i in range(n)],
-            "final_poly": [list(self.final_poly[i]) for i in range(self.final_len)], "final_len": int(self.final_len),
-        }
+        d = {k: list(getattr(self, k)) for k in self.VEC}
+        d.update({k: int(getattr(self, k)) for k in self.SCALAR})
+        d["fri_roots"] = [list(self.fri_roots[i]) for i in range(n)]
+        d["fri_betas"] = [list(self.fri_betas[i]) for i in range(n)]
+        d["final_poly"] = [list(self.final_poly[i]) for i in range(self.final_len)]
+        return d
+
+    @classmethod
+    def from_dict(cls, d):
+        p = cls()
+        for k in cls.VEC:
+            for i, v in enumerate(d[k]):
+                getattr(p, k)[i] = v
+        for k in cls.SCALAR:
+            setattr(p, k, d[k])
+        for i in range(d["n_fri_layers"]):
+            for j in range(8):
+                p.fri_roots[i][j] = d["fri_roots"][i][j]
+            for j in range(4):
+                p.fri_betas[i][j] = d["fri_betas"][i][j]
+        for i in range(d["final_len"]):
+            for j in range(4):
+                p.final_poly[i][j] = d["final_poly"][i][j]
+        return p
+
+
+class AirC(C.Structure):
+    _fields_ = [("bc", C.c_void_p), ("spans", C.c_void_p), ("n_constraints", C.c_size_t),
+                ("ibc", C.c_void_p), ("ispans", C.c_void_p), ("ints", C.c_void_p), ("n_ints", C.c_size_t)]
+
+
+class ParamsC(C.Structure):
+    _fields_ = [("n_queries", C.c_uint32), ("pow_bits", C.c_uint32), ("fast", C.c_int), ("cheat_opening", C.c_int)]
+
+
+class Air:
+    """orc_air_t: constraints (bytecode, spans) + bus interactions `bus` = (interactions [(bus_id, num_args, args_index_off)],
+    arg_spans [(off, len)], bytecode) as returned by powdr_b200.machine.compile_bus(machine, 1) (column-index convention)."""
+
+    def __init__(self, bc, spans, bus=None):
+        self.bc = _u32(bc)
+        self.spans = compile_spans(spans)
+        self.n_constraints = len(spans)
+        ints, isp, ibc = bus if bus else ([], [], [])
+        self.ibc = _u32(ibc if len(ibc) else [0])
+        self.ispans = compile_spans(isp)
+        self.ints = (Interaction * max(1, len(ints)))()
+        for i, (b, n, o) in enumerate(ints):
+            self.ints[i].bus_id, self.ints[i].num_args, self.ints[i].args_index_off = b, n, o
+        self.n_ints = len(ints)
+        self.c = AirC(self.bc.ctypes.data, C.addressof(self.spans), self.n_constraints, self.ibc.ctypes.data, C.addressof(self.ispans),
+                      C.addressof(self.ints), self.n_ints)
+
+    @property
+    def perm_width(self):
+        lib().orc_perm_width.restype = C.c_size_t
+        return int(lib().orc_perm_width(C.byref(self.c)))
 
 
 _lib = None
@@ -277,58 +331,132 @@ def apc_apply_bus(out, num_calls, bc, interactions, arg_spans, var=(3, 1 << 18),
     return var_hist, t_hist, b_hist
 
 
-def prove_segment(trace, bc, spans):
-    t, bc = _u32(trace), _u32(bc)
-    w, n = t.shape
-    proof = SegmentProof()
-    st = (C.c_double * 8)()
-    lib().orc_prove_segment(_p(t), C.c_uint(n.bit_length() - 1), C.c_size_t(w), _p(bc), compile_spans(spans),
-                            C.c_size_t(len(spans)), C.byref(proof), st)
-    return proof.as_dict(), list(st)[:6]
+STAGES = ("lde", "merkle", "logup_gen", "logup_commit", "quotient", "quotient_commit", "openings", "fri_commit", "pow", "query")
 
 
-def proof_struct(d):
-    """dict (as returned by prove_segment here or by powdr_b200.Context.prove_segment) -> SegmentProof ctypes struct"""
-    p = SegmentProof()
-    for k in ("trace_root", "quotient_root", "alpha", "zeta", "openings_root", "gamma"):
-        for i, v in enumerate(d[k]):
-            getattr(p, k)[i] = v
-    p.n_fri_layers = d["n_fri_layers"]
-    p.final_len = d["final_len"]
-    for i in range(d["n_fri_layers"]):
-        for j in range(8):
-            p.fri_roots[i][j] = d["fri_roots"][i][j]
-        for j in range(4):
-            p.fri_betas[i][j] = d["fri_betas"][i][j]
-    for i in range(d["final_len"]):
-        for j in range(4):
-            p.final_poly[i][j] = d["final_poly"][i][j]
-    return p
+def query_words(log_n, width, perm_width=0):
+    lib().orc_query_words.restype = C.c_size_t
+    return int(lib().orc_query_words(C.c_uint(log_n), C.c_size_t(width), C.c_size_t(perm_width)))
 
 
-def verify_segment(bc, spans, log_n, width, proof, ys, queries, check_constraints=False):
-    """0 = accept; see oracle.h for the failure codes"""
-    bc, ys, q = _u32(bc), _u32(ys), _u32(queries)
-    p = proof_struct(proof)
-    lib().orc_verify_segment.restype = C.c_int
-    return lib().orc_verify_segment(_p(bc), compile_spans(spans), C.c_size_t(len(spans)), C.c_uint(log_n), C.c_size_t(width),
-                                    C.byref(p), _p(ys), _p(q), C.c_size_t(q.shape[0]), C.c_int(1 if check_constraints else 0))
-
-
-def query_words(log_n, width):
-    log_m = log_n + 1
-    return 1 + width + 8 * log_m + 8 + 8 * log_m + sum(8 + 8 * (log_m - 1 - i) for i in range(log_n))
-
-
-def prove_segment_q(trace, bc, spans, n_queries):
-    """-> (proof dict, opened values (width+8, 4), query openings (n_queries, words))"""
-    t, bc = _u32(trace), _u32(bc)
+def prove(trace, bc, spans, bus=None, n_queries=8, pow_bits=4, fast=False, cheat_opening=False):
+    """-> (proof dict, opened values (n_open, 4), query openings (n_queries, words), {stage: seconds})"""
+    t = _u32(trace)
     w, n = t.shape
     log_n = n.bit_length() - 1
+    air = bus if isinstance(bus, Air) else Air(bc, spans, bus)
+    wp = air.perm_width
     proof = SegmentProof()
-    st = (C.c_double * 8)()
-    ys = np.empty((w + 8, 4), dtype=np.uint32)
-    q = np.empty((n_queries, query_words(log_n, w)), dtype=np.uint32)
-    lib().orc_prove_segment_q(_p(t), C.c_uint(log_n), C.c_size_t(w), _p(bc), compile_spans(spans), C.c_size_t(len(spans)),
-                              C.byref(proof), st, _p(ys), C.c_size_t(n_queries), _p(q))
-    return proof.as_dict(), ys, q
+    st = (C.c_double * 10)()
+    ys = np.empty((w + 2 * wp + 8, 4), dtype=np.uint32)
+    q = np.empty((n_queries, query_words(log_n, w, wp)), dtype=np.uint32)
+    prm = ParamsC(n_queries, pow_bits, 1 if fast else 0, 1 if cheat_opening else 0)
+    lib().orc_prove_segment(_p(t), C.c_uint(log_n), C.c_size_t(w), C.byref(air.c), C.byref(prm), C.byref(proof), st, _p(ys), _p(q))
+    return proof.as_dict(), ys, q, dict(zip(STAGES, list(st)))
+
+
+def prove_segment(trace, bc, spans, bus=None, n_queries=0, pow_bits=0, fast=False):
+    d, _, _, st = prove(trace, bc, spans, bus, n_queries, pow_bits, fast)
+    return d, st
+
+
+def prove_segment_q(trace, bc, spans, n_queries, bus=None, pow_bits=4, fast=False):
+    d, ys, q, _ = prove(trace, bc, spans, bus, n_queries, pow_bits, fast)
+    return d, ys, q
+
+
+def verify_segment(bc, spans, log_n, width, proof, ys, queries, check_constraints=False, bus=None):
+    """0 = accept; see oracle.h for the failure codes"""
+    air = bus if isinstance(bus, Air) else Air(bc, spans, bus)
+    ys, q = _u32(ys), _u32(queries)
+    p = SegmentProof.from_dict(proof)
+    lib().orc_verify_segment.restype = C.c_int
+    return lib().orc_verify_segment(C.byref(air.c), C.c_uint(log_n), C.c_size_t(width), C.byref(p), _p(ys), _p(q),
+                                    C.c_int(1 if check_constraints else 0))
+
+
+def grind(challenger, bits):
+    lib().orc_grind.restype = C.c_uint32
+    return int(lib().orc_grind(C.byref(challenger.s), C.c_uint(bits)))
+
+
+def logup_perm_trace(trace, bus, alpha_lu, beta_lu):
+    """-> (perm (4*(n_chunks+1), N), cumulative sum [4], chunk_start list)"""
+    t = _u32(trace)
+    w, n = t.shape
+    air = Air([], [], bus)
+    cs = np.zeros(air.n_ints + 1, dtype=np.uint32)
+    lib().orc_logup_chunks.restype = C.c_int
+    ibc, isp, ints = C.c_void_p(air.c.ibc), C.c_void_p(air.c.ispans), C.c_void_p(air.c.ints)
+    nc = lib().orc_logup_chunks(ibc, isp, ints, C.c_size_t(air.n_ints), C.c_uint(3), _p(cs))
+    assert nc >= 0
+    perm = np.empty((4 * (nc + 1), n), dtype=np.uint32)
+    cum = np.empty(4, dtype=np.uint32)
+    a, b = _u32(alpha_lu), _u32(beta_lu)
+    lib().orc_logup_perm_trace(_p(t), C.c_uint(n.bit_length() - 1), ibc, isp, ints, C.c_size_t(air.n_ints), _p(cs),
+                               C.c_size_t(nc), _p(a), _p(b), _p(perm), _p(cum))
+    return perm, cum, cs[:nc + 1].tolist()
+
+
+# ---- AVX-512 Montgomery implementations of the heavy primitives (oracle/fast.c): same semantics as the functions above ----
+def fast_available():
+    lib().orcf_available.restype = C.c_int
+    return bool(lib().orcf_available())
+
+
+def fast_lde_batch(trace, log_blowup=1, shift=GENERATOR):
+    t = _u32(trace)
+    w, n = t.shape
+    out = np.empty((w, n << log_blowup), dtype=np.uint32)
+    lib().orcf_lde_batch(_p(t), C.c_uint(n.bit_length() - 1), C.c_size_t(w), C.c_uint(log_blowup), C.c_uint32(shift), _p(out))
+    return out
+
+
+def fast_merkle_commit(mats):
+    mats = [_u32(m) for m in mats]
+    h = mats[0].shape[1]
+    ptrs = (C.c_void_p * len(mats))(*[m.ctypes.data for m in mats])
+    widths = (C.c_size_t * len(mats))(*[m.shape[0] for m in mats])
+    flat = np.empty((2 * h - 1, 8), dtype=np.uint32)
+    lib().orcf_merkle_commit(ptrs, widths, C.c_size_t(len(mats)), C.c_uint(h.bit_length() - 1), _p(flat))
+    layers, off, n = [], 0, h
+    while n >= 1:
+        layers.append(flat[off:off + n])
+        off += n
+        n >>= 1
+    return layers
+
+
+def fast_constraint_fold(bc, spans, mat, alpha):
+    bc, m, al = _u32(bc), _u32(mat), _u32(alpha)
+    w, h = m.shape
+    out = np.empty((4, h), dtype=np.uint32)
+    lib().orcf_constraint_fold(_p(bc), compile_spans(spans), C.c_size_t(len(spans)), _p(m), C.c_size_t(h), _p(al), _p(out))
+    return out
+
+
+def fast_quotient(bc, spans, lde, log_n, alpha, shift=GENERATOR):
+    bc, m, al = _u32(bc), _u32(lde), _u32(alpha)
+    out = np.empty((2, 4, 1 << log_n), dtype=np.uint32)
+    lib().orcf_quotient(_p(bc), compile_spans(spans), C.c_size_t(len(spans)), _p(m), C.c_uint(log_n), C.c_uint(1),
+                        C.c_uint32(shift), _p(al), _p(out))
+    return out
+
+
+def fast_eval_at_point(mat, shift, zeta):
+    m, z = _u32(mat), _u32(zeta)
+    w, n = m.shape
+    out = np.empty((w, 4), dtype=np.uint32)
+    lib().orcf_eval_at_point(_p(m), C.c_uint(n.bit_length() - 1), C.c_size_t(w), C.c_uint32(shift), _p(z), _p(out))
+    return out
+
+
+def fast_deep_quotient(mats, shift, zeta, gamma, ys):
+    mats = [_u32(x) for x in mats]
+    m = mats[0].shape[1]
+    ptrs = (C.c_void_p * len(mats))(*[x.ctypes.data for x in mats])
+    widths = (C.c_size_t * len(mats))(*[x.shape[0] for x in mats])
+    z, g, y = _u32(zeta), _u32(gamma), _u32(ys)
+    out = np.empty((m, 4), dtype=np.uint32)
+    lib().orcf_deep_quotient(ptrs, widths, C.c_size_t(len(mats)), C.c_uint(m.bit_length() - 1), C.c_uint32(shift), _p(z), _p(g), _p(y), _p(out))
+    return out

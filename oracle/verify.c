@@ -2,9 +2,10 @@
  * ORACLE (test infrastructure, not product code): an independent VERIFIER for the segment proof object.
  * The reference's own tests pin the prover only by validity -- a proof produced by engine E must verify under the CPU
  * engine (verify_app_proof::<BabyBearPoseidon2CpuEngine>, /root/reference/openvm-riscv/src/lib.rs:337-341).
- * This file plays that role for the transcript of DESIGN.md §3: it re-derives every challenge, recomputes the reduced
- * opening from the opened rows, checks every Merkle path, every FRI fold and the final polynomial, and (optionally, for
- * satisfying traces) the constraint identity  sum_k alpha^(C-1-k) c_k(T(zeta)) = Z_H(zeta) * Q(zeta).
+ * This file plays that role for the transcript v2 of DESIGN.md §3: it re-derives every challenge (LogUp, alpha, zeta, gamma,
+ * betas), checks the proof of work, recomputes the reduced opening (two opening points) from the opened rows, checks every
+ * Merkle path, every FRI fold, that the final polynomial is CONSTANT and matches, and (optionally, for satisfying traces) the
+ * constraint identity  Horner_alpha(c_k(T(zeta)), LogUp constraints at zeta) = Z_H(zeta) * Q(zeta).
  * It shares no state with the prover: inputs are the proof struct, the opened values and the query openings.
  */
 #include "oracle.h"
@@ -45,58 +46,84 @@ static bb4_t eval_ext(const uint32_t* bc, uint32_t len, const uint32_t* vals) {
     return st[0];
 }
 
-int orc_verify_segment(const uint32_t* bc, const orc_span_t* spans, size_t n_constraints, unsigned log_n, size_t width,
-                       const orc_segment_proof_t* proof, const uint32_t* ys, const uint32_t* queries, size_t n_queries,
-                       int check_constraints) {
+bb4_t orc_logup_fold_at_point(bb4_t acc, bb4_t alpha, const uint32_t* main_ys, const uint32_t* perm_ys, const uint32_t* perm_next_ys,
+                              unsigned log_n, bb4_t zeta, const uint32_t* ibc, const orc_span_t* isp, const orc_interaction_t* ints, size_t n_ints,
+                              const uint32_t* chunk_start, size_t n_chunks, bb4_t al, const uint32_t beta_lu[4], bb4_t cumsum);
+
+int orc_verify_segment(const orc_air_t* air, unsigned log_n, size_t width, const orc_segment_proof_t* proof, const uint32_t* ys,
+                       const uint32_t* queries, int check_constraints) {
     const unsigned log_m = log_n + 1;
-    const size_t n = (size_t)1 << log_n, n_open = width + 8;
+    const size_t n = (size_t)1 << log_n;
     if (proof->n_fri_layers != log_n || proof->final_len != 2) return 20;
+    size_t n_chunks = 0, wp = 0;
+    uint32_t* chunk_start = NULL;
+    if (air->n_ints) {
+        chunk_start = (uint32_t*)malloc((air->n_ints + 1) * sizeof(uint32_t));
+        int nc = orc_logup_chunks(air->ibc, air->ispans, air->ints, air->n_ints, 3, chunk_start);
+        if (nc < 0) { free(chunk_start); return 20; }
+        n_chunks = (size_t)nc;
+        wp = 4 * (n_chunks + 1);
+    }
+    if (proof->perm_width != wp) { free(chunk_start); return 20; }
+    const size_t n_open = orc_num_opened(width, wp);
+    const size_t n_queries = proof->n_queries;
+    int rc = 0;
+#define FAIL(code) do { rc = (code); goto done; } while (0)
+    bb4_t* gp = NULL;
 
     /* 1. transcript */
     orc_challenger_t ch;
     orc_challenger_init(&ch);
     uint32_t t4[4];
     orc_challenger_observe(&ch, proof->trace_root, 8);
+    if (air->n_ints) {
+        orc_challenger_sample_ext(&ch, t4);
+        if (memcmp(t4, proof->logup_alpha, 16)) FAIL(1);
+        orc_challenger_sample_ext(&ch, t4);
+        if (memcmp(t4, proof->logup_beta, 16)) FAIL(1);
+        orc_challenger_observe(&ch, proof->perm_root, 8);
+        orc_challenger_observe(&ch, proof->cumulative_sum, 4);
+    }
     orc_challenger_sample_ext(&ch, t4);
-    if (memcmp(t4, proof->alpha, 16)) return 1;
+    if (memcmp(t4, proof->alpha, 16)) FAIL(2);
     orc_challenger_observe(&ch, proof->quotient_root, 8);
     orc_challenger_sample_ext(&ch, t4);
-    if (memcmp(t4, proof->zeta, 16)) return 2;
-    {
-        size_t rows = 1;
-        unsigned lr = 0;
-        while (rows * 8 < 4 * n_open) { rows <<= 1; lr++; }
-        uint32_t* buf = (uint32_t*)calloc(rows * 8, 4);
-        memcpy(buf, ys, 16 * n_open);
-        uint32_t* layer = (uint32_t*)malloc(8 * rows * 4);
-        for (size_t r = 0; r < rows; r++) orc_hash_row(buf + 8 * r, 8, layer + 8 * r);
-        for (size_t m = rows >> 1; m >= 1; m >>= 1) {
-            for (size_t j = 0; j < m; j++) { uint32_t o[8]; orc_compress(layer + 16 * j, layer + 16 * j + 8, o); memcpy(layer + 8 * j, o, 32); }
-            if (m == 1) break;
-        }
-        int ok = memcmp(layer, proof->openings_root, 32) == 0;
-        free(buf);
-        free(layer);
-        if (!ok) return 3;
-    }
-    orc_challenger_observe(&ch, proof->openings_root, 8);
+    if (memcmp(t4, proof->zeta, 16)) FAIL(3);
+    orc_challenger_observe(&ch, ys, 4 * n_open);
     orc_challenger_sample_ext(&ch, t4);
-    if (memcmp(t4, proof->gamma, 16)) return 3;
+    if (memcmp(t4, proof->gamma, 16)) FAIL(4);
     for (uint32_t i = 0; i < proof->n_fri_layers; i++) {
         orc_challenger_observe(&ch, proof->fri_roots[i], 8);
         orc_challenger_sample_ext(&ch, t4);
-        if (memcmp(t4, proof->fri_betas[i], 16)) return 4;
+        if (memcmp(t4, proof->fri_betas[i], 16)) FAIL(5);
+    }
+    /* the final polynomial has one coefficient: both evaluations of the last layer must be that constant */
+    if (memcmp(proof->final_poly[0], proof->final_poly[1], 16)) FAIL(15);
+    orc_challenger_observe(&ch, proof->final_poly[0], 4);
+    {
+        const uint32_t mask = proof->pow_bits >= 31 ? 0x7fffffffu : ((1u << proof->pow_bits) - 1);
+        if (proof->pow_witness >= BB_P) FAIL(6);
+        orc_challenger_observe(&ch, &proof->pow_witness, 1);
+        if (orc_challenger_sample(&ch) & mask) FAIL(6);
     }
 
     const bb4_t zeta = ld4(proof->zeta), gamma = ld4(proof->gamma), alpha = ld4(proof->alpha);
+    const bb4_t zeta_next = bb4_scale(zeta, bb_root_of_unity(log_n));
+    const uint32_t* ys_main = ys;
+    const uint32_t* ys_perm = ys + 4 * width;
+    const uint32_t* ys_perm_next = ys + 4 * (width + wp);
+    const uint32_t* ys_q = ys + 4 * (width + 2 * wp);
 
     /* 2. constraint identity at zeta (only meaningful for a satisfying trace) */
     if (check_constraints) {
         bb4_t acc = bb4_from_base(0);
-        for (size_t k = 0; k < n_constraints; k++) {
+        for (size_t k = 0; k < air->n_constraints; k++) {
             acc = bb4_mul(acc, alpha);
-            acc = bb4_add(acc, eval_ext(bc + spans[k].off, spans[k].len, ys));
+            acc = bb4_add(acc, eval_ext(air->bc + air->spans[k].off, air->spans[k].len, ys_main));
         }
+        if (air->n_ints)
+            acc = orc_logup_fold_at_point(acc, alpha, ys_main, ys_perm, ys_perm_next, log_n, zeta, air->ibc, air->ispans, air->ints, air->n_ints,
+                                          chunk_start, n_chunks, ld4(proof->logup_alpha), proof->logup_beta, ld4(proof->cumulative_sum));
         bb4_t zn = bb4_pow(zeta, n);
         uint32_t gn = bb_pow(BB_GENERATOR, n);
         /* Q(zeta) = sum_b (zeta^N - g^N (-1)^(1-b)) / (2 g^N (-1)^b) * Q_b(zeta),  Q_b = sum_l x^l-basis limb l of chunk b */
@@ -110,49 +137,60 @@ int orc_verify_segment(const uint32_t* bc, const orc_span_t* spans, size_t n_con
             for (int l = 0; l < 4; l++) {
                 bb4_t e = bb4_from_base(0);
                 e.c[l] = 1;                                             /* basis element x^l of Ext4 */
-                qb = bb4_add(qb, bb4_mul(e, ld4(ys + 4 * (width + 4 * b + l))));
+                qb = bb4_add(qb, bb4_mul(e, ld4(ys_q + 4 * (4 * b + l))));
             }
             q = bb4_add(q, bb4_mul(bb4_scale(num, den), qb));
         }
         bb4_t zh = zn;
         zh.c[0] = bb_sub(zh.c[0], 1);
-        if (!eq4(acc, bb4_mul(zh, q))) return 12;
+        if (!eq4(acc, bb4_mul(zh, q))) FAIL(16);
     }
 
     /* 3. queries */
-    size_t wpq = 1 + width + 8 * log_m + 8 + 8 * log_m;
-    for (unsigned i = 0; i < log_n; i++) wpq += 8 + 8 * (log_m - 1 - i);
-    bb4_t* gp = (bb4_t*)malloc(n_open * sizeof(bb4_t));
-    bb4_t cur = bb4_from_base(1), ysum = bb4_from_base(0);
+    const size_t wpq = orc_query_words(log_n, width, wp);
+    gp = (bb4_t*)malloc(n_open * sizeof(bb4_t));
+    bb4_t cur = bb4_from_base(1), ysum0 = bb4_from_base(0), ysum1 = bb4_from_base(0);
     for (size_t j = 0; j < n_open; j++) {
         gp[j] = cur;
-        ysum = bb4_add(ysum, bb4_mul(cur, ld4(ys + 4 * j)));
+        const int next_group = j >= width + wp && j < width + 2 * wp;
+        if (next_group) ysum1 = bb4_add(ysum1, bb4_mul(cur, ld4(ys + 4 * j)));
+        else ysum0 = bb4_add(ysum0, bb4_mul(cur, ld4(ys + 4 * j)));
         cur = bb4_mul(cur, gamma);
     }
     const uint32_t two_inv = bb_inv(2);
-    int rc = 0;
     for (size_t qi = 0; qi < n_queries && !rc; qi++) {
         const uint32_t* o = queries + qi * wpq;
         const size_t r = o[0];
-        if (r != (orc_challenger_sample(&ch) & (((size_t)1 << log_m) - 1))) { rc = 5; break; }
+        if (r != (orc_challenger_sample(&ch) & (((size_t)1 << log_m) - 1))) { rc = 7; break; }
         const uint32_t* trow = o + 1;
         const uint32_t* tpath = trow + width;
-        const uint32_t* qrow = tpath + 8 * log_m;
+        const uint32_t* prow = tpath + 8 * log_m;
+        const uint32_t* ppath = prow + wp;
+        const uint32_t* qrow = wp ? ppath + 8 * log_m : prow;
         const uint32_t* qpath = qrow + 8;
         const uint32_t* fr = qpath + 8 * log_m;
         uint32_t leaf[8];
         orc_hash_row(trow, width, leaf);
-        if (!check_path(leaf, r, tpath, log_m, proof->trace_root)) { rc = 6; break; }
+        if (!check_path(leaf, r, tpath, log_m, proof->trace_root)) { rc = 8; break; }
+        if (wp) {
+            orc_hash_row(prow, wp, leaf);
+            if (!check_path(leaf, r, ppath, log_m, proof->perm_root)) { rc = 9; break; }
+        }
         orc_hash_row(qrow, 8, leaf);
-        if (!check_path(leaf, r, qpath, log_m, proof->quotient_root)) { rc = 7; break; }
-        bb4_t acc = bb4_from_base(0);
-        for (size_t j = 0; j < width; j++) acc = bb4_add(acc, bb4_scale(gp[j], trow[j]));
-        for (size_t j = 0; j < 8; j++) acc = bb4_add(acc, bb4_scale(gp[width + j], qrow[j]));
-        acc = bb4_sub(acc, ysum);
+        if (!check_path(leaf, r, qpath, log_m, proof->quotient_root)) { rc = 10; break; }
+        bb4_t a0 = bb4_from_base(0), a1 = bb4_from_base(0);
+        for (size_t j = 0; j < width; j++) a0 = bb4_add(a0, bb4_scale(gp[j], trow[j]));
+        for (size_t j = 0; j < wp; j++) {
+            a0 = bb4_add(a0, bb4_scale(gp[width + j], prow[j]));
+            a1 = bb4_add(a1, bb4_scale(gp[width + wp + j], prow[j]));
+        }
+        for (size_t j = 0; j < 8; j++) a0 = bb4_add(a0, bb4_scale(gp[width + 2 * wp + j], qrow[j]));
+        a0 = bb4_sub(a0, ysum0);
+        a1 = bb4_sub(a1, ysum1);
         uint32_t x = bb_mul(BB_GENERATOR, bb_pow(bb_root_of_unity(log_m), bitrev32((uint32_t)r, log_m)));
-        bb4_t d = bb4_from_base(x);
-        d = bb4_sub(d, zeta);
-        bb4_t val = bb4_mul(acc, bb4_inv(d));
+        bb4_t d0 = bb4_sub(bb4_from_base(x), zeta), d1 = bb4_sub(bb4_from_base(x), zeta_next);
+        bb4_t val = bb4_mul(a0, bb4_inv(d0));
+        if (wp) val = bb4_add(val, bb4_mul(a1, bb4_inv(d1)));
         size_t idx = r;
         uint32_t shift = BB_GENERATOR;
         for (unsigned i = 0; i < log_n; i++) {
@@ -161,10 +199,10 @@ int orc_verify_segment(const uint32_t* bc, const orc_span_t* spans, size_t n_con
             const uint32_t* path = fr + 8;
             fr += 8 + 8 * log_h;
             bb4_t lo = ld4(pair), hi = ld4(pair + 4);
-            if (!eq4((idx & 1) ? hi : lo, val)) { rc = i == 0 ? 8 : 10; break; }
+            if (!eq4((idx & 1) ? hi : lo, val)) { rc = i == 0 ? 11 : 13; break; }
             const size_t j = idx >> 1;
             orc_hash_row(pair, 8, leaf);
-            if (!check_path(leaf, j, path, log_h, proof->fri_roots[i])) { rc = 9; break; }
+            if (!check_path(leaf, j, path, log_h, proof->fri_roots[i])) { rc = 12; break; }
             uint32_t xj = bb_mul(shift, bb_pow(bb_root_of_unity(log_len), bitrev32((uint32_t)j, log_h)));
             bb4_t beta = ld4(proof->fri_betas[i]);
             bb4_t s = bb4_scale(bb4_add(lo, hi), two_inv);
@@ -173,8 +211,11 @@ int orc_verify_segment(const uint32_t* bc, const orc_span_t* spans, size_t n_con
             idx = j;
             shift = bb_mul(shift, shift);
         }
-        if (!rc && !eq4(val, ld4(proof->final_poly[idx]))) rc = 11;
+        if (!rc && !eq4(val, ld4(proof->final_poly[idx]))) rc = 14;
     }
+done:
     free(gp);
+    free(chunk_start);
     return rc;
+#undef FAIL
 }

@@ -298,3 +298,55 @@ def synthetic_machine(width, n_constraints, seed=0):
             acc = term if acc is None else [acc, "+", term]
         cons.append(acc)
     return SymbolicMachine(cons)
+
+
+def synthetic_bus(machine_or_width, n_interactions, seed=0, quadratic_every=0):
+    """Synthetic bus interactions with the SHAPE of an APC's: the bus mix of the reference's keccak fixture
+    (/root/reference/autoprecompiles/tests/keccak_apc_pre_opt.json.gz, SURVEY.md App. A: bus 3 variable range checker 39 %,
+    bus 1 memory 31 %, bus 6 bitwise lookup 16 %, bus 0 execution bridge 10 %, bus 2 pc lookup 5 %) and their argument
+    tuples (periphery.rs:179-236: bitwise [x, y, x^y, selector], range checker [value, max_bits]; memory
+    [address space, pointer, 4 data limbs, timestamp]; execution bridge [pc, timestamp]; pc lookup 9 words), every
+    expression of degree <= 1 (mult is a column or a negated column -- a guarded APC multiplies by is_valid), so two
+    interactions share a LogUp chunk.  quadratic_every > 0 makes every such interaction carry one degree-2 argument (bus
+    degree bound 2, openvm/src/lib.rs:97-101), which forces a chunk of its own.
+    Returns the list in the JSON schema of SymbolicBusInteraction ({"id", "mult", "args"})."""
+    width = machine_or_width if isinstance(machine_or_width, int) else machine_or_width.width
+    names = ["c%d@%d" % (i, i) for i in range(width)] if isinstance(machine_or_width, int) else machine_or_width.column_names
+    s = [(seed * 0x9E3779B97F4A7C15 + 0xB05B05) & (2**64 - 1)]
+
+    def rnd():
+        s[0] = (s[0] + 0x9E3779B97F4A7C15) & (2**64 - 1)
+        z = s[0]
+        z = ((z ^ (z >> 30)) * 0xBF58476D1CE4E5B9) & (2**64 - 1)
+        z = ((z ^ (z >> 27)) * 0x94D049BB133111EB) & (2**64 - 1)
+        return z ^ (z >> 31)
+
+    def col():
+        return names[rnd() % width]
+
+    def lin():
+        k = rnd() % 4
+        if k == 0:
+            return [col(), "+", int(rnd() % 65536)]
+        if k == 1:
+            return [col(), "-", [int(2 + rnd() % (P - 2)), "*", col()]]
+        return col()
+
+    out = []
+    for i in range(n_interactions):
+        t = rnd() % 100
+        mult = col() if rnd() % 2 else ["-", col()]
+        if t < 39:
+            bus, args = 3, [lin(), int(1 + rnd() % 17)]
+        elif t < 70:
+            bus, args = 1, [int(1 + rnd() % 2), lin(), col(), col(), col(), col(), lin()]
+        elif t < 86:
+            bus, args = 6, [col(), col(), col(), int(rnd() % 2)]
+        elif t < 96:
+            bus, args = 0, [int(rnd() % (1 << 22)), lin()]
+        else:
+            bus, args = 2, [int(rnd() % (1 << 22))] + [int(rnd() % 4096) for _ in range(8)]
+        if quadratic_every and i % quadratic_every == quadratic_every - 1:
+            args[0] = [col(), "*", col()]
+        out.append({"id": bus, "mult": mult, "args": args})
+    return out

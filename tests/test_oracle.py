@@ -315,18 +315,19 @@ def test_verifier_accepts_honest_and_rejects_tampered(orc):
     bc, spans = M.compile_constraints(mach)
     trace = rand_field(np.random.default_rng(79), (mach.width, 1 << 7))
     proof, ys, q = orc.prove_segment_q(trace, bc, spans, 6)
-    assert proof == orc.prove_segment(trace, bc, spans)[0]
+    p0 = orc.prove_segment(trace, bc, spans, n_queries=6, pow_bits=4)[0]
+    assert proof == p0
     assert orc.verify_segment(bc, spans, 7, mach.width, proof, ys, q) == 0
     q2 = q.copy(); q2[2, 5] ^= 1
-    assert orc.verify_segment(bc, spans, 7, mach.width, proof, ys, q2) == 6          # trace row no longer matches its path
+    assert orc.verify_segment(bc, spans, 7, mach.width, proof, ys, q2) == 8          # trace row no longer matches its path
     q3 = q.copy(); q3[0, -3] ^= 1
-    assert orc.verify_segment(bc, spans, 7, mach.width, proof, ys, q3) == 9          # FRI layer path
+    assert orc.verify_segment(bc, spans, 7, mach.width, proof, ys, q3) == 12         # FRI layer path
     q4 = q.copy(); q4[1, 1 + mach.width + 8 * 8 + 8 + 8 * 8 + 2] ^= 1               # a layer-0 pair value
-    assert orc.verify_segment(bc, spans, 7, mach.width, proof, ys, q4) in (8, 9, 10)
+    assert orc.verify_segment(bc, spans, 7, mach.width, proof, ys, q4) in (11, 12, 13)
     ys2 = ys.copy(); ys2[3, 1] = (int(ys2[3, 1]) + 1) % P
-    assert orc.verify_segment(bc, spans, 7, mach.width, proof, ys2, q) == 3          # opened values are bound by the transcript
+    assert orc.verify_segment(bc, spans, 7, mach.width, proof, ys2, q) == 4          # every opened value is bound by the transcript
     bad = dict(proof); bad["final_poly"] = [[1, 2, 3, 4], [1, 2, 3, 4]]
-    assert orc.verify_segment(bc, spans, 7, mach.width, bad, ys, q) == 11
+    assert orc.verify_segment(bc, spans, 7, mach.width, bad, ys, q) in (6, 7)        # final polynomial is observed before the PoW
 
 
 def test_verifier_constraint_identity_on_satisfying_and_unsatisfying_traces(orc):
@@ -343,7 +344,7 @@ def test_verifier_constraint_identity_on_satisfying_and_unsatisfying_traces(orc)
     trace[2, 17] = (int(trace[2, 17]) + 1) % P                                       # one bad cell
     proof, ys, q = orc.prove_segment_q(trace, bc, spans, 5)
     assert orc.verify_segment(bc, spans, 7, 3, proof, ys, q, check_constraints=False) == 0    # the PCS part is still sound
-    assert orc.verify_segment(bc, spans, 7, 3, proof, ys, q, check_constraints=True) == 12
+    assert orc.verify_segment(bc, spans, 7, 3, proof, ys, q, check_constraints=True) == 16
 
 
 def test_large_preopt_fixture_against_python_evaluator(orc):
