@@ -33,6 +33,7 @@ int main(int argc, char** argv) {
 
     pb_ctx_t* ctx = NULL;
     CHECK(pb_ctx_create(&ctx, 0, NULL));            /* PB_ERR_NO_DEVICE without a GPU: there is no CPU path */
+    CHECK(pb_ctx_set_fri_params(ctx, 4, 16));       /* 4 queries, 16 proof-of-work bits */
     pb_air_t* air = NULL;
     CHECK(pb_air_compile(ctx, bytecode, sizeof bytecode / sizeof bytecode[0], constraints, 2, (uint32_t)width, &air));
 
@@ -60,13 +61,13 @@ int main(int argc, char** argv) {
     printf("\n");
 
     size_t wpq = 0;
-    CHECK(pb_query_words(log_n, width, &wpq));
+    CHECK(pb_query_words(log_n, width, 0, &wpq));
     uint32_t* q = (uint32_t*)malloc(4 * wpq * 4);
-    CHECK(pb_query_segment(ctx, 4, q, 4 * wpq));
+    CHECK(pb_query_segment(ctx, q, 4 * wpq));            /* 4 queries: pb_ctx_set_fri_params above */
     printf("query_rows %u %u %u %u\n", q[0], q[wpq], q[2 * wpq], q[3 * wpq]);
-    float ms[9];
+    float ms[PB_N_STAGES];
     CHECK(pb_last_stage_ms(ctx, ms));
-    printf("total_ms %.3f launches %llu\n", ms[8], (unsigned long long)pb_launch_count(ctx));
+    printf("total_ms %.3f launches %llu\n", ms[PB_N_STAGES - 1], (unsigned long long)pb_launch_count(ctx));
 
     free(q);
     CHECK(pb_host_free(trace));

@@ -111,32 +111,43 @@ int pb_deep_quotient(pb_ctx_t* ctx, const uint32_t* const* d_mats, const size_t*
 /* ---- whole segment: the metric's unit of work ------------------------------------------------------------------------
  * Replaces engine.prove(pk, ProvingContext{common_main}) for one APC chip behind sdk.app_prover(exe)?.prove(stdin)
  * (/root/reference/openvm-riscv/src/lib.rs:327-332; AirProvingContext built at
- * /root/reference/openvm/src/powdr_extension/trace_generator/cuda/mod.rs:415-419): main trace commit (LDE + Merkle),
- * quotient, quotient commit, openings at zeta, reduced opening, FRI commit phase.  Transcript documented in DESIGN.md. */
+ * /root/reference/openvm/src/powdr_extension/trace_generator/cuda/mod.rs:415-419).  Stages, in the V1 metric names of
+ * /root/reference/openvm/metrics-viewer/CLAUDE.md:52-78: main_trace_commit (LDE + Merkle), perm_trace_commit (the LogUp
+ * permutation trace of the AIR's bus interactions: generated, LDE'd, committed), quotient_poly_compute, quotient_poly_commit,
+ * pcs_opening (openings at zeta / zeta*w, reduced opening, FRI commit phase, proof of work, queries).
+ * Transcript v2 is documented in DESIGN.md §3 (CPU restatement and independent verifier live in the test tree). */
 typedef struct {
     uint32_t trace_root[8];
-    uint32_t quotient_root[8];
+    uint32_t logup_alpha[4], logup_beta[4];   /* LogUp challenges; zero when the AIR has no interactions */
+    uint32_t perm_root[8];
+    uint32_t cumulative_sum[4];               /* exposed value phi(N-1) of the running sum */
     uint32_t alpha[4];
+    uint32_t quotient_root[8];
     uint32_t zeta[4];              /* out-of-domain opening point */
-    uint32_t openings_root[8];     /* Merkle root (rows of 8, zero padded to a power of two) over the opened values */
     uint32_t gamma[4];             /* batching challenge of the reduced opening */
     uint32_t n_fri_layers;
     uint32_t fri_roots[32][8];
     uint32_t fri_betas[32][4];
-    uint32_t final_poly[8][4];
+    uint32_t final_poly[8][4];     /* last FRI layer (2^log_blowup evaluations of the constant final polynomial) */
     uint32_t final_len;
+    uint32_t pow_witness;
+    uint32_t pow_bits, n_queries, perm_width;
 } pb_segment_proof_t;               /* all values canonical */
 #define PB_TRACE_ON_DEVICE 1u       /* `trace` is a device pointer (value-only timing); else host memory, copied in */
+/* FRI parameters of the context; default 100 queries, 16 proof-of-work bits (the reference's app configuration for
+ * log_blowup 1: standard_fri_params_with_100_bits_conjectured_security in the un-vendored SDK -- recollection) */
+int pb_ctx_set_fri_params(pb_ctx_t* ctx, uint32_t n_queries, uint32_t pow_bits);
 int pb_prove_segment(pb_ctx_t* ctx, const pb_air_t* air, const uint32_t* trace, size_t log_n, size_t width, uint32_t flags,
                      pb_segment_proof_t* proof);
-/* ---- query phase (completes SURVEY.md §8f-4): the state of the last pb_prove_segment stays on the device ------------------
- * pb_query_segment samples n_queries indices from the transcript (sample_bits(log_m) each, continuing after the FRI commit
- * phase) and gathers, per query (canonical words, pb_query_words of them):
- *   [ r | trace LDE row (width) | trace path (log_m x 8) | quotient row (8) | quotient path (log_m x 8) |
- *     per FRI layer i: opened pair row (8), path ((log_m-1-i) x 8) ]
- * pb_last_openings: the values opened at zeta, [(width + 8)][4] canonical. */
-int pb_query_words(size_t log_n, size_t width, size_t* words_per_query);
-int pb_query_segment(pb_ctx_t* ctx, size_t n_queries, uint32_t* h_out, size_t out_capacity_words);
+/* ---- query phase: the state of the last pb_prove_segment stays on the device ----------------------------------------------
+ * pb_query_segment samples n_queries indices from the transcript (sample_bits(log_m) each, continuing after the proof of work)
+ * and gathers, per query (canonical words, pb_query_words of them):
+ *   [ r | trace LDE row (width) | trace path (log_m x 8) | perm LDE row (perm_width) | perm path (log_m x 8)  (both absent
+ *     when perm_width = 0) | quotient row (8) | quotient path (log_m x 8) | per FRI layer i: opened pair row (8), path ((log_m-1-i) x 8) ]
+ * pb_last_openings: the opened values, [(width + 2*perm_width + 8)][4] canonical:
+ *   main at zeta | perm at zeta | perm at zeta*w | quotient chunks at zeta. */
+int pb_query_words(size_t log_n, size_t width, size_t perm_width, size_t* words_per_query);
+int pb_query_segment(pb_ctx_t* ctx, uint32_t* h_out, size_t out_capacity_words);
 int pb_last_openings(pb_ctx_t* ctx, uint32_t* h_ys, size_t capacity_words);
 
 /* ---- one segment across G = 2^g GPUs, one process (and one pb_ctx) per GPU: SURVEY.md §8e ----
@@ -164,8 +175,10 @@ int pb_lde_shard(pb_ctx_t* ctx, const uint32_t* d_trace, size_t log_n, size_t wi
 int pb_prove_segment_sharded(pb_ctx_t* ctx, const pb_air_t* air, const uint32_t* trace_cols, size_t log_n, size_t width, uint32_t flags,
                              const pb_comm_t* comm, pb_segment_proof_t* proof);
 
-/* per-stage device milliseconds of the last pb_prove_segment: [h2d, lde, merkle, quotient, qlde, qmerkle, open, fri, total] */
-int pb_last_stage_ms(pb_ctx_t* ctx, float ms[9]);
+/* per-stage device milliseconds of the last pb_prove_segment:
+ * [h2d, lde, merkle, logup_gen, logup_commit, quotient, qlde, qmerkle, open, fri, pow, total] */
+#define PB_N_STAGES 12
+int pb_last_stage_ms(pb_ctx_t* ctx, float ms[PB_N_STAGES]);
 /* kernels launched by this context since creation (bench.py's gpu_launches) */
 uint64_t pb_launch_count(pb_ctx_t* ctx);
 /* CUDA-event timing of the dominant kernel (Poseidon2 leaf hashing of column-major matrices) since the last call:
@@ -178,6 +191,24 @@ typedef struct { int air_index; int col; int row; int apc_col; } Subst;         
 typedef struct { uint32_t off; uint32_t len; } ExprSpan;                                               /* cuda_abi.rs:162-169 */
 typedef struct { uint64_t col_base; ExprSpan span; } DerivedExprSpec;                                  /* cuda_abi.rs:88-95 */
 typedef struct { uint32_t bus_id; uint32_t num_args; uint32_t args_index_off; } DevInteraction;        /* cuda_abi.rs:150-160 */
+/* ---- LogUp / bus interactions of an AIR -------------------------------------------------------------------
+ * Attaches the bus interactions PowdrAir::eval pushes (/root/reference/openvm/src/powdr_extension/chip.rs:117-128) to a compiled
+ * AIR, in the layout compile_bus_to_gpu produces (cuda/mod.rs:143-177: per interaction the spans [mult, arg_0 .. arg_{k-1}]
+ * from args_index_off) with the PUSH_APC operand being the COLUMN INDEX.  Generates and compiles the AIR's LogUp kernels
+ * (NVRTC, sm_100a); pb_prove_segment then runs the permutation-trace phase for this AIR.  HOST pointers. */
+int pb_air_set_interactions(pb_ctx_t* ctx, pb_air_t* air, const uint32_t* bytecode, size_t n_words, const ExprSpan* arg_spans,
+                            size_t n_arg_spans, const DevInteraction* interactions, size_t n_interactions);
+/* host-only check of the LogUp code generator (no device needed): generates and compiles the kernels, reports their size */
+int pb_air_logup_compile_only(const uint32_t* bytecode, size_t n_words, const ExprSpan* arg_spans, size_t n_arg_spans,
+                              const DevInteraction* interactions, size_t n_interactions, uint32_t width, size_t* cubin_bytes,
+                              size_t* perm_width);
+/* width of the permutation trace in base columns: 4 * (number of LogUp chunks + 1), 0 without interactions */
+int pb_air_perm_width(const pb_air_t* air, size_t* perm_width);
+/* the one collective of the per-chip / per-segment sharding (north_star "single NCCL all-gather of Merkle caps"):
+ * all_caps[r*8 .. r*8+8) = rank r's local_cap, through the caller's pb_comm_t (device pointers; no NCCL is linked here, which is
+ * also why pb_ctx_create takes no ncclComm_t: the collectives are callbacks so that the same library serves NCCL, MPI or tests) */
+int pb_allgather_caps(pb_ctx_t* ctx, const pb_comm_t* comm, const uint32_t* d_local_cap, uint32_t* d_all_caps);
+
 int _apc_tracegen(uint32_t* d_output, size_t output_height, const OriginalAir* d_original_airs, const Subst* d_subs,
                   size_t n_subs, int num_apc_calls);
 int _apc_apply_derived_expr(uint32_t* d_output, size_t output_height, int num_apc_calls, const DerivedExprSpec* d_specs,

@@ -355,7 +355,7 @@ def prove(trace, bc, spans, bus=None, n_queries=8, pow_bits=4, fast=False, cheat
     return proof.as_dict(), ys, q, dict(zip(STAGES, list(st)))
 
 
-def prove_segment(trace, bc, spans, bus=None, n_queries=0, pow_bits=0, fast=False):
+def prove_segment(trace, bc, spans, bus=None, n_queries=8, pow_bits=4, fast=False):
     d, _, _, st = prove(trace, bc, spans, bus, n_queries, pow_bits, fast)
     return d, st
 

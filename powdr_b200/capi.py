@@ -16,6 +16,7 @@ EXPORTS = [
     "pb_device_alloc", "pb_device_free", "pb_copy_h2d", "pb_copy_d2h", "pb_memset_zero", "pb_to_monty", "pb_from_monty",
     "pb_lde_batch", "pb_air_compile", "pb_air_free", "pb_air_is_jit", "pb_air_jit_compile_only", "pb_quotient", "pb_constraint_fold", "pb_merkle_commit",
     "pb_merkle_commit_rows8", "pb_poseidon2_permute", "pb_fri_fold", "pb_eval_at_point", "pb_deep_quotient", "pb_prove_segment", "pb_query_words", "pb_query_segment", "pb_last_openings", "pb_last_stage_ms",
+    "pb_ctx_set_fri_params", "pb_air_set_interactions", "pb_air_perm_width", "pb_air_logup_compile_only", "pb_allgather_caps",
     "pb_shard_columns", "pb_lde_shard", "pb_prove_segment_sharded",
     "pb_launch_count", "pb_leaf_kernel_profile", "_apc_tracegen", "_apc_apply_derived_expr", "_apc_apply_bus",
 ]
@@ -52,20 +53,27 @@ class DevInteraction(C.Structure):
 
 
 class SegmentProof(C.Structure):
-    _fields_ = [("trace_root", C.c_uint32 * 8), ("quotient_root", C.c_uint32 * 8), ("alpha", C.c_uint32 * 4),
-                ("zeta", C.c_uint32 * 4), ("openings_root", C.c_uint32 * 8), ("gamma", C.c_uint32 * 4),
+    """pb_segment_proof_t (include/powdr_b200.h)"""
+    _fields_ = [("trace_root", C.c_uint32 * 8), ("logup_alpha", C.c_uint32 * 4), ("logup_beta", C.c_uint32 * 4),
+                ("perm_root", C.c_uint32 * 8), ("cumulative_sum", C.c_uint32 * 4), ("alpha", C.c_uint32 * 4),
+                ("quotient_root", C.c_uint32 * 8), ("zeta", C.c_uint32 * 4), ("gamma", C.c_uint32 * 4),
                 ("n_fri_layers", C.c_uint32), ("fri_roots", (C.c_uint32 * 8) * 32), ("fri_betas", (C.c_uint32 * 4) * 32),
-                ("final_poly", (C.c_uint32 * 4) * 8), ("final_len", C.c_uint32)]
+                ("final_poly", (C.c_uint32 * 4) * 8), ("final_len", C.c_uint32), ("pow_witness", C.c_uint32),
+                ("pow_bits", C.c_uint32), ("n_queries", C.c_uint32), ("perm_width", C.c_uint32)]
+    VEC = ("trace_root", "logup_alpha", "logup_beta", "perm_root", "cumulative_sum", "alpha", "quotient_root", "zeta", "gamma")
+    SCALAR = ("n_fri_layers", "final_len", "pow_witness", "pow_bits", "n_queries", "perm_width")
 
     def as_dict(self):
         n = self.n_fri_layers
-        return {
-            "trace_root": list(self.trace_root), "quotient_root": list(self.quotient_root), "alpha": list(self.alpha),
-            "zeta": list(self.zeta), "openings_root": list(self.openings_root), "gamma": list(self.gamma),
-            "n_fri_layers": int(n), "fri_roots": [list(self.fri_roots[i]) for i in range(n)],
-            "fri_betas": [list(self.fri_betas[i]) for i in range(n)],
-            "final_poly": [list(self.final_poly[i]) for i in range(self.final_len)], "final_len": int(self.final_len),
-        }
+        d = {k: list(getattr(self, k)) for k in self.VEC}
+        d.update({k: int(getattr(self, k)) for k in self.SCALAR})
+        d["fri_roots"] = [list(self.fri_roots[i]) for i in range(n)]
+        d["fri_betas"] = [list(self.fri_betas[i]) for i in range(n)]
+        d["final_poly"] = [list(self.final_poly[i]) for i in range(self.final_len)]
+        return d
+
+
+STAGES = ("h2d", "lde", "merkle", "logup_gen", "logup_commit", "quotient", "qlde", "qmerkle", "open", "fri", "pow", "total")
 
 
 _lib = None
@@ -137,7 +145,9 @@ class DeviceBuffer:
 
 
 class Air:
-    def __init__(self, ctx, bytecode, spans, width):
+    def __init__(self, ctx, bytecode, spans, width, bus=None):
+        """bus: (interactions [(bus_id, num_args, args_index_off)], arg_spans [(off, len)], bytecode) as returned by
+        powdr_b200.machine.compile_bus(machine, 1) -- attaches the AIR's bus interactions (LogUp phase of the prover)"""
         self.ctx, self.width, self.n_constraints = ctx, width, len(spans)
         bc = _u32(bytecode)
         sp = (Span * max(1, len(spans)))()
@@ -147,6 +157,21 @@ class Air:
         _chk(ctx.lib.pb_air_compile(ctx.h, bc.ctypes.data_as(C.c_void_p), C.c_size_t(bc.size), sp, C.c_size_t(len(spans)),
                                     C.c_uint32(width), C.byref(h)), "pb_air_compile")
         self.h = h
+        self.perm_width = 0
+        if bus and len(bus[0]):
+            ints, isp, ibc = bus
+            ibc = _u32(ibc)
+            spn = (Span * max(1, len(isp)))()
+            for i, (o, l) in enumerate(isp):
+                spn[i].off, spn[i].len = o, l
+            di = (DevInteraction * len(ints))()
+            for i, (b, n, o) in enumerate(ints):
+                di[i].bus_id, di[i].num_args, di[i].args_index_off = b, n, o
+            _chk(ctx.lib.pb_air_set_interactions(ctx.h, self.h, ibc.ctypes.data_as(C.c_void_p), C.c_size_t(ibc.size), spn, C.c_size_t(len(isp)),
+                                                 di, C.c_size_t(len(ints))), "pb_air_set_interactions")
+            wp = C.c_size_t()
+            _chk(ctx.lib.pb_air_perm_width(self.h, C.byref(wp)), "pb_air_perm_width")
+            self.perm_width = int(wp.value)
 
     @property
     def is_jit(self):
@@ -167,6 +192,7 @@ class Context:
         _chk(self.lib.pb_ctx_create(C.byref(h), C.c_int(device), C.c_void_p(stream or 0)), "pb_ctx_create")
         self.h = h
         self.device = device
+        self.n_queries = 100
 
     def close(self):
         if self.h:
@@ -194,8 +220,12 @@ class Context:
         return raw
 
     # ---- stages ----
-    def air(self, bytecode, spans, width):
-        return Air(self, bytecode, spans, width)
+    def air(self, bytecode, spans, width, bus=None):
+        return Air(self, bytecode, spans, width, bus)
+
+    def set_fri_params(self, n_queries, pow_bits):
+        _chk(self.lib.pb_ctx_set_fri_params(self.h, C.c_uint32(n_queries), C.c_uint32(pow_bits)), "pb_ctx_set_fri_params")
+        self.n_queries = n_queries
 
     def lde_batch(self, d_trace_ptr, log_n, width, d_lde_ptr, log_blowup=1, shift=31):
         _chk(self.lib.pb_lde_batch(self.h, C.c_void_p(d_trace_ptr), C.c_size_t(log_n), C.c_size_t(width), C.c_uint32(log_blowup),
@@ -265,20 +295,21 @@ class Context:
                                                C.c_uint32(1 if on_device else 0), C.byref(comm.c), C.byref(proof)), "pb_prove_segment_sharded")
         return proof.as_dict()
 
-    def query_segment(self, log_n, width, n_queries):
-        """-> (n_queries, words_per_query) uint32 array of openings for the last prove_segment, and the opened values (width+8, 4)"""
+    def query_segment(self, log_n, width, perm_width=0):
+        """-> (n_queries, words_per_query) uint32 array of openings for the last prove_segment (n_queries from set_fri_params),
+        and the opened values (width + 2*perm_width + 8, 4)"""
         wpq = C.c_size_t()
-        _chk(self.lib.pb_query_words(C.c_size_t(log_n), C.c_size_t(width), C.byref(wpq)), "pb_query_words")
-        out = np.empty((n_queries, wpq.value), dtype=np.uint32)
-        _chk(self.lib.pb_query_segment(self.h, C.c_size_t(n_queries), out.ctypes.data_as(C.c_void_p), C.c_size_t(out.size)), "pb_query_segment")
-        ys = np.empty((width + 8, 4), dtype=np.uint32)
+        _chk(self.lib.pb_query_words(C.c_size_t(log_n), C.c_size_t(width), C.c_size_t(perm_width), C.byref(wpq)), "pb_query_words")
+        out = np.empty((self.n_queries, wpq.value), dtype=np.uint32)
+        _chk(self.lib.pb_query_segment(self.h, out.ctypes.data_as(C.c_void_p), C.c_size_t(out.size)), "pb_query_segment")
+        ys = np.empty((width + 2 * perm_width + 8, 4), dtype=np.uint32)
         _chk(self.lib.pb_last_openings(self.h, ys.ctypes.data_as(C.c_void_p), C.c_size_t(ys.size)), "pb_last_openings")
         return out, ys
 
     def last_stage_ms(self):
-        ms = (C.c_float * 9)()
+        ms = (C.c_float * len(STAGES))()
         _chk(self.lib.pb_last_stage_ms(self.h, ms), "pb_last_stage_ms")
-        return dict(zip(["h2d", "lde", "merkle", "quotient", "qlde", "qmerkle", "open", "fri", "total"], [float(x) for x in ms]))
+        return dict(zip(STAGES, [float(x) for x in ms]))
 
     def launch_count(self):
         return int(self.lib.pb_launch_count(self.h))

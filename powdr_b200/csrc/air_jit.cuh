@@ -8,6 +8,7 @@
 #pragma once
 #include <algorithm>
 #include <atomic>
+#include <mutex>
 #include <thread>
 #include <unordered_map>
 #include <cuda.h>
@@ -39,27 +40,31 @@ struct Api {
     CUresult (*LaunchKernel)(CUfunction, unsigned, unsigned, unsigned, unsigned, unsigned, unsigned, unsigned, CUstream, void**, void**) = nullptr;
 };
 
+inline void api_init(Api& a);
 inline Api& api() {
     static Api a;
-    if (a.tried) return a;
+    static std::once_flag once;           // pb_air_compile may be called from several host threads
+    std::call_once(once, [] { api_init(a); });
+    return a;
+}
+inline void api_init(Api& a) {
     a.tried = true;
     void* hn = nullptr;
     for (const char* n : {"libnvrtc.so.12", "libnvrtc.so", "/usr/local/cuda/lib64/libnvrtc.so.12", "/usr/local/cuda/lib64/libnvrtc.so"})
         if ((hn = dlopen(n, RTLD_NOW | RTLD_GLOBAL))) break;
     void* hc = dlopen("libcuda.so.1", RTLD_NOW | RTLD_GLOBAL);
-    if (!hn) return a;
-#define PB_SYM(field, handle, name) *(void**)(&a.field) = dlsym(handle, name); if (!a.field) return a;
+    if (!hn) return;
+#define PB_SYM(field, handle, name) *(void**)(&a.field) = dlsym(handle, name); if (!a.field) return;
     PB_SYM(CreateProgram, hn, "nvrtcCreateProgram") PB_SYM(CompileProgram, hn, "nvrtcCompileProgram")
     PB_SYM(GetCUBINSize, hn, "nvrtcGetCUBINSize") PB_SYM(GetCUBIN, hn, "nvrtcGetCUBIN")
     PB_SYM(GetProgramLogSize, hn, "nvrtcGetProgramLogSize") PB_SYM(GetProgramLog, hn, "nvrtcGetProgramLog")
     PB_SYM(DestroyProgram, hn, "nvrtcDestroyProgram")
     a.nvrtc_ok = true;
-    if (!hc) return a;
+    if (!hc) return;
     PB_SYM(ModuleLoadData, hc, "cuModuleLoadData") PB_SYM(ModuleGetFunction, hc, "cuModuleGetFunction")
     PB_SYM(ModuleUnload, hc, "cuModuleUnload") PB_SYM(LaunchKernel, hc, "cuLaunchKernel")
 #undef PB_SYM
     a.ok = true;
-    return a;
 }
 
 struct Kernel {

@@ -18,6 +18,7 @@
 #include "bb31.cuh"
 #include "deep.cuh"
 #include "fri.cuh"
+#include "logup_jit.cuh"
 #include "ntt.cuh"
 #include "ntt_fast.cuh"
 #include "poseidon2.cuh"
@@ -43,19 +44,18 @@ struct P2Host {   // Montgomery constants for the host-side transcript permutati
 };
 
 void host_external_linear(uint32_t s[16]) {
-    static const uint32_t M4[4][4] = {{2, 3, 1, 1}, {1, 2, 3, 1}, {1, 1, 2, 3}, {3, 1, 1, 2}};
+    // M4 = [[2,3,1,1],[1,2,3,1],[1,1,2,3],[3,1,1,2]] on each 4-chunk as an add chain, then add the column sums
     for (int c = 0; c < 16; c += 4) {
-        uint32_t y[4];
-        for (int i = 0; i < 4; i++) {
-            uint32_t acc = 0;
-            for (int j = 0; j < 4; j++)
-                for (uint32_t k = 0; k < M4[i][j]; k++) acc = bb::add(acc, s[c + j]);
-            y[i] = acc;
-        }
-        for (int i = 0; i < 4; i++) s[c + i] = y[i];
+        const uint32_t x0 = s[c], x1 = s[c + 1], x2 = s[c + 2], x3 = s[c + 3];
+        const uint32_t t01 = bb::add(x0, x1), t23 = bb::add(x2, x3), t0123 = bb::add(t01, t23);
+        const uint32_t t01123 = bb::add(t0123, x1), t01233 = bb::add(t0123, x3);
+        s[c + 3] = bb::add(t01233, bb::dbl(x0));
+        s[c + 1] = bb::add(t01123, bb::dbl(x2));
+        s[c] = bb::add(t01123, t01);
+        s[c + 2] = bb::add(t01233, t23);
     }
-    uint32_t q[4] = {0, 0, 0, 0};
-    for (int i = 0; i < 16; i++) q[i & 3] = bb::add(q[i & 3], s[i]);
+    uint32_t q[4];
+    for (int i = 0; i < 4; i++) q[i] = bb::add(bb::add(s[i], s[4 + i]), bb::add(s[8 + i], s[12 + i]));
     for (int i = 0; i < 16; i++) s[i] = bb::add(s[i], q[i & 3]);
 }
 inline uint32_t host_sbox(uint32_t x) {
@@ -154,6 +154,13 @@ struct pb_air {
     size_t n_code = 0, n_pool = 0;
     airjit::Kernel jit;                 // NVRTC-compiled straight-line evaluator of this AIR
     bool jit_ok = false;
+    // LogUp / bus interactions (pb_air_set_interactions): program, generated kernels, per-proof constant buffers
+    bool has_lu = false;
+    logup::Program lu;
+    logup::Kernels lujit;
+    uint4* d_kc = nullptr;              // [n_ints]   alpha_lu + beta^k (bus+1) + literal arguments
+    uint4* d_bt = nullptr;              // [max_args + 1] beta powers
+    uint4* d_apl = nullptr;             // [n_chunks] alpha^(n_chunks + 2 - c)
 };
 
 struct pb_ctx {
@@ -174,21 +181,23 @@ struct pb_ctx {
     DevBuf<uint32_t> ws_layers_q, ws_layers_open, ws_fri_words, ws_fri_trees, ws_qidx, ws_qout;
     DevBuf<uint32_t> ws_shard_send, ws_shard_recv, ws_shard_coef, ws_gather, ws_gather2;   // multi-GPU segment (shard_api.inl)
     DevBuf<uint32_t> ws_qraw;             // running constraint fold between the chunks of a JIT-compiled AIR, [4][rows]
+    DevBuf<uint32_t> ws_perm, ws_perm_lde, ws_layers_p, ws_rowsum, ws_scan_tot, ws_lu_raw, ws_lu_s, ws_pow;   // LogUp phase + PoW
+    uint32_t n_queries = 100, pow_bits = 16;
     // what pb_query_segment needs from the last pb_prove_segment (everything stays resident on the device)
     struct {
         bool valid = false;
-        size_t log_n = 0, log_m = 0, width = 0;
+        size_t log_n = 0, log_m = 0, width = 0, perm_width = 0;
         uint32_t n_layers = 0;
         size_t word_off[32] = {0}, tree_off[32] = {0};
         Challenger ch;                       // transcript state after the FRI commit phase
-        std::vector<uint32_t> ys;            // opened values, Montgomery, [(width + 8)][4]
+        std::vector<uint32_t> ys;            // opened values, Montgomery, [(width + 2 perm_width + 8)][4]
     } seg;
     cudaStream_t copy_stream = nullptr;   // H2D chunks of the host-input pipeline
     cudaStream_t lde_streams[8] = {nullptr};   // PB_LDE_STREAMS experiment
     cudaEvent_t lde_join[8] = {nullptr}, lde_fork = nullptr;
     cudaEvent_t ev_copy[2] = {nullptr}, ev_free[2] = {nullptr};
-    cudaEvent_t ev[10] = {nullptr};
-    float stage_ms[9] = {0};               // h2d, lde, merkle, quotient, qlde, qmerkle, open(+deep), fri, total
+    cudaEvent_t ev[16] = {nullptr};
+    float stage_ms[PB_N_STAGES] = {0};     // h2d, lde, merkle, logup_gen, logup_commit, quotient, qlde, qmerkle, open(+deep), fri, pow, total
     // live timing of the dominant kernel (Poseidon2 leaf hashing over column-major matrices): event pairs on the stream
     static constexpr int KPROF = 16;
     cudaEvent_t kp_a[KPROF] = {nullptr}, kp_b[KPROF] = {nullptr};
@@ -335,19 +344,23 @@ int pb_ctx_create(pb_ctx_t** out, int device, void* cuda_stream) {
     pb_ctx* ctx = new pb_ctx();
     ctx->device = device;
     ctx->stream = (cudaStream_t)cuda_stream;
-    for (auto& e : ctx->ev) CK(cudaEventCreate(&e));
-    CK(cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking));
-    for (int i = 0; i < 2; i++) {
-        CK(cudaEventCreateWithFlags(&ctx->ev_copy[i], cudaEventDisableTiming));
-        CK(cudaEventCreateWithFlags(&ctx->ev_free[i], cudaEventDisableTiming));
-    }
-    for (int i = 0; i < pb_ctx::KPROF; i++) { CK(cudaEventCreate(&ctx->kp_a[i])); CK(cudaEventCreate(&ctx->kp_b[i])); }
-    CK(cudaFuncSetAttribute(ntt::strided_pass_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 4 << ntt::LOG_TILE_MAX));
-    CK(cudaFuncSetAttribute(ntt::strided_pass_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 4 << ntt::LOG_TILE_MAX));
-    CK(cudaFuncSetAttribute(ntt::transposed_pass_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 4 << ntt::LOG_TILE_MAX));
-    CK(cudaFuncSetAttribute(ntt::transposed_pass_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 4 << ntt::LOG_TILE_MAX));
-    int rc = upload_p2(ctx, PB_P2_RC_EXT, PB_P2_RC_INT, PB_P2_DIAG_M1);
-    if (rc) { delete ctx; return rc; }
+    // any failure below releases what was created so far (pb_ctx_destroy tolerates a half-built context)
+    auto init = [&]() -> int {
+        for (auto& e : ctx->ev) CK(cudaEventCreate(&e));
+        CK(cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking));
+        for (int i = 0; i < 2; i++) {
+            CK(cudaEventCreateWithFlags(&ctx->ev_copy[i], cudaEventDisableTiming));
+            CK(cudaEventCreateWithFlags(&ctx->ev_free[i], cudaEventDisableTiming));
+        }
+        for (int i = 0; i < pb_ctx::KPROF; i++) { CK(cudaEventCreate(&ctx->kp_a[i])); CK(cudaEventCreate(&ctx->kp_b[i])); }
+        CK(cudaFuncSetAttribute(ntt::strided_pass_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 4 << ntt::LOG_TILE_MAX));
+        CK(cudaFuncSetAttribute(ntt::strided_pass_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 4 << ntt::LOG_TILE_MAX));
+        CK(cudaFuncSetAttribute(ntt::transposed_pass_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 4 << ntt::LOG_TILE_MAX));
+        CK(cudaFuncSetAttribute(ntt::transposed_pass_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 4 << ntt::LOG_TILE_MAX));
+        return upload_p2(ctx, PB_P2_RC_EXT, PB_P2_RC_INT, PB_P2_DIAG_M1);
+    };
+    const int rc = init();
+    if (rc) { pb_ctx_destroy(ctx); return rc; }
     *out = ctx;
     return 0;
 }
@@ -363,6 +376,8 @@ int pb_ctx_destroy(pb_ctx_t* ctx) {
     ctx->ws_ys.release(); ctx->ws_w.release(); ctx->ws_part.release(); ctx->ws_gp.release(); ctx->coltab2.release();
     ctx->ws_layers_q.release(); ctx->ws_layers_open.release(); ctx->ws_fri_words.release(); ctx->ws_fri_trees.release();
     ctx->ws_qidx.release(); ctx->ws_qout.release();
+    ctx->ws_perm.release(); ctx->ws_perm_lde.release(); ctx->ws_layers_p.release(); ctx->ws_rowsum.release(); ctx->ws_scan_tot.release();
+    ctx->ws_lu_raw.release(); ctx->ws_lu_s.release(); ctx->ws_pow.release();
     ctx->ws_qraw.release(); ctx->ws_shard_send.release(); ctx->ws_shard_recv.release(); ctx->ws_shard_coef.release(); ctx->ws_gather.release(); ctx->ws_gather2.release();
     ctx->ws_qnat.release(); ctx->ws_qlde.release(); ctx->ws_f0.release(); ctx->ws_f1.release(); ctx->ws_state.release();
     if (ctx->copy_stream) cudaStreamDestroy(ctx->copy_stream);
@@ -377,6 +392,9 @@ int pb_ctx_synchronize(pb_ctx_t* ctx) { CK(cudaStreamSynchronize(ctx->stream)); 
 
 int pb_ctx_set_poseidon2(pb_ctx_t* ctx, const uint32_t rc_ext[8][16], const uint32_t rc_int[13], const uint32_t diag_m1[16]) {
     if (!ctx || !rc_ext || !rc_int || !diag_m1) return PB_ERR_INVALID_ARG;
+    // NOTE: the device-side constants are one __constant__ symbol per process and GPU: every context on this GPU hashes with
+    // the last instantiation set (documented in include/powdr_b200.h); the host-side transcript constants are per context.
+    CK(cudaSetDevice(ctx->device));
     return upload_p2(ctx, rc_ext, rc_int, diag_m1);
 }
 
@@ -650,15 +668,19 @@ int pb_air_is_jit(const pb_air_t* a) { return a && a->jit_ok ? 1 : 0; }
 int pb_air_free(pb_air_t* a) {
     if (!a) return 0;
     if (a->jit_ok) airjit::destroy(a->jit);
+    if (a->has_lu) logup::destroy(a->lujit);
+    cudaFree(a->d_kc); cudaFree(a->d_bt); cudaFree(a->d_apl);
     cudaFree(a->d_code); cudaFree(a->d_spans); cudaFree(a->d_pool); cudaFree(a->d_alpha_pows);
     delete a;
     return 0;
 }
 
-static int upload_alpha_pows(pb_ctx* ctx, const pb_air* a, bb::E4 alpha) {
+static int upload_alpha_pows(pb_ctx* ctx, const pb_air* a, bb::E4 alpha, size_t extra = 0) {
+    // alpha_pows[k] = alpha^(C-1-k+extra): `extra` = number of constraints folded after the AIR's own (the LogUp ones)
     const size_t C = a->n_constraints;
     std::vector<uint32_t> ap(4 * std::max<size_t>(1, C));
     bb::E4 cur = {{bb::R1, 0, 0, 0}};
+    for (size_t e = 0; e < extra; e++) cur = bb::e4_mul(cur, alpha);
     for (size_t k = C; k-- > 0;) {          // alpha_pows[k] = alpha^(C-1-k)
         memcpy(&ap[4 * k], cur.c, 16);
         cur = bb::e4_mul(cur, alpha);
@@ -689,11 +711,16 @@ int pb_quotient(pb_ctx_t* ctx, const pb_air_t* a, const uint32_t* d_lde, size_t 
     return 0;
 }
 
+static int constraint_fold_m(pb_ctx* ctx, const pb_air* a, const uint32_t* d_mat, size_t height, bb::E4 alpha_m, size_t extra, uint32_t* d_out);
 int pb_constraint_fold(pb_ctx_t* ctx, const pb_air_t* a, const uint32_t* d_mat, size_t height, const uint32_t alpha[4], uint32_t* d_out) {
     if (!ctx || !a || !d_mat || !alpha || !d_out) return PB_ERR_INVALID_ARG;
     if (!height) return 0;
-    int rc = upload_alpha_pows(ctx, a, h_e4_from_canon(alpha));
+    return constraint_fold_m(ctx, a, d_mat, height, h_e4_from_canon(alpha), 0, d_out);
+}
+static int constraint_fold_m(pb_ctx* ctx, const pb_air* a, const uint32_t* d_mat, size_t height, bb::E4 alpha_m, size_t extra, uint32_t* d_out) {
+    int rc = upload_alpha_pows(ctx, a, alpha_m, extra);
     if (rc) return rc;
+    if (a->n_constraints == 0) { CK(cudaMemsetAsync(d_out, 0, 16 * height, ctx->stream)); return 0; }
     if (a->jit_ok) {
         if (a->jit.fns.size() > 1) { rc = ctx->ws_qraw.ensure(4 * height); if (rc) return rc; }
         rc = airjit::launch(a->jit, ctx->stream, d_mat, height, 0, a->d_alpha_pows, 0u, 0u, d_out, 0, ctx->ws_qraw.p);
@@ -818,47 +845,59 @@ static int eval_at_point_m(pb_ctx* ctx, const uint32_t* d_mat, size_t log_n, siz
     return 0;
 }
 
-// reduced opening over shift*H' (bit-reversed rows) of the columns in `cols`; ys_m: host, [n_cols][4] Montgomery
-static int deep_quotient_m(pb_ctx* ctx, const std::vector<const uint32_t*>& cols, size_t log_m, uint32_t shift_m, bb::E4 zeta_m,
-                           bb::E4 gamma_m, const uint32_t* ys_m, uint32_t* d_out, size_t row0 = 0, size_t n_rows = 0) {
-    // rows [row0, row0 + n_rows) of the domain only (n_rows = 0: all of it); cols[] then point at that row block
+// reduced opening over shift*H' (bit-reversed rows).  `cols[j]` is opened at point zs[grp[j]]; its gamma exponent is j (the order
+// in which the opened values are observed).  ys_m: host, [n_cols][4] Montgomery.  One kernel launch per point (the later ones
+// accumulate into d_out).  rows [row0, row0 + n_rows) of the domain only when n_rows != 0 (cols[] then point at that row block).
+static int deep_quotient_groups_m(pb_ctx* ctx, const std::vector<const uint32_t*>& cols, const std::vector<uint32_t>& grp, const std::vector<bb::E4>& zs,
+                                  size_t log_m, uint32_t shift_m, bb::E4 gamma_m, const uint32_t* ys_m, uint32_t* d_out, size_t row0 = 0, size_t n_rows = 0) {
     const size_t n_cols = cols.size(), M = n_rows ? n_rows : (size_t)1 << log_m;
-    if (n_cols == 0) return PB_ERR_INVALID_ARG;
+    if (n_cols == 0 || grp.size() != n_cols) return PB_ERR_INVALID_ARG;
     std::vector<uint4> gs(n_cols);
-    bb::E4 cur = {{bb::R1, 0u, 0u, 0u}}, ysum = {{0u, 0u, 0u, 0u}};
+    std::vector<bb::E4> ysum(zs.size(), bb::E4{{0u, 0u, 0u, 0u}});
+    bb::E4 cur = {{bb::R1, 0u, 0u, 0u}};
     for (size_t j = 0; j < n_cols; j++) {
         uint32_t c[4];
         for (int l = 0; l < 4; l++) c[l] = h_from_m(cur.c[l]);
         gs[j] = make_uint4(c[0], c[1], c[2], c[3]);
         bb::E4 y;
         memcpy(y.c, ys_m + 4 * j, 16);
-        ysum = bb::e4_add(ysum, bb::e4_mul(cur, y));
+        ysum[grp[j]] = bb::e4_add(ysum[grp[j]], bb::e4_mul(cur, y));
         cur = bb::e4_mul(cur, gamma_m);
-    }
-    // runs of equally spaced columns
-    deep::DeepSegs segs{};
-    for (size_t j = 0; j < n_cols;) {
-        if (segs.n == deep::DQ_MAX_SEGS) return PB_ERR_UNSUPPORTED;
-        size_t k = j + 1;
-        const ptrdiff_t st = k < n_cols ? cols[k] - cols[j] : 0;
-        while (k < n_cols && st > 0 && cols[k] - cols[k - 1] == st) k++;
-        if (st <= 0) k = j + 1;
-        segs.base[segs.n] = cols[j];
-        segs.stride[segs.n] = st > 0 ? (size_t)st : 0;
-        segs.count[segs.n] = (uint32_t)(k - j);
-        segs.n++;
-        j = k;
     }
     int rc = ctx->ws_gp.ensure(2 * n_cols);          // uint2 elements: one uint4 per column
     if (rc) return rc;
     CK(cudaMemcpyAsync(ctx->ws_gp.p, gs.data(), gs.size() * sizeof(uint4), cudaMemcpyHostToDevice, ctx->stream));
     CK(cudaStreamSynchronize(ctx->stream));           // gs is a host temporary
-    deep::deep_quotient_kernel<<<(unsigned)((M + 255) / 256), 256, 0, ctx->stream>>>(segs, M, (int)log_m, row0, shift_m, h_root_of_unity_m((int)log_m),
-                                                                                    reinterpret_cast<const uint4*>(ctx->ws_gp.p), ysum, zeta_m,
-                                                                                    reinterpret_cast<uint4*>(d_out));
-    LAUNCHED(ctx);
+    for (size_t q = 0; q < zs.size(); q++) {
+        // runs of equally spaced columns of this group with consecutive exponents
+        deep::DeepSegs segs{};
+        for (size_t j = 0; j < n_cols;) {
+            if (grp[j] != q) { j++; continue; }
+            if (segs.n == deep::DQ_MAX_SEGS) return PB_ERR_UNSUPPORTED;
+            size_t k = j + 1;
+            const ptrdiff_t st = (k < n_cols && grp[k] == q) ? cols[k] - cols[j] : 0;
+            while (k < n_cols && grp[k] == q && st > 0 && cols[k] - cols[k - 1] == st) k++;
+            if (st <= 0) k = j + 1;
+            segs.base[segs.n] = cols[j];
+            segs.stride[segs.n] = st > 0 ? (size_t)st : 0;
+            segs.count[segs.n] = (uint32_t)(k - j);
+            segs.gp_off[segs.n] = (uint32_t)j;
+            segs.n++;
+            j = k;
+        }
+        if (segs.n == 0) continue;
+        deep::deep_quotient_kernel<<<(unsigned)((M + 255) / 256), 256, 0, ctx->stream>>>(segs, M, (int)log_m, row0, shift_m, h_root_of_unity_m((int)log_m),
+                                                                                        reinterpret_cast<const uint4*>(ctx->ws_gp.p), ysum[q], zs[q],
+                                                                                        reinterpret_cast<uint4*>(d_out), q > 0 ? 1 : 0);
+        LAUNCHED(ctx);
+    }
     CK(cudaGetLastError());
     return 0;
+}
+static int deep_quotient_m(pb_ctx* ctx, const std::vector<const uint32_t*>& cols, size_t log_m, uint32_t shift_m, bb::E4 zeta_m,
+                           bb::E4 gamma_m, const uint32_t* ys_m, uint32_t* d_out, size_t row0 = 0, size_t n_rows = 0) {
+    return deep_quotient_groups_m(ctx, cols, std::vector<uint32_t>(cols.size(), 0u), std::vector<bb::E4>{zeta_m}, log_m, shift_m, gamma_m, ys_m, d_out,
+                                  row0, n_rows);
 }
 
 int pb_eval_at_point(pb_ctx_t* ctx, const uint32_t* d_mat, size_t log_n, size_t width, uint32_t shift, const uint32_t zeta[4], uint32_t* d_ys) {
@@ -880,248 +919,9 @@ int pb_deep_quotient(pb_ctx_t* ctx, const uint32_t* const* d_mats, const size_t*
     return deep_quotient_m(ctx, cols, log_m, h_to_m(shift), h_e4_from_canon(zeta), h_e4_from_canon(gamma), ys.data(), d_out);
 }
 
-// ---------------------------------------------------------------------------------------------------------------------
-int pb_prove_segment(pb_ctx_t* ctx, const pb_air_t* a, const uint32_t* trace, size_t log_n, size_t width, uint32_t flags,
-                     pb_segment_proof_t* proof) {
-    if (!ctx || !a || !trace || !proof) return PB_ERR_INVALID_ARG;
-    if (log_n < 1 || log_n > 24 || width == 0 || width != a->width) return PB_ERR_INVALID_ARG;
-    const uint32_t log_blowup = 1;
-    const size_t N = (size_t)1 << log_n, M = N << log_blowup;
-    const size_t log_m = log_n + log_blowup;
-    int rc;
-    memset(proof, 0, sizeof *proof);
-    cudaStream_t st = ctx->stream;
-#define RC(x) do { rc = (x); if (rc) return rc; } while (0)
-    CK(cudaEventRecord(ctx->ev[0], st));
-    RC(ctx->ws_lde.ensure(width * M));
-    RC(ctx->ws_layers.ensure(8 * (2 * M)));
-    RC(ctx->ws_q.ensure(8 * N));
-    RC(ctx->ws_qnat.ensure(8 * N));
-    RC(ctx->ws_qlde.ensure(8 * M));
-    RC(ctx->ws_f0.ensure(4 * M));
-    RC(ctx->ws_f1.ensure(4 * (M / 2)));
-    Challenger ch;
-    ch.k = &ctx->p2;
-    uint32_t root_m[8];
-    const uint32_t* d_trace_full = trace;        // device-resident trace (the caller's buffer, or ws_trace in host mode)
+#include "segment.inl"
 
-    if (flags & PB_TRACE_ON_DEVICE) {
-        // main trace commit: LDE then Merkle
-        CK(cudaEventRecord(ctx->ev[1], st));
-        RC(pb_lde_batch(ctx, trace, log_n, width, log_blowup, bb::GEN, ctx->ws_lde.p));
-        CK(cudaEventRecord(ctx->ev[2], st));
-        const uint32_t* mats1[1] = {ctx->ws_lde.p};
-        RC(pb_merkle_commit(ctx, mats1, &width, 1, log_m, ctx->ws_layers.p, nullptr));
-        CK(cudaEventRecord(ctx->ev[3], st));
-    } else {
-        // Host trace: software pipeline over column chunks.  The PCIe copy of chunk k+1 (copy stream, double-buffered
-        // staging) overlaps the LDE and the sponge absorption of chunk k (compute stream); per-row sponge states live in
-        // HBM between chunks.  Stage clocks in this mode: [1]->[2] = copy+LDE+leaf hashing overlapped, [2]->[3] = upper layers.
-        size_t cw = std::max<size_t>(8, ((((size_t)256 << 20) / (4 * N)) / 8) * 8);     // ~256 MB per chunk, multiple of the sponge rate
-        if (const char* e = getenv("PB_PIPE_CHUNK_COLS")) cw = std::max<size_t>(8, ((size_t)atol(e) / 8) * 8);
-        cw = std::min<size_t>(width, cw);
-        // The pipeline is PCIe-bound in steady state (8.5 GB at ~50 GB/s = 171 ms vs 163 ms of LDE + hashing), so what is exposed is
-        // the first copy (nothing to hide behind) and the compute of the last chunk (no copy left to hide it): ramp the chunk
-        // width up from 8 columns at the start and down to 8 at the end.  Every chunk but the last is a multiple of the sponge rate.
-        std::vector<size_t> chunk_c0, chunk_w;
-        {
-            std::vector<size_t> ws;
-            const size_t r8 = width % 8;
-            if (width >= 4 * cw + 112) {
-                for (size_t w0 : {8, 16, 32}) ws.push_back(w0);
-                size_t mid = width - r8 - 112;
-                while (mid > 0) { const size_t w0 = std::min(cw, mid); ws.push_back(w0); mid -= w0; }
-                ws.push_back(32); ws.push_back(16); ws.push_back(8 + r8);
-            } else {
-                for (size_t c0 = 0, wk = 8; c0 < width; c0 += ws.back(), wk = std::min(cw, 2 * wk)) ws.push_back(std::min(wk, width - c0));
-            }
-            size_t c0 = 0;
-            for (size_t w0 : ws) { chunk_c0.push_back(c0); chunk_w.push_back(w0); c0 += w0; }
-        }
-        const size_t n_chunks = chunk_w.size();
-        RC(ctx->ws_trace.ensure(width * N));          // whole trace stays resident: it is read again for the openings at zeta
-        d_trace_full = ctx->ws_trace.p;
-        RC(ctx->ws_state.ensure(16 * M));
-        std::vector<const uint32_t*> cols(width);
-        for (size_t c = 0; c < width; c++) cols[c] = ctx->ws_lde.p + c * M;
-        RC(ctx->coltab.ensure(width));
-        CK(cudaMemcpyAsync(ctx->coltab.p, cols.data(), width * sizeof(void*), cudaMemcpyHostToDevice, st));
-        CK(cudaEventRecord(ctx->ev[1], st));
-        CK(cudaEventRecord(ctx->ev_free[0], st));          // orders the first copies after everything already queued on st
-        CK(cudaEventRecord(ctx->ev_free[1], st));
-        for (size_t k = 0; k < n_chunks; k++) {
-            const int b = (int)(k & 1);
-            const size_t c0 = chunk_c0[k], wk = chunk_w[k];
-            uint32_t* stage = ctx->ws_trace.p + c0 * N;
-            CK(cudaStreamWaitEvent(ctx->copy_stream, ctx->ev_free[b], 0));
-            CK(cudaMemcpyAsync(stage, trace + c0 * N, wk * N * 4, cudaMemcpyHostToDevice, ctx->copy_stream));
-            CK(cudaEventRecord(ctx->ev_copy[b], ctx->copy_stream));
-            CK(cudaStreamWaitEvent(st, ctx->ev_copy[b], 0));
-            RC(pb_lde_batch(ctx, stage, log_n, wk, log_blowup, bb::GEN, ctx->ws_lde.p + c0 * M));
-            CK(cudaEventRecord(ctx->ev_free[b], st));
-            p2::leaf_absorb_cols_kernel<<<(unsigned)((M + p2::LEAF_THREADS - 1) / p2::LEAF_THREADS), p2::LEAF_THREADS, 0, st>>>(ctx->coltab.p + c0, (uint32_t)wk, M, ctx->ws_state.p,
-                                                                                    ctx->ws_layers.p, k == 0, k + 1 == n_chunks);
-            LAUNCHED(ctx);
-        }
-        CK(cudaEventRecord(ctx->ev[2], st));
-        RC(merkle_upper(ctx, ctx->ws_layers.p, log_m));
-        CK(cudaEventRecord(ctx->ev[3], st));
-    }
-    RC(read_root(ctx, ctx->ws_layers.p, log_m, root_m));
-    for (int i = 0; i < 8; i++) proof->trace_root[i] = h_from_m(root_m[i]);
-    ch.observe(root_m, 8);
-    bb::E4 alpha = ch.sample_ext();
-    for (int i = 0; i < 4; i++) proof->alpha[i] = h_from_m(alpha.c[i]);
-
-    // quotient
-    RC(pb_quotient(ctx, a, ctx->ws_lde.p, log_n, log_blowup, bb::GEN, proof->alpha, ctx->ws_q.p));
-    CK(cudaEventRecord(ctx->ev[4], st));
-
-    // quotient commit: chunk b = evals over g*w_{2N}^b*H (bit-reversed) -> natural -> LDE with shift g/s_b = w_{2N}^-b
-    {
-        const size_t tot = 8 * N;
-        ntt::bitrev_rows_kernel<<<(unsigned)((tot + 255) / 256), 256, 0, st>>>(ctx->ws_q.p, ctx->ws_qnat.p, (int)log_n, 8);
-        LAUNCHED(ctx);
-        const uint32_t w2n_inv = h_from_m(bb::inv(h_root_of_unity_m((int)log_n + 1)));
-        RC(pb_lde_batch(ctx, ctx->ws_qnat.p, log_n, 4, log_blowup, 1u, ctx->ws_qlde.p));
-        RC(pb_lde_batch(ctx, ctx->ws_qnat.p + 4 * N, log_n, 4, log_blowup, w2n_inv, ctx->ws_qlde.p + 4 * M));
-    }
-    CK(cudaEventRecord(ctx->ev[5], st));
-    const uint32_t* mats2[2] = {ctx->ws_qlde.p, ctx->ws_qlde.p + 4 * M};
-    const size_t w2[2] = {4, 4};
-    RC(ctx->ws_layers_q.ensure(8 * (2 * M)));
-    RC(pb_merkle_commit(ctx, mats2, w2, 2, log_m, ctx->ws_layers_q.p, nullptr));
-    CK(cudaEventRecord(ctx->ev[6], st));
-    RC(read_root(ctx, ctx->ws_layers_q.p, log_m, root_m));
-    for (int i = 0; i < 8; i++) proof->quotient_root[i] = h_from_m(root_m[i]);
-    ch.observe(root_m, 8);
-    const bb::E4 zeta = ch.sample_ext();
-    for (int i = 0; i < 4; i++) proof->zeta[i] = h_from_m(zeta.c[i]);
-
-    // openings at zeta: trace columns over H, quotient chunk b over g*w_{2N}^b*H; the opened values are committed as rows of 8
-    // (zero padded to a power of two) and that root is observed
-    const size_t n_open = width + 8;
-    size_t open_rows = 1, log_open_rows = 0;
-    while (open_rows * 8 < 4 * n_open) { open_rows <<= 1; log_open_rows++; }
-    RC(ctx->ws_ys.ensure(8 * open_rows));
-    CK(cudaMemsetAsync(ctx->ws_ys.p, 0, 32 * open_rows, st));
-    {
-        const uint32_t g_c = bb::GEN, gw_c = h_from_m(bb::mul(h_to_m(bb::GEN), h_root_of_unity_m((int)log_n + 1)));
-        RC(eval_at_point_m(ctx, d_trace_full, log_n, width, h_to_m(1u), zeta, ctx->ws_ys.p));
-        RC(eval_at_point_m(ctx, ctx->ws_qnat.p, log_n, 4, h_to_m(g_c), zeta, ctx->ws_ys.p + 4 * width));
-        RC(eval_at_point_m(ctx, ctx->ws_qnat.p + 4 * N, log_n, 4, h_to_m(gw_c), zeta, ctx->ws_ys.p + 4 * (width + 4)));
-    }
-    RC(ctx->ws_layers_open.ensure(8 * (2 * open_rows)));
-    RC(pb_merkle_commit_rows8(ctx, ctx->ws_ys.p, log_open_rows, ctx->ws_layers_open.p, nullptr));
-    std::vector<uint32_t>& ys_h = ctx->seg.ys;
-    ys_h.assign(4 * n_open, 0u);
-    CK(cudaMemcpyAsync(ys_h.data(), ctx->ws_ys.p, 16 * n_open, cudaMemcpyDeviceToHost, st));
-    RC(read_root(ctx, ctx->ws_layers_open.p, log_open_rows, root_m));
-    for (int i = 0; i < 8; i++) proof->openings_root[i] = h_from_m(root_m[i]);
-    ch.observe(root_m, 8);
-    const bb::E4 gamma = ch.sample_ext();
-    for (int i = 0; i < 4; i++) proof->gamma[i] = h_from_m(gamma.c[i]);
-
-    // FRI commit phase on the reduced opening ro(x) = sum_j gamma^j (f_j(x) - f_j(zeta)) / (x - zeta) over g*H'
-    {
-        std::vector<const uint32_t*> cols(n_open);
-        for (size_t c = 0; c < width; c++) cols[c] = ctx->ws_lde.p + c * M;
-        for (size_t c = 0; c < 8; c++) cols[width + c] = ctx->ws_qlde.p + c * M;
-        // every FRI codeword and every layer tree stays resident (back to back) for the query phase
-        RC(ctx->ws_fri_words.ensure(8 * M + 64));
-        RC(ctx->ws_fri_trees.ensure(8 * (2 * M)));
-        RC(deep_quotient_m(ctx, cols, log_m, h_to_m(bb::GEN), zeta, gamma, ys_h.data(), ctx->ws_fri_words.p));
-    }
-    CK(cudaEventRecord(ctx->ev[8], st));
-    uint32_t* f = ctx->ws_fri_words.p;
-    size_t log_len = log_m, word_off = 0, tree_off = 0;
-    uint32_t shift_m = h_to_m(bb::GEN);
-    uint32_t layer = 0;
-    while (log_len > log_blowup) {
-        uint32_t* tree = ctx->ws_fri_trees.p + tree_off;
-        ctx->seg.word_off[layer] = word_off;
-        ctx->seg.tree_off[layer] = tree_off;
-        RC(pb_merkle_commit_rows8(ctx, f, log_len - 1, tree, nullptr));
-        RC(read_root(ctx, tree, log_len - 1, root_m));
-        for (int i = 0; i < 8; i++) proof->fri_roots[layer][i] = h_from_m(root_m[i]);
-        ch.observe(root_m, 8);
-        bb::E4 beta = ch.sample_ext();
-        for (int i = 0; i < 4; i++) proof->fri_betas[layer][i] = h_from_m(beta.c[i]);
-        uint32_t* g = f + ((size_t)4 << log_len);
-        RC(fri_fold_m(ctx, f, log_len, shift_m, beta, g));
-        word_off += (size_t)4 << log_len;
-        tree_off += 8 * (((size_t)2 << (log_len - 1)) - 1);
-        f = g;
-        shift_m = bb::mul(shift_m, shift_m);
-        log_len--;
-        layer++;
-    }
-    ctx->seg.valid = true;
-    ctx->seg.log_n = log_n; ctx->seg.log_m = log_m; ctx->seg.width = width; ctx->seg.n_layers = layer;
-    ctx->seg.ch = ch;
-    proof->n_fri_layers = layer;
-    proof->final_len = 1u << log_len;
-    uint32_t fin[8 * 4];
-    CK(cudaMemcpyAsync(fin, f, 16 * proof->final_len, cudaMemcpyDeviceToHost, st));
-    CK(cudaEventRecord(ctx->ev[7], st));
-    CK(cudaStreamSynchronize(st));
-    for (uint32_t i = 0; i < proof->final_len; i++)
-        for (int l = 0; l < 4; l++) proof->final_poly[i][l] = h_from_m(fin[4 * i + l]);
-    for (int i = 0; i < 6; i++) cudaEventElapsedTime(&ctx->stage_ms[i], ctx->ev[i], ctx->ev[i + 1]);
-    cudaEventElapsedTime(&ctx->stage_ms[6], ctx->ev[6], ctx->ev[8]);     // openings + reduced opening
-    cudaEventElapsedTime(&ctx->stage_ms[7], ctx->ev[8], ctx->ev[7]);     // FRI commit phase
-    cudaEventElapsedTime(&ctx->stage_ms[8], ctx->ev[0], ctx->ev[7]);
-#undef RC
-    return 0;
-}
-
-// query phase of the last pb_prove_segment: indices from the transcript (sample_bits(log_m) each), openings gathered on the device
-static size_t query_words(size_t log_n, size_t width) {
-    const size_t log_m = log_n + 1, layers = log_n;      // log_blowup 1, final_poly_len 1
-    size_t w = 1 + width + 8 * log_m + 8 + 8 * log_m;
-    for (size_t i = 0; i < layers; i++) w += 8 + 8 * (log_m - 1 - i);
-    return w;
-}
-
-int pb_query_words(size_t log_n, size_t width, size_t* words_per_query) {
-    if (!words_per_query || log_n < 1 || log_n > 24) return PB_ERR_INVALID_ARG;
-    *words_per_query = query_words(log_n, width);
-    return 0;
-}
-
-int pb_query_segment(pb_ctx_t* ctx, size_t n_queries, uint32_t* h_out, size_t out_capacity_words) {
-    if (!ctx || !h_out || !n_queries) return PB_ERR_INVALID_ARG;
-    if (!ctx->seg.valid) return PB_ERR_INVALID_ARG;
-    const size_t wpq = query_words(ctx->seg.log_n, ctx->seg.width);
-    if (out_capacity_words < wpq * n_queries) return PB_ERR_INVALID_ARG;
-    int rc;
-    std::vector<uint32_t> idx(n_queries);
-    Challenger ch = ctx->seg.ch;
-    for (size_t q = 0; q < n_queries; q++) idx[q] = h_from_m(ch.sample()) & (uint32_t)(((size_t)1 << ctx->seg.log_m) - 1);
-    if ((rc = ctx->ws_qidx.ensure(n_queries))) return rc;
-    if ((rc = ctx->ws_qout.ensure(wpq * n_queries))) return rc;
-    CK(cudaMemcpyAsync(ctx->ws_qidx.p, idx.data(), 4 * n_queries, cudaMemcpyHostToDevice, ctx->stream));
-    fri::QueryDesc d;
-    d.lde = ctx->ws_lde.p; d.qlde = ctx->ws_qlde.p; d.tree_t = ctx->ws_layers.p; d.tree_q = ctx->ws_layers_q.p;
-    d.fri_words = ctx->ws_fri_words.p; d.fri_trees = ctx->ws_fri_trees.p;
-    d.m = (size_t)1 << ctx->seg.log_m; d.width = (uint32_t)ctx->seg.width; d.log_m = (int)ctx->seg.log_m; d.n_layers = (int)ctx->seg.n_layers;
-    for (int i = 0; i < 32; i++) { d.word_off[i] = ctx->seg.word_off[i]; d.tree_off[i] = ctx->seg.tree_off[i]; }
-    fri::gather_queries_kernel<<<(unsigned)n_queries, 256, 0, ctx->stream>>>(d, ctx->ws_qidx.p, ctx->ws_qout.p, wpq);
-    LAUNCHED(ctx);
-    CK(cudaGetLastError());
-    CK(cudaMemcpyAsync(h_out, ctx->ws_qout.p, 4 * wpq * n_queries, cudaMemcpyDeviceToHost, ctx->stream));
-    CK(cudaStreamSynchronize(ctx->stream));
-    return 0;
-}
-
-// opened values of the last pb_prove_segment, canonical, [(width + 8)][4]
-int pb_last_openings(pb_ctx_t* ctx, uint32_t* h_ys, size_t capacity_words) {
-    if (!ctx || !h_ys || !ctx->seg.valid || capacity_words < ctx->seg.ys.size()) return PB_ERR_INVALID_ARG;
-    for (size_t i = 0; i < ctx->seg.ys.size(); i++) h_ys[i] = h_from_m(ctx->seg.ys[i]);
-    return 0;
-}
-
-int pb_last_stage_ms(pb_ctx_t* ctx, float ms[9]) {
+int pb_last_stage_ms(pb_ctx_t* ctx, float ms[PB_N_STAGES]) {
     if (!ctx || !ms) return PB_ERR_INVALID_ARG;
     memcpy(ms, ctx->stage_ms, sizeof ctx->stage_ms);
     return 0;

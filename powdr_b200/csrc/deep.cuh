@@ -160,6 +160,7 @@ struct DeepSegs {
     const uint32_t* base[DQ_MAX_SEGS];     // first column of the run, already offset to the row block
     size_t stride[DQ_MAX_SEGS];            // words between consecutive columns
     uint32_t count[DQ_MAX_SEGS];
+    uint32_t gp_off[DQ_MAX_SEGS];          // gamma exponent of the run's first column
     int n;
 };
 
@@ -169,14 +170,14 @@ __device__ __forceinline__ void dq_mac(Acc96 (&acc)[4], uint32_t f, const uint4 
 
 __global__ void __launch_bounds__(256) deep_quotient_kernel(DeepSegs segs, size_t m, int log_m, size_t row0, uint32_t shift_m, uint32_t omega_m,
                                                             const uint4* __restrict__ gpow, bb::E4 ysum, bb::E4 zeta,
-                                                            uint4* __restrict__ out) {
+                                                            uint4* __restrict__ out, int accumulate) {
     __shared__ uint4 sg[DQ_CHUNK];
     const size_t r = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     const bool live = r < m;
     const size_t rr = live ? r : m - 1;           // dead threads of the last CTA still take part in the staging barriers
     Acc96 acc[4] = {{0u, 0u, 0u}, {0u, 0u, 0u}, {0u, 0u, 0u}, {0u, 0u, 0u}};
-    size_t jglob = 0;
     for (int sgi = 0; sgi < segs.n; sgi++) {
+        const size_t jglob = segs.gp_off[sgi];
         const size_t stride = segs.stride[sgi];
         const uint32_t count = segs.count[sgi];
         for (uint32_t c0 = 0; c0 < count; c0 += DQ_CHUNK) {
@@ -204,7 +205,6 @@ __global__ void __launch_bounds__(256) deep_quotient_kernel(DeepSegs segs, size_
             }
             for (; j < nc; j++) dq_mac(acc, __ldg(p + (size_t)j * stride), sg[j]);
         }
-        jglob += count;
     }
     if (!live) return;
     bb::E4 a;
@@ -214,7 +214,11 @@ __global__ void __launch_bounds__(256) deep_quotient_kernel(DeepSegs segs, size_
     }
     const uint32_t x = bb::mul(shift_m, bb::pow(omega_m, (uint64_t)(__brev((uint32_t)(row0 + r)) >> (32 - log_m))));
     bb::E4 d = {{bb::sub(x, zeta.c[0]), bb::neg(zeta.c[1]), bb::neg(zeta.c[2]), bb::neg(zeta.c[3])}};
-    const bb::E4 v = bb::e4_mul(a, e4_inv(d));
+    bb::E4 v = bb::e4_mul(a, e4_inv(d));
+    if (accumulate) {
+        const uint4 o = out[r];
+        v.c[0] = bb::add(v.c[0], o.x); v.c[1] = bb::add(v.c[1], o.y); v.c[2] = bb::add(v.c[2], o.z); v.c[3] = bb::add(v.c[3], o.w);
+    }
     out[r] = make_uint4(v.c[0], v.c[1], v.c[2], v.c[3]);
 }
 

@@ -36,7 +36,7 @@ __global__ void __launch_bounds__(256) combine_chunks_kernel(const uint32_t* __r
 
 // ---------------- query phase: gather the openings a verifier needs for each sampled index ----------------
 // One CTA per query.  Output (canonical words) per query:
-//   [ r | trace row (W) | trace path (log_m x 8) | quotient row (8) | quotient path (log_m x 8) |
+//   [ r | trace row (W) | trace path (log_m x 8) | perm row (Wp) | perm path (log_m x 8)  (when Wp > 0) | quotient row (8) | quotient path (log_m x 8) |
 //     per FRI layer i: pair row (8), path ((log_m-1-i) x 8) ]
 // Merkle trees are node-major with level k at node offset 2^(h+1) - 2^(h-k+1); the sibling of leaf idx at level k is (idx>>k)^1.
 namespace fri {
@@ -46,6 +46,9 @@ struct QueryDesc {
     const uint32_t* qlde;       // quotient chunk LDEs, column-major [8][M]
     const uint32_t* tree_t;     // digest layers of the trace commitment
     const uint32_t* tree_q;     // digest layers of the quotient commitment
+    const uint32_t* plde;       // LogUp permutation-trace LDE, column-major [perm_width][M] (unused when perm_width = 0)
+    const uint32_t* tree_p;     // digest layers of the permutation-trace commitment
+    uint32_t perm_width;
     const uint32_t* fri_words;  // all FRI codewords back to back (layer i at word_off[i])
     const uint32_t* fri_trees;  // all FRI layer trees back to back (layer i at tree_off[i], in words)
     size_t m;
@@ -74,6 +77,12 @@ __global__ void __launch_bounds__(256) gather_queries_kernel(QueryDesc d, const 
     o += d.width;
     copy_path(d.tree_t, d.log_m, r, o);
     o += 8 * d.log_m;
+    if (d.perm_width) {
+        for (uint32_t c = threadIdx.x; c < d.perm_width; c += blockDim.x) o[c] = bb::from_monty(d.plde[(size_t)c * d.m + r]);
+        o += d.perm_width;
+        copy_path(d.tree_p, d.log_m, r, o);
+        o += 8 * d.log_m;
+    }
     for (uint32_t c = threadIdx.x; c < 8; c += blockDim.x) o[c] = bb::from_monty(d.qlde[(size_t)c * d.m + r]);
     o += 8;
     copy_path(d.tree_q, d.log_m, r, o);

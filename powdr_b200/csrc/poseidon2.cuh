@@ -281,6 +281,25 @@ __global__ void __launch_bounds__(256) compress_block_kernel(uint4* level, size_
     }
 }
 
+// proof-of-work grinding (Plonky3 `grind`): candidate w = base + thread; the challenger's duplex state with the pending inputs
+// already written in is `st`, the witness goes to slot `pos`, ONE permutation, the sampled word is output slot 7; accept when
+// its canonical value has the `mask` bits clear.  found <- min accepted witness (atomicMin), 0xffffffff when none in this batch.
+struct GrindState { uint32_t s[16]; };
+__global__ void __launch_bounds__(256, 1) grind_kernel(GrindState st, int pos, uint32_t mask, uint32_t base, uint32_t count, uint32_t* found) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= count) return;
+    const uint32_t w = base + i;
+    if (w >= bb::P) return;
+    uint32_t s[16];
+#pragma unroll
+    for (int k = 0; k < 16; k++) s[k] = st.s[k];
+#pragma unroll
+    for (int k = 0; k < 8; k++)
+        if (k == pos) s[k] = bb::to_monty(w);
+    permute(s);
+    if ((bb::from_monty(s[7]) & mask) == 0) atomicMin(found, w);
+}
+
 // single permutation per thread on [n][16] states -- used by tests and the throughput micro-benchmark
 #ifndef PB_V_MINBLOCKS
 #define PB_V_MINBLOCKS 1

@@ -185,6 +185,7 @@ int pb_prove_segment_sharded(pb_ctx_t* ctx, const pb_air_t* a, const uint32_t* t
                              const pb_comm_t* comm, pb_segment_proof_t* proof) {
     if (!ctx || !a || !proof || !comm || !comm->all_gather || !comm->all_to_all) return PB_ERR_INVALID_ARG;
     if (log_n < 1 || log_n > 24 || width == 0 || width != a->width) return PB_ERR_INVALID_ARG;
+    if (a->has_lu) return PB_ERR_UNSUPPORTED;      // the LogUp phase needs whole trace rows: not sharded yet
     ShardGeom s;
     if (!make_shard_geom(log_n, comm->world, &s) || comm->rank < 0 || comm->rank >= comm->world) return PB_ERR_UNSUPPORTED;
     const int G = s.G, rho = comm->rank;
@@ -195,6 +196,8 @@ int pb_prove_segment_sharded(pb_ctx_t* ctx, const pb_air_t* a, const uint32_t* t
     if (w_my && !trace_cols) return PB_ERR_INVALID_ARG;
     int rc;
     memset(proof, 0, sizeof *proof);
+    proof->pow_bits = ctx->pow_bits;
+    proof->n_queries = ctx->n_queries;
     cudaStream_t st = ctx->stream;
     ctx->seg.valid = false;
 #define RC(x) do { rc = (x); if (rc) return rc; } while (0)
@@ -282,11 +285,9 @@ int pb_prove_segment_sharded(pb_ctx_t* ctx, const pb_air_t* a, const uint32_t* t
     const bb::E4 zeta = ch.sample_ext();
     for (int i = 0; i < 4; i++) proof->zeta[i] = h_from_m(zeta.c[i]);
 
-    // ---- openings at zeta: my trace columns, gathered; the 8 quotient columns on every rank ----
+    // ---- openings at zeta: my trace columns, gathered; the 8 quotient columns on every rank; every value observed ----
     const size_t n_open = width + 8;
-    size_t open_rows = 1, log_open_rows = 0;
-    while (open_rows * 8 < 4 * n_open) { open_rows <<= 1; log_open_rows++; }
-    RC(ctx->ws_ys.ensure(std::max(8 * open_rows, 4 * ((size_t)G * per + 8))));
+    RC(ctx->ws_ys.ensure(4 * ((size_t)G * per + 8)));
     RC(ctx->ws_gather2.ensure(4 * per + 4 * (size_t)G * per));
     {
         uint32_t* ys_my = ctx->ws_gather2.p;                    // [per][4]
@@ -294,20 +295,16 @@ int pb_prove_segment_sharded(pb_ctx_t* ctx, const pb_air_t* a, const uint32_t* t
         CK(cudaMemsetAsync(ys_my, 0, 16 * per, st));
         if (w_my) RC(eval_at_point_m(ctx, d_my, log_n, w_my, h_to_m(1u), zeta, ys_my));
         COMM(all_gather, ys_my, ys_all, 16 * per);
-        CK(cudaMemsetAsync(ctx->ws_ys.p, 0, 32 * open_rows, st));
         CK(cudaMemcpyAsync(ctx->ws_ys.p, ys_all, 16 * width, cudaMemcpyDeviceToDevice, st));
         const uint32_t g_c = bb::GEN, gw_c = h_from_m(bb::mul(h_to_m(bb::GEN), h_root_of_unity_m((int)log_n + 1)));
         RC(eval_at_point_m(ctx, ctx->ws_qnat.p, log_n, 4, h_to_m(g_c), zeta, ctx->ws_ys.p + 4 * width));
         RC(eval_at_point_m(ctx, ctx->ws_qnat.p + 4 * N, log_n, 4, h_to_m(gw_c), zeta, ctx->ws_ys.p + 4 * (width + 4)));
     }
-    RC(ctx->ws_layers_open.ensure(8 * (2 * open_rows)));
-    RC(pb_merkle_commit_rows8(ctx, ctx->ws_ys.p, log_open_rows, ctx->ws_layers_open.p, nullptr));
     std::vector<uint32_t>& ys_h = ctx->seg.ys;
     ys_h.assign(4 * n_open, 0u);
     CK(cudaMemcpyAsync(ys_h.data(), ctx->ws_ys.p, 16 * n_open, cudaMemcpyDeviceToHost, st));
-    RC(read_root(ctx, ctx->ws_layers_open.p, log_open_rows, root_m));
-    for (int i = 0; i < 8; i++) proof->openings_root[i] = h_from_m(root_m[i]);
-    ch.observe(root_m, 8);
+    CK(cudaStreamSynchronize(st));
+    ch.observe(ys_h.data(), (int)(4 * n_open));
     const bb::E4 gamma = ch.sample_ext();
     for (int i = 0; i < 4; i++) proof->gamma[i] = h_from_m(gamma.c[i]);
 
@@ -372,10 +369,24 @@ int pb_prove_segment_sharded(pb_ctx_t* ctx, const pb_air_t* a, const uint32_t* t
     CK(cudaStreamSynchronize(st));
     for (uint32_t i = 0; i < proof->final_len; i++)
         for (int l = 0; l < 4; l++) proof->final_poly[i][l] = h_from_m(fin[4 * i + l]);
-    for (int i = 0; i < 6; i++) cudaEventElapsedTime(&ctx->stage_ms[i], ctx->ev[i], ctx->ev[i + 1]);
-    cudaEventElapsedTime(&ctx->stage_ms[6], ctx->ev[6], ctx->ev[8]);
-    cudaEventElapsedTime(&ctx->stage_ms[7], ctx->ev[8], ctx->ev[7]);
-    cudaEventElapsedTime(&ctx->stage_ms[8], ctx->ev[0], ctx->ev[7]);
+    ch.observe(fin, 4);
+    {   // proof of work: every rank grinds the same transcript state (2^pow_bits permutations: microseconds)
+        uint32_t w = 0;
+        RC(grind(ctx, ch, ctx->pow_bits, &w));
+        proof->pow_witness = w;
+    }
+    CK(cudaEventRecord(ctx->ev[9], st));
+    CK(cudaStreamSynchronize(st));
+    // stage clocks in the layout of pb_last_stage_ms (no LogUp phase here)
+    float t[8];
+    for (int i = 0; i < 6; i++) cudaEventElapsedTime(&t[i], ctx->ev[i], ctx->ev[i + 1]);
+    cudaEventElapsedTime(&t[6], ctx->ev[6], ctx->ev[8]);
+    cudaEventElapsedTime(&t[7], ctx->ev[8], ctx->ev[7]);
+    memset(ctx->stage_ms, 0, sizeof ctx->stage_ms);
+    ctx->stage_ms[0] = t[0]; ctx->stage_ms[1] = t[1]; ctx->stage_ms[2] = t[2]; ctx->stage_ms[5] = t[3]; ctx->stage_ms[6] = t[4];
+    ctx->stage_ms[7] = t[5]; ctx->stage_ms[8] = t[6]; ctx->stage_ms[9] = t[7];
+    cudaEventElapsedTime(&ctx->stage_ms[10], ctx->ev[7], ctx->ev[9]);
+    cudaEventElapsedTime(&ctx->stage_ms[11], ctx->ev[0], ctx->ev[9]);
 #undef COMM
 #undef RC
     return 0;

@@ -25,5 +25,6 @@ def orc():
 def ctx():
     import powdr_b200
     c = powdr_b200.Context(0)
+    c.set_fri_params(8, 4)          # small FRI parameters for the parity tests (oracle wrappers default to the same)
     yield c
     c.close()

@@ -406,9 +406,13 @@ def test_gpu_proof_and_queries_match_oracle_and_verify(ctx, orc, log_n, width, n
     air, bc, spans = _compile(ctx, mach)
     trace = rand_field(np.random.default_rng(83), (mach.width, 1 << log_n))
     d = ctx.to_device(trace)
-    proof = ctx.prove_segment(air, d.ptr, log_n, mach.width, on_device=True)
-    queries, ys = ctx.query_segment(log_n, mach.width, 12)
-    exp_proof, exp_ys, exp_q = orc.prove_segment_q(trace, bc, spans, 12)
+    ctx.set_fri_params(12, 9)
+    try:
+        proof = ctx.prove_segment(air, d.ptr, log_n, mach.width, on_device=True)
+        queries, ys = ctx.query_segment(log_n, mach.width)
+    finally:
+        ctx.set_fri_params(8, 4)
+    exp_proof, exp_ys, exp_q = orc.prove_segment_q(trace, bc, spans, 12, pow_bits=9)
     assert proof == exp_proof and (ys == exp_ys).all() and (queries == exp_q).all()
     assert orc.verify_segment(bc, spans, log_n, mach.width, proof, ys, queries) == 0
 
@@ -426,15 +430,82 @@ def test_gpu_proof_of_a_satisfying_trace_verifies_with_the_constraint_identity(c
     trace = np.stack([b, c, dd])
     dev = ctx.to_device(trace)
     proof = ctx.prove_segment(air, dev.ptr, log_n, 3, on_device=True)
-    queries, ys = ctx.query_segment(log_n, 3, 30)
+    queries, ys = ctx.query_segment(log_n, 3)
     assert orc.verify_segment(bc, spans, log_n, 3, proof, ys, queries, check_constraints=True) == 0
     trace[1, 5] = (int(trace[1, 5]) + 1) % P if b[5] else trace[1, 5]
     trace[2, 9] = (int(trace[2, 9]) + 1) % P
     dev = ctx.to_device(trace)
     proof = ctx.prove_segment(air, dev.ptr, log_n, 3, on_device=True)
-    queries, ys = ctx.query_segment(log_n, 3, 30)
+    queries, ys = ctx.query_segment(log_n, 3)
     assert orc.verify_segment(bc, spans, log_n, 3, proof, ys, queries, check_constraints=False) == 0
-    assert orc.verify_segment(bc, spans, log_n, 3, proof, ys, queries, check_constraints=True) == 12
+    assert orc.verify_segment(bc, spans, log_n, 3, proof, ys, queries, check_constraints=True) == 16
+
+
+# ---------------------------------------------------------------- LogUp / bus-interaction argument
+@pytest.mark.parametrize("log_n,width,n_ints,quad,ncons", [(3, 12, 5, 0, 0), (7, 20, 9, 3, 4), (10, 33, 40, 7, 6), (12, 10, 1, 0, 2)])
+def test_logup_segment_matches_oracle_and_verifies(ctx, orc, log_n, width, n_ints, quad, ncons):
+    """bus interactions attached to the AIR: permutation trace, running sum, LogUp constraints in the quotient, two opening
+    points -- proof, opened values and query openings bit-identical to the oracle's; the independent verifier accepts"""
+    M = _machine()
+    base = M.synthetic_machine(width, ncons, seed=3) if ncons else None
+    mach = M.SymbolicMachine(base.constraints if base else [], M.synthetic_bus(width, n_ints, 10 + log_n, quad))
+    bc, spans = M.compile_constraints(mach)
+    bus = M.compile_bus(mach, 1)
+    air = ctx.air(bc, spans, mach.width, bus)
+    assert air.perm_width > 0
+    rng = np.random.default_rng(log_n)
+    trace = rand_field(rng, (mach.width, 1 << log_n))
+    d = ctx.to_device(trace)
+    proof = ctx.prove_segment(air, d.ptr, log_n, mach.width, on_device=True)
+    queries, ys = ctx.query_segment(log_n, mach.width, air.perm_width)
+    exp_proof, exp_ys, exp_q, _ = orc.prove(trace, bc, spans, bus, n_queries=8, pow_bits=4)
+    assert proof["perm_width"] == air.perm_width == exp_proof["perm_width"]
+    assert proof["cumulative_sum"] == exp_proof["cumulative_sum"] and proof["perm_root"] == exp_proof["perm_root"]
+    assert proof["quotient_root"] == exp_proof["quotient_root"]
+    assert proof == exp_proof and (ys == exp_ys).all() and (queries == exp_q).all()
+    assert orc.verify_segment(bc, spans, log_n, mach.width, proof, ys, queries, check_constraints=(ncons == 0), bus=bus) == 0
+    # host-resident trace takes the pipelined commit, then the same LogUp phase
+    from powdr_b200.capi import R_MOD_P
+    host = ((trace.astype(np.uint64) * np.uint64(R_MOD_P)) % np.uint64(P)).astype(np.uint32)
+    assert ctx.prove_segment(air, host.ctypes.data, log_n, mach.width, on_device=False) == exp_proof
+
+
+def test_logup_at_scale_verifies(ctx, orc):
+    """2^15 rows x 300 interactions (150+ chunks, several JIT groups): too slow for the scalar oracle prover, so the check is
+    the independent verifier (all challenges, proof of work, 8 queries with three Merkle paths each, folds) plus the LogUp
+    identity at zeta, which holds for ANY trace when the AIR has interactions only"""
+    M = _machine()
+    mach = M.SymbolicMachine([], M.synthetic_bus(96, 300, 77, quadratic_every=11))
+    bus = M.compile_bus(mach, 1)
+    air = ctx.air([], [], mach.width, bus)
+    log_n = 15
+    trace = rand_field(np.random.default_rng(15), (mach.width, 1 << log_n))
+    d = ctx.to_device(trace)
+    proof = ctx.prove_segment(air, d.ptr, log_n, mach.width, on_device=True)
+    queries, ys = ctx.query_segment(log_n, mach.width, air.perm_width)
+    assert proof["final_poly"][0] == proof["final_poly"][1]
+    assert orc.verify_segment([], [], log_n, mach.width, proof, ys, queries, check_constraints=True, bus=bus) == 0
+
+
+def test_proof_of_work_default_parameters(orc):
+    """default context parameters (100 queries, 16 PoW bits): the GPU grinding kernel finds the same (smallest) witness as the oracle"""
+    import powdr_b200
+    M = _machine()
+    c2 = powdr_b200.Context(0)
+    try:
+        mach = M.synthetic_machine(9, 3, seed=2)
+        bc, spans = M.compile_constraints(mach)
+        air = c2.air(bc, spans, mach.width)
+        trace = rand_field(np.random.default_rng(16), (mach.width, 1 << 6))
+        d = c2.to_device(trace)
+        proof = c2.prove_segment(air, d.ptr, 6, mach.width, on_device=True)
+        queries, ys = c2.query_segment(6, mach.width)
+        exp, exp_ys, exp_q, _ = orc.prove(trace, bc, spans, None, n_queries=100, pow_bits=16)
+        assert proof["pow_bits"] == 16 and proof["n_queries"] == 100 and proof["pow_witness"] == exp["pow_witness"]
+        assert proof == exp and (queries == exp_q).all()
+        assert orc.verify_segment(bc, spans, 6, mach.width, proof, ys, queries) == 0
+    finally:
+        c2.close()
 
 
 def test_large_preopt_fixture_jit_chunks_and_interpreter_agree_with_oracle(ctx, orc, monkeypatch):
@@ -485,7 +556,7 @@ def test_plain_c_client_produces_the_same_commitments(ctx, orc, tmp_path):
     mach = M.SymbolicMachine([[[A, "*", B], "-", Cc], [[A, "*", [A, "-", 1]], "*", [A, "-", 2]]], [], [])
     assert mach.width == 3
     bc, spans = M.compile_constraints(mach)
-    exp, _ = orc.prove_segment(trace, bc, spans)
+    exp, _ = orc.prove_segment(trace, bc, spans, n_queries=0, pow_bits=0)
     assert [int(x) for x in out["trace_root"]] == exp["trace_root"]
     assert [int(x) for x in out["quotient_root"]] == exp["quotient_root"]
     fin = [int(x) for x in out["fri_layers"][4:]]

@@ -163,6 +163,32 @@ def test_product_never_imports_the_oracle():
                 assert "import oracle" not in txt and "from oracle" not in txt and "oracle/" not in txt.replace("the oracle/", ""), f
 
 
+def test_logup_codegen_compiles_for_sm100a_without_a_device():
+    """host-only check of the LogUp generator (pb_air_logup_compile_only): chunking by the degree rule, generated CUDA C for the
+    permutation-trace and the fold kernels accepted by NVRTC for sm_100a; malformed interaction tables are rejected"""
+    import ctypes as C
+    import numpy as np
+    import powdr_b200
+    from powdr_b200 import machine as M, capi
+    lib = powdr_b200.load_library()
+    mach = M.SymbolicMachine([], M.synthetic_bus(24, 21, 3, quadratic_every=5))
+    ints, isp, ibc = M.compile_bus(mach, 1)
+    ibc = np.array(ibc, dtype=np.uint32)
+    spn = (capi.Span * len(isp))()
+    for i, (o, l) in enumerate(isp):
+        spn[i].off, spn[i].len = o, l
+    di = (capi.DevInteraction * len(ints))()
+    for i, (b, n, o) in enumerate(ints):
+        di[i].bus_id, di[i].num_args, di[i].args_index_off = b, n, o
+    cb, wp = C.c_size_t(), C.c_size_t()
+    args = (ibc.ctypes.data_as(C.c_void_p), C.c_size_t(ibc.size), spn, C.c_size_t(len(isp)), di, C.c_size_t(len(ints)), C.c_uint32(mach.width))
+    assert lib.pb_air_logup_compile_only(*args, C.byref(cb), C.byref(wp)) == 0
+    # 21 interactions, every 5th with a degree-2 argument (own chunk): 4 singles + ceil-pairs of the runs of 4 -> 4 + 4*2 + 1 = 13 chunks
+    assert wp.value == 4 * (13 + 1) and cb.value > 10000
+    di[3].args_index_off = len(isp)              # spans out of range
+    assert lib.pb_air_logup_compile_only(*args, C.byref(cb), C.byref(wp)) == -4
+
+
 def test_chunked_jit_compiles_a_9168_constraint_machine_in_parallel():
     """the real pre-optimisation fixture is 141 k bytecode words: as one NVRTC module that took 11 minutes, as 2 k-word chunks on
     all host threads it must stay a key-generation-time cost (seconds to tens of seconds)"""
@@ -248,4 +274,7 @@ def test_entry_points_reject_null_arguments_before_touching_the_device():
     assert lib.pb_poseidon2_permute(z, z, n0, C.c_int(1)) == INVALID
     first, count = C.c_size_t(), C.c_size_t()
     assert lib.pb_shard_columns(C.c_size_t(10), C.c_int(4), C.c_int(4), C.byref(first), C.byref(count)) == INVALID      # rank out of range
-    assert lib.pb_query_words(C.c_size_t(10), C.c_size_t(3), z) == INVALID
+    assert lib.pb_query_words(C.c_size_t(10), C.c_size_t(3), n0, z) == INVALID
+    assert lib.pb_air_set_interactions(z, z, z, n0, z, n0, z, n0) == INVALID
+    assert lib.pb_allgather_caps(z, z, z, z) == INVALID
+    assert lib.pb_ctx_set_fri_params(z, C.c_uint32(8), C.c_uint32(4)) == INVALID
