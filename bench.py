@@ -1,15 +1,17 @@
 #!/usr/bin/env python3
 """bench.py -- proof-gen seconds for the guest-keccak APC segment shape (2^20 rows x 2022 columns, 187 constraints of
-degree <= 3) on N B200s, through the C ABI of include/powdr_b200.h.
+degree <= 3, 1734 bus interactions: /root/reference/openvm-riscv/src/lib.rs:1377-1386) on N B200s, through the C ABI of
+include/powdr_b200.h.
 
   python bench.py --gpus N --steps K --warmup W                 # native CUDA arm (torchrun launches N ranks for N > 1)
-  python bench.py --impl reference --gpus N --steps K --warmup W  # the CPU restatement on the host cores (rank 0 only)
+  python bench.py --impl reference --gpus N --steps K --warmup W  # the CPU implementation on the host cores (rank 0 only)
 
-One step = one segment per GPU through the whole hot path (LDE -> Poseidon2 Merkle -> quotient -> quotient commit ->
-FRI commit phase).  `value` = device-timed seconds per segment with the trace already resident in HBM (max over ranks,
-divided by the N segments proved concurrently); `e2e` = the same through pb_prove_segment with the trace in pinned HOST
-memory (H2D inside the timed region, proof read back).  Inputs (8.5 GB/segment) exceed the 126 MB L2, so no L2 flush is
-needed between iterations.  torch is plumbing only: device memory, the stream, events and torch.distributed/NCCL.
+One step = one segment per GPU through the whole path: main trace commit (LDE + Poseidon2 Merkle) -> LogUp permutation trace
+(generate, LDE, commit) -> quotient -> quotient commit -> openings at zeta / zeta*w -> FRI commit phase -> proof of work (16 bits)
+-> 100 queries.  `value` = device-timed seconds per segment with the trace already resident in HBM (max over ranks, divided by
+the N segments proved concurrently); `e2e` = the same through pb_prove_segment + pb_query_segment with the trace in pinned
+HOST memory (H2D inside the timed region, proof and query openings read back).  Inputs (8.5 GB/segment) exceed the 126 MB
+L2, so no L2 flush is needed between iterations.  torch is plumbing only: device memory, the stream, events, NCCL.
 """
 import argparse
 import math
@@ -36,7 +38,11 @@ def parse():
     ap.add_argument("--log-n", type=int, default=20)
     ap.add_argument("--width", type=int, default=2022)          # keccak APC: 2022 main columns
     ap.add_argument("--constraints", type=int, default=187)     # ... 187 constraints (openvm-riscv/src/lib.rs:1377-1386)
-    ap.add_argument("--cpu-sample-log-n", type=int, default=15)
+    ap.add_argument("--interactions", type=int, default=1734)   # ... 1734 bus interactions (same test)
+    ap.add_argument("--queries", type=int, default=100)
+    ap.add_argument("--pow-bits", type=int, default=16)
+    ap.add_argument("--cpu-budget-s", type=float, default=150.0, help="wall-clock budget of the CPU arm (full-size runs until it is spent)")
+    ap.add_argument("--cpu-log-n", type=int, default=-1, help="rows of the CPU run (default: the full 2^log_n if host memory allows)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-sharded", action="store_true", help="skip the one-segment-on-all-GPUs (strong scaling) measurement at N > 1")
@@ -47,15 +53,18 @@ def parse():
 
 
 def workload_name(a):
-    return "guest-keccak APC shape: 2^%d rows x %d cols, %d constraints deg<=3, log_blowup 1 (synthetic AIR + uniform trace)" % (
-        a.log_n, a.width, a.constraints)
+    return ("guest-keccak APC shape: 2^%d rows x %d cols, %d constraints deg<=3, %d bus interactions (LogUp), log_blowup 1, "
+            "%d queries, %d PoW bits (synthetic AIR + uniform trace)" % (a.log_n, a.width, a.constraints, a.interactions, a.queries, a.pow_bits))
 
 
 def machine_for(a):
+    """-> (machine, constraint bytecode, spans, bus) ; bus = compile_bus(machine, 1) or None"""
     from powdr_b200 import machine as M
-    mach = M.synthetic_machine(a.width, a.constraints, seed=0xB2000001)
+    base = M.synthetic_machine(a.width, a.constraints, seed=0xB2000001)
+    mach = M.SymbolicMachine(base.constraints, M.synthetic_bus(base, a.interactions, seed=0xB2000002)) if a.interactions else base
+    assert mach.width == base.width
     bc, spans = M.compile_constraints(mach)
-    return mach, bc, spans
+    return mach, bc, spans, (M.compile_bus(mach, 1) if a.interactions else None)
 
 
 class ClockSampler:
@@ -111,42 +120,84 @@ class ClockSampler:
         return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": mx, "reasons": sorted(reasons), "samples": len(sm), "window": window}
 
 
-def cpu_baseline(a, mach, bc, spans):
-    """the oracle (C restatement, OpenMP over all host cores) on a bounded sample, scaled linearly to 2^log_n rows"""
-    import numpy as np
+CPU_STAGES = ("lde", "merkle", "logup_gen", "logup_commit", "quotient", "quotient_commit", "openings", "fri_commit", "pow", "query")
+
+
+def _mem_available_gb():
+    try:
+        for line in open("/proc/meminfo"):
+            if line.startswith("MemAvailable"):
+                return int(line.split()[1]) / 1e6
+    except Exception:
+        pass
+    return 0.0
+
+
+def cpu_prepare(a):
+    """pins OpenMP before the CPU library loads; returns (orc, threads)"""
+    n_cpu = os.cpu_count() or 1
+    os.environ.setdefault("OMP_PROC_BIND", "close")
+    os.environ.setdefault("OMP_PLACES", "cores")
+    os.environ.setdefault("OMP_NUM_THREADS", str(n_cpu))
     from oracle import orc
-    ln = min(a.cpu_sample_log_n, a.log_n)
+    orc.build()
+    return orc, orc.num_threads()
+
+
+def cpu_run(a, orc, mach, bc, spans, bus, log_n):
+    """one whole-segment proof on the host cores: the CPU implementation of the same path (oracle/prove.c driving the AVX-512
+    Montgomery primitives of oracle/fast.c; falls back to the scalar ones without AVX-512) -> (seconds, stage seconds)"""
+    import numpy as np
     rng = np.random.default_rng(0xB2000001)
-    trace = rng.integers(0, P, size=(mach.width, 1 << ln), dtype=np.uint32)
+    trace = rng.integers(0, P, size=(mach.width, 1 << log_n), dtype=np.uint32)
+    air = orc.Air(bc, spans, bus)
     t0 = time.time()
-    _, st = orc.prove_segment(trace, bc, spans, n_queries=100, pow_bits=16, fast=True)
-    st = [st[k] for k in ("lde", "merkle", "quotient", "quotient_commit", "openings", "fri_commit")]
-    dt = time.time() - t0
+    _, _, _, st = orc.prove(trace, bc, spans, air, n_queries=a.queries, pow_bits=a.pow_bits, fast=True)
+    return time.time() - t0, st
+
+
+def cpu_baseline(a, mach, bc, spans, bus, budget_s=None, max_runs=1):
+    """Times the CPU arm at the FULL configuration when host memory allows (trace + LDE + permutation trace + its LDE, ~4.6x the
+    trace bytes), else on the largest power-of-two row count that fits, scaled by rows (said in `sample`)."""
+    orc, threads = cpu_prepare(a)
+    wp = orc.Air(bc, spans, bus).perm_width
+    need_gb = lambda ln: 4.0 * (1 << ln) * (3.2 * mach.width + 3.2 * wp + 64) / 1e9
+    ln = a.log_n if a.cpu_log_n < 0 else min(a.cpu_log_n, a.log_n)
+    avail = _mem_available_gb()
+    while ln > 12 and avail and need_gb(ln) > 0.8 * avail:
+        ln -= 1
+    cpu_run(a, orc, mach, bc, spans, bus, min(ln, 12))                      # warm-up: library load, thread pool
+    runs, stages = [], None
+    t_start = time.time()
+    while len(runs) < max_runs and (not runs or budget_s is None or (time.time() - t_start) + runs[-1] < budget_s):
+        dt, stages = cpu_run(a, orc, mach, bc, spans, bus, ln)
+        runs.append(dt)
     scale = float(1 << (a.log_n - ln))
-    return {"value": dt * scale, "unit": "s", "cores": orc.num_threads(), "kind": "port",
-            "sample": "oracle prove_segment on 2^%d rows x %d cols (%.2f s), scaled x%d by rows (NTT log factor ignored: underestimates CPU time)" % (
-                ln, mach.width, dt, int(scale)),
-            "stages_s": dict(zip(["lde", "merkle", "quotient", "quotient_commit", "openings", "fri_commit"], [s * scale for s in st]))}
+    v = sum(runs) / len(runs) * scale
+    simd = "avx512" if orc.fast_available() else "scalar"
+    sample = ("full configuration: 2^%d rows x %d cols, %d constraints, %d interactions; %d timed run(s) %s s" % (
+        ln, mach.width, len(spans), a.interactions, len(runs), ["%.2f" % r for r in runs])) if scale == 1.0 else (
+        "2^%d rows x %d cols (host memory %.0f GB does not hold the full 2^%d-row working set of %.0f GB), %d run(s) %s s, scaled x%d by rows" % (
+            ln, mach.width, avail, a.log_n, need_gb(a.log_n), len(runs), ["%.2f" % r for r in runs], int(scale)))
+    return {"value": v, "unit": "s", "cores": threads, "kind": "port", "simd": simd, "sample": sample, "runs": len(runs),
+            "omp": {k: os.environ.get(k) for k in ("OMP_PROC_BIND", "OMP_PLACES", "OMP_NUM_THREADS")},
+            "stages_s": {k: stages[k] * scale for k in CPU_STAGES}}
 
 
 def run_reference(a):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    mach, bc, spans = machine_for(a)
-    vals = []
-    base = None
-    for i in range(a.warmup + a.steps):
-        base = cpu_baseline(a, mach, bc, spans)
-        if i >= a.warmup:
-            vals.append(base["value"])
-    v = sum(vals) / len(vals)
-    base["value"] = v
+    mach, bc, spans, bus = machine_for(a)
+    # full-size runs until the budget is spent (at most --steps of them); `steps` in the line = the runs actually timed
+    base = cpu_baseline(a, mach, bc, spans, bus, budget_s=a.cpu_budget_s, max_runs=max(1, a.steps))
+    v = base["value"]
     print(json.dumps({
-        "impl": "reference", "metric": METRIC, "value": v, "unit": "s", "n_gpus": a.gpus, "steps": a.steps, "warmup": a.warmup,
-        "ms_per_step": v * 1e3, "higher_is_better": False, "scaling": "weak", "vs_baseline": None, "dtype": "u32 (BabyBear)",
-        "data": "synthetic", "config": {"workload": workload_name(a), "note": "CPU restatement (oracle port) of the same path; the reference's "
-                                        "own prover is an un-vendored Rust crate and cannot be built here"},
+        "impl": "reference", "metric": METRIC, "value": v, "unit": "s", "n_gpus": a.gpus, "steps": base["runs"], "warmup": 1,
+        "ms_per_step": v * 1e3, "higher_is_better": False, "scaling": "weak", "vs_baseline": None, "dtype": "u32 (BabyBear, Montgomery, AVX-512 lanes)",
+        "data": "synthetic", "config": {"workload": workload_name(a), "note": "CPU implementation of the same path (same proof bit for bit) on all host "
+                                        "cores; the reference's own prover is an un-vendored Rust crate and cannot be built here (DESIGN.md §5)",
+                                        "steps_requested": a.steps},
         "cpu_baseline": base, "e2e": {"value": v, "unit": "s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}))
 
 
@@ -169,8 +220,12 @@ def run_native(a):
 
     stream = torch.cuda.current_stream()
     ctx = powdr_b200.Context(local, stream.cuda_stream)      # raises without the CUDA library / a GPU: no fallback
-    mach, bc, spans = machine_for(a)
-    air = ctx.air(bc, spans, mach.width)
+    ctx.set_fri_params(a.queries, a.pow_bits)
+    mach, bc, spans, bus = machine_for(a)
+    t_key = time.time()
+    air = ctx.air(bc, spans, mach.width, bus)                # key generation: NVRTC builds of the constraint and LogUp kernels
+    keygen_s = time.time() - t_key
+    wp = air.perm_width
     n, w = 1 << a.log_n, mach.width
     gen = torch.Generator(device=dev)
     gen.manual_seed(0xB2000000 + 1 + rank)
@@ -180,6 +235,7 @@ def run_native(a):
 
     def step_device():
         proof = ctx.prove_segment(air, trace.data_ptr(), a.log_n, w, on_device=True)
+        ctx.query_segment(a.log_n, w, wp)                     # query phase: 100 openings gathered on the device, read back
         if world > 1:   # the path's one exchange: all-gather of the segment commitments (Merkle caps) over NCCL/NVLink
             caps.copy_(torch.tensor(proof["trace_root"] + proof["quotient_root"], dtype=torch.int64).to(torch.int32), non_blocking=True)
             parallel.all_gather_caps(caps.view(2, 8), dist)
@@ -218,6 +274,9 @@ def run_native(a):
     ms_per_step = float(t.item()) / a.steps
     value = ms_per_step / 1e3 / world                           # seconds per segment, N segments proved per step
 
+    from powdr_b200.capi import SegmentProof
+    import ctypes
+    C_sizeof_proof = ctypes.sizeof(SegmentProof)
     e2e = None
     if not a.no_e2e:
         host = torch.empty((w, n), dtype=torch.int32, pin_memory=True)
@@ -231,6 +290,7 @@ def run_native(a):
         f0.record(stream)
         for _ in range(a.steps):
             p2 = ctx.prove_segment(air, host.data_ptr(), a.log_n, w, on_device=False)
+            q2, ys2 = ctx.query_segment(a.log_n, w, wp)
         f1.record(stream)
         sync_all()
         wall = (time.time() - t_wall) / a.steps
@@ -240,12 +300,12 @@ def run_native(a):
             dist.all_reduce(te, op=dist.ReduceOp.MAX)
         e2e = {"value": float(te.item()) / world, "unit": "s", "h2d_bytes_per_step": 4 * w * n * world,
                "proof_equals_device_path": p2 == proof,           # same trace through the host-input pipeline: same proof
-               "d2h_bytes_per_step": (16 + 4 + 12 * proof["n_fri_layers"] + 4 * proof["final_len"]) * 4 * world,
+               "d2h_bytes_per_step": (C_sizeof_proof + int(q2.nbytes) + int(ys2.nbytes)) * world,
                "stages_ms": ctx.last_stage_ms()}
 
     sharded = None
     if world > 1 and not a.no_sharded:
-        sharded = sharded_segment(a, ctx, air, dist, dev, stream, world, rank)
+        sharded = sharded_segment(a, ctx, ctx.air(bc, spans, mach.width), dist, dev, stream, world, rank)
 
     if rank == 0:
         peaks = {}
@@ -260,13 +320,15 @@ def run_native(a):
             traffic = json.load(open(os.path.join(ROOT, "profiles", "leaf_kernel_traffic.json")))["dram_bytes_per_launch"]
         except Exception:
             pass
-        nn, ww = float(n), float(w)
-        alg = {"lde": 12 * nn * ww, "merkle": 8 * nn * ww + 64 * nn, "quotient": 8 * nn * ww + 32 * nn}
+        nn, ww, wpp = float(n), float(w), float(wp)
+        alg = {"lde": 12 * nn * ww, "merkle": 8 * nn * ww + 64 * nn, "quotient": 8 * nn * (ww + (2 * wpp if wp else 0)) + 32 * nn,
+               "logup_gen": 4 * nn * (ww + wpp), "logup_commit": 12 * nn * wpp + 8 * nn * wpp + 64 * nn}
         out = {
             "metric": METRIC, "value": value, "unit": "s", "n_gpus": world, "steps": a.steps, "warmup": a.warmup,
             "ms_per_step": ms_per_step, "higher_is_better": False, "scaling": "weak", "vs_baseline": None,
             "dtype": "u32 (BabyBear, Montgomery)", "data": "synthetic",
             "config": {"workload": workload_name(a), "segments_per_step": world, "l2": "inputs (%.1f GB) exceed L2, no flush" % (4 * nn * ww / 1e9),
+                       "timed_region": "pb_prove_segment + pb_query_segment per step",
                        "parallelism": "1 segment per GPU, NCCL all-gather of Merkle caps" if world > 1 else "single GPU"},
             "gpu_launches": launches, "clocks": clocks,
             "roofline": {"bound": "hbm", "kernel": "p2::leaf_hash_cols_kernel (Poseidon2 leaf hashing)", "achieved": achieved, "peak": peak,
@@ -281,7 +343,7 @@ def run_native(a):
                                                         "frac": (perms * 657.6 / (leaf_ms / 1e3)) / peak_i if leaf_ms > 0 else 0.0})(
                 (leaf_bytes / (4.0 * ww + 32.0)) * math.ceil(ww / 8.0) if n_leaf else 0.0,
                 12.6 * 148 * ((clocks or {}).get("sm_mhz") or 1965.0) * 1e6),
-            "stages_ms": stage_ms,
+            "stages_ms": stage_ms, "keygen_s": keygen_s, "perm_width": wp,
             "stage_roofline_frac": {k: (alg[k] / 1e9) / (stage_ms[k] / 1e3) / peak for k in alg if stage_ms.get(k, 0) > 0},
             "segments_per_s": world / (ms_per_step / 1e3),
         }
@@ -290,7 +352,7 @@ def run_native(a):
         if sharded:
             out["one_segment_on_all_gpus"] = sharded
         if world == 1 and not a.no_cpu_baseline:
-            out["cpu_baseline"] = cpu_baseline(a, mach, bc, spans)
+            out["cpu_baseline"] = cpu_baseline(a, mach, bc, spans, bus)
         print(json.dumps(out))
     if world > 1:
         dist.barrier()
@@ -344,6 +406,7 @@ def sharded_segment(a, ctx, air, dist, dev, stream, world, rank):
     ok = torch.tensor([1 if proof == single else 0], dtype=torch.int32, device=dev)
     dist.all_reduce(ok, op=dist.ReduceOp.MIN)
     out = {"value": sec, "unit": "s", "scaling": "strong", "single_gpu_s": single_ms / 1e3, "speedup": single_ms / 1e3 / sec,
+           "workload": "the same segment WITHOUT its bus interactions (the sharded prover has no LogUp phase yet, DESIGN.md §6)",
            "proof_equals_single_gpu": bool(ok.item()), "stages_ms": stages,
            "collectives_per_segment": calls // max(1, a.steps + max(2, min(3, a.warmup))),
            "collective_bytes_per_rank_per_segment": nbytes // max(1, a.steps + max(2, min(3, a.warmup)))}

@@ -551,3 +551,221 @@ void orcf_deep_quotient(const uint32_t* const* mats, const size_t* widths, size_
     orcf_deep_quotient_groups(cols, grp, total, zeta, 1, log_m, shift, gamma, ys, out);
     free(cols); free(grp);
 }
+
+/* =====================================================================================================================
+ * LogUp / bus argument, 16 rows per vector (semantics: logup.c).  Montgomery inside, canonical at the edges. */
+typedef struct { V c[4]; } V4;
+static inline V4 v4_add(V4 a, V4 b) { V4 r; for (int i = 0; i < 4; i++) r.c[i] = v_add(a.c[i], b.c[i]); return r; }
+static inline V4 v4_sub(V4 a, V4 b) { V4 r; for (int i = 0; i < 4; i++) r.c[i] = v_sub(a.c[i], b.c[i]); return r; }
+static inline V4 v4_scale(V4 a, V s) { V4 r; for (int i = 0; i < 4; i++) r.c[i] = v_mul(a.c[i], s); return r; }
+static inline V v_x11(V x) { V x2 = v_add(x, x), x4 = v_add(x2, x2), x8 = v_add(x4, x4); return v_add(v_add(x8, x2), x); }
+static inline V4 v4_mul(V4 a, V4 b) {
+    const V b1 = v_x11(b.c[1]), b2 = v_x11(b.c[2]), b3 = v_x11(b.c[3]);
+    V4 r;
+    r.c[0] = v_add(v_add(v_mul(a.c[0], b.c[0]), v_mul(a.c[1], b3)), v_add(v_mul(a.c[2], b2), v_mul(a.c[3], b1)));
+    r.c[1] = v_add(v_add(v_mul(a.c[0], b.c[1]), v_mul(a.c[1], b.c[0])), v_add(v_mul(a.c[2], b3), v_mul(a.c[3], b2)));
+    r.c[2] = v_add(v_add(v_mul(a.c[0], b.c[2]), v_mul(a.c[1], b.c[1])), v_add(v_mul(a.c[2], b.c[0]), v_mul(a.c[3], b3)));
+    r.c[3] = v_add(v_add(v_mul(a.c[0], b.c[3]), v_mul(a.c[1], b.c[2])), v_add(v_mul(a.c[2], b.c[1]), v_mul(a.c[3], b.c[0])));
+    return r;
+}
+static inline V4 v4_bcast(bb4_t m) { V4 r; for (int i = 0; i < 4; i++) r.c[i] = VSET(m.c[i]); return r; }
+static V v_inv(V a) {                       /* a^(p-2), lane-wise, Montgomery (0 -> 0) */
+    V r = VSET(R1);
+    for (uint32_t e = P - 2; e; e >>= 1) { if (e & 1) r = v_mul(r, a); a = v_mul(a, a); }
+    return r;
+}
+static V4 v4_inv(V4 x) {                    /* same tower as bb4_inv */
+    const V W = VSET(to_m(BB_EXT_W));
+    V A0 = v_add(v_mul(x.c[0], x.c[0]), v_mul(W, v_mul(x.c[2], x.c[2]))), A1 = v_add(v_mul(x.c[0], x.c[2]), v_mul(x.c[0], x.c[2]));
+    V B0 = v_add(v_mul(x.c[1], x.c[1]), v_mul(W, v_mul(x.c[3], x.c[3]))), B1 = v_add(v_mul(x.c[1], x.c[3]), v_mul(x.c[1], x.c[3]));
+    V n0 = v_sub(A0, v_mul(W, B1)), n1 = v_sub(A1, B0);
+    V d = v_inv(v_sub(v_mul(n0, n0), v_mul(W, v_mul(n1, n1))));
+    V4 s = {{v_mul(n0, d), _mm512_setzero_si512(), v_neg(v_mul(n1, d)), _mm512_setzero_si512()}};
+    V4 cj = {{x.c[0], v_neg(x.c[1]), x.c[2], v_neg(x.c[3])}};
+    return v4_mul(cj, s);
+}
+
+/* one packed expression (constants already Montgomery) on rows r0..r0+15 of a column-major matrix -> Montgomery vector */
+static inline V eval16(const uint32_t* bc, uint32_t len, const uint32_t* mat, size_t height, size_t r0) {
+    const V vr2 = VSET(R2);
+    V st[16];
+    int sp = 0;
+    for (uint32_t ip = 0; ip < len;) {
+        const uint32_t op = bc[ip++];
+        switch (op) {
+        case OP_PUSH_APC: st[sp++] = v_mul(_mm512_loadu_si512(mat + (size_t)bc[ip++] * height + r0), vr2); break;
+        case OP_PUSH_CONST: st[sp++] = VSET(bc[ip++]); break;
+        case OP_ADD: sp--; st[sp - 1] = v_add(st[sp - 1], st[sp]); break;
+        case OP_SUB: sp--; st[sp - 1] = v_sub(st[sp - 1], st[sp]); break;
+        case OP_MUL: sp--; st[sp - 1] = v_mul(st[sp - 1], st[sp]); break;
+        case OP_NEG: st[sp - 1] = v_neg(st[sp - 1]); break;
+        default: st[sp - 1] = v_inv_or_zero(st[sp - 1]); break;
+        }
+    }
+    return st[0];
+}
+
+typedef struct {
+    uint32_t* code;             /* interaction bytecode with Montgomery constants */
+    bb4_t alpha_m;              /* alpha_lu, Montgomery limbs */
+    bb4_t* kc;                  /* per interaction: alpha_lu + beta^k (bus + 1), Montgomery */
+    bb4_t* betas;               /* beta^j, Montgomery */
+} lu_ctx_t;
+
+static void lu_ctx_init(lu_ctx_t* L, const uint32_t* ibc, const orc_span_t* isp, const orc_interaction_t* ints, size_t n_ints,
+                        const uint32_t alpha_lu[4], const uint32_t beta_lu[4]) {
+    size_t n_spans = 0, maxk = 0;
+    for (size_t i = 0; i < n_ints; i++) {
+        if (ints[i].args_index_off + ints[i].num_args + 1 > n_spans) n_spans = ints[i].args_index_off + ints[i].num_args + 1;
+        if (ints[i].num_args > maxk) maxk = ints[i].num_args;
+    }
+    size_t nw;
+    L->code = pack_code(ibc, isp, n_spans, &nw);
+    bb4_t al = {{alpha_lu[0], alpha_lu[1], alpha_lu[2], alpha_lu[3]}}, be = {{beta_lu[0], beta_lu[1], beta_lu[2], beta_lu[3]}};
+    bb4_t* bc_ = (bb4_t*)malloc((maxk + 1) * sizeof(bb4_t));
+    L->betas = (bb4_t*)malloc((maxk + 1) * sizeof(bb4_t));
+    bc_[0] = bb4_from_base(1);
+    for (size_t j = 1; j <= maxk; j++) bc_[j] = bb4_mul(bc_[j - 1], be);
+    for (size_t j = 0; j <= maxk; j++) L->betas[j] = e4_to_m(bc_[j]);
+    L->kc = (bb4_t*)malloc((n_ints ? n_ints : 1) * sizeof(bb4_t));
+    for (size_t i = 0; i < n_ints; i++) L->kc[i] = e4_to_m(bb4_add(al, bb4_scale(bc_[ints[i].num_args], (ints[i].bus_id + 1) % P)));
+    L->alpha_m = e4_to_m(al);
+    free(bc_);
+}
+static void lu_ctx_free(lu_ctx_t* L) { free(L->code); free(L->kc); free(L->betas); }
+
+/* (m_i, d_i) of every interaction on 16 rows, then per chunk (N_c, D_c) */
+static void lu_chunks16(const lu_ctx_t* L, const orc_span_t* isp, const orc_interaction_t* ints, const uint32_t* chunk_start, size_t n_chunks,
+                        const uint32_t* mat, size_t height, size_t r0, V* mv, V4* dv, V4* Nc, V4* Dc) {
+    for (size_t c = 0; c < n_chunks; c++) {
+        const uint32_t a = chunk_start[c], e = chunk_start[c + 1];
+        for (uint32_t i = a; i < e; i++) {
+            const orc_span_t* s = isp + ints[i].args_index_off;
+            mv[i - a] = eval16(L->code + s[0].off, s[0].len, mat, height, r0);
+            V4 d = v4_bcast(L->kc[i]);
+            for (uint32_t j = 0; j < ints[i].num_args; j++) {
+                const V x = eval16(L->code + s[1 + j].off, s[1 + j].len, mat, height, r0);
+                d = v4_add(d, v4_scale(v4_bcast(L->betas[j]), x));
+            }
+            dv[i - a] = d;
+        }
+        /* N = sum_i m_i prod_{j != i} d_j,  D = prod_i d_i  (incrementally) */
+        V4 D = dv[0], N = {{mv[0], _mm512_setzero_si512(), _mm512_setzero_si512(), _mm512_setzero_si512()}};
+        for (uint32_t i = 1; i < e - a; i++) {
+            N = v4_add(v4_mul(N, dv[i]), v4_scale(D, mv[i]));
+            D = v4_mul(D, dv[i]);
+        }
+        Nc[c] = N;
+        Dc[c] = D;
+    }
+}
+
+void orcf_logup_perm_trace(const uint32_t* trace, unsigned log_n, const uint32_t* ibc, const orc_span_t* isp, const orc_interaction_t* ints,
+                           size_t n_ints, const uint32_t* chunk_start, size_t n_chunks, const uint32_t alpha_lu[4], const uint32_t beta_lu[4],
+                           uint32_t* perm, uint32_t cumsum[4]) {
+    const size_t n = (size_t)1 << log_n;
+    if (n < 16) { orc_logup_perm_trace(trace, log_n, ibc, isp, ints, n_ints, chunk_start, n_chunks, alpha_lu, beta_lu, perm, cumsum); return; }
+    lu_ctx_t L;
+    lu_ctx_init(&L, ibc, isp, ints, n_ints, alpha_lu, beta_lu);
+    size_t max_chunk = 1;
+    for (size_t c = 0; c < n_chunks; c++) if (chunk_start[c + 1] - chunk_start[c] > max_chunk) max_chunk = chunk_start[c + 1] - chunk_start[c];
+    uint32_t* rowsum = (uint32_t*)aligned_alloc(64, 4 * n * sizeof(uint32_t));
+    const V one = VSET(1);
+#pragma omp parallel
+    {
+        V* mv = (V*)aligned_alloc(64, max_chunk * sizeof(V));
+        V4* dv = (V4*)aligned_alloc(64, max_chunk * sizeof(V4));
+        V4* Nc = (V4*)aligned_alloc(64, n_chunks * sizeof(V4));
+        V4* Dc = (V4*)aligned_alloc(64, n_chunks * sizeof(V4));
+        V4* pre = (V4*)aligned_alloc(64, n_chunks * sizeof(V4));
+#pragma omp for schedule(static)
+        for (long r0 = 0; r0 < (long)n; r0 += 16) {
+            lu_chunks16(&L, isp, ints, chunk_start, n_chunks, trace, n, (size_t)r0, mv, dv, Nc, Dc);
+            /* Montgomery's trick across the chunks of this row block: one Ext4 inversion per 16 rows */
+            V4 acc = v4_bcast((bb4_t){{R1, 0, 0, 0}});
+            for (size_t c = 0; c < n_chunks; c++) { pre[c] = acc; acc = v4_mul(acc, Dc[c]); }
+            V4 inv = v4_inv(acc), rs = {{_mm512_setzero_si512(), _mm512_setzero_si512(), _mm512_setzero_si512(), _mm512_setzero_si512()}};
+            for (size_t c = n_chunks; c-- > 0;) {
+                const V4 dinv = v4_mul(inv, pre[c]);
+                inv = v4_mul(inv, Dc[c]);
+                const V4 v = v4_mul(Nc[c], dinv);
+                rs = v4_add(rs, v);
+                for (int l = 0; l < 4; l++) _mm512_storeu_si512(perm + (4 * c + l) * n + (size_t)r0, v_mul(v.c[l], one));
+            }
+            for (int l = 0; l < 4; l++) _mm512_storeu_si512(rowsum + (size_t)l * n + (size_t)r0, v_mul(rs.c[l], one));
+        }
+        free(mv); free(dv); free(Nc); free(Dc); free(pre);
+    }
+    uint32_t phi[4] = {0, 0, 0, 0};
+    for (size_t r = 0; r < n; r++)
+        for (int l = 0; l < 4; l++) { phi[l] = s_add(phi[l], rowsum[(size_t)l * n + r]); perm[(4 * n_chunks + l) * n + r] = phi[l]; }
+    memcpy(cumsum, phi, 16);
+    free(rowsum);
+    lu_ctx_free(&L);
+}
+
+void orcf_logup_fold(const uint32_t* lde, const uint32_t* perm_lde, unsigned log_n, uint32_t shift, const uint32_t* ibc, const orc_span_t* isp,
+                     const orc_interaction_t* ints, size_t n_ints, const uint32_t* chunk_start, size_t n_chunks, const uint32_t alpha_lu[4],
+                     const uint32_t beta_lu[4], const uint32_t cumsum[4], const uint32_t alpha[4], uint32_t* acc4) {
+    const size_t n = (size_t)1 << log_n, m = n << 1;
+    const unsigned log_m = log_n + 1;
+    if (n < 16) { orc_logup_fold(lde, perm_lde, log_n, shift, ibc, isp, ints, n_ints, chunk_start, n_chunks, alpha_lu, beta_lu, cumsum, alpha, acc4); return; }
+    lu_ctx_t L;
+    lu_ctx_init(&L, ibc, isp, ints, n_ints, alpha_lu, beta_lu);
+    size_t max_chunk = 1;
+    for (size_t c = 0; c < n_chunks; c++) if (chunk_start[c + 1] - chunk_start[c] > max_chunk) max_chunk = chunk_start[c + 1] - chunk_start[c];
+    const bb4_t a_m = e4_to_m((bb4_t){{alpha[0], alpha[1], alpha[2], alpha[3]}});
+    const bb4_t cs_m = e4_to_m((bb4_t){{cumsum[0], cumsum[1], cumsum[2], cumsum[3]}});
+    const uint32_t w_m = bb_root_of_unity(log_m), w_n_inv = bb_inv(bb_root_of_unity(log_n)), sn = bb_pow(shift, n);
+    const V vr2 = VSET(R2), one = VSET(1);
+#pragma omp parallel
+    {
+        V* mv = (V*)aligned_alloc(64, max_chunk * sizeof(V));
+        V4* dv = (V4*)aligned_alloc(64, max_chunk * sizeof(V4));
+        V4* Nc = (V4*)aligned_alloc(64, n_chunks * sizeof(V4));
+        V4* Dc = (V4*)aligned_alloc(64, n_chunks * sizeof(V4));
+#pragma omp for schedule(static)
+        for (long r0 = 0; r0 < (long)m; r0 += 16) {
+            lu_chunks16(&L, isp, ints, chunk_start, n_chunks, lde, m, (size_t)r0, mv, dv, Nc, Dc);
+            uint32_t rn[16], sel[3][16];
+            int contiguous = 1;
+            for (int l = 0; l < 16; l++) {
+                const uint32_t i_nat = bitrev32((uint32_t)(r0 + l), log_m);
+                rn[l] = bitrev32((uint32_t)((i_nat + 2) & (m - 1)), log_m);
+                if (rn[l] != rn[0] + (uint32_t)l) contiguous = 0;
+                const uint32_t x = bb_mul(shift, bb_pow(w_m, i_nat));
+                const uint32_t zh = bb_sub((i_nat & 1) ? bb_neg(sn) : sn, 1);
+                sel[0][l] = to_m(bb_mul(zh, bb_inv(bb_sub(x, 1))));
+                sel[1][l] = to_m(bb_sub(x, w_n_inv));
+                sel[2][l] = to_m(bb_mul(zh, bb_inv(bb_sub(x, w_n_inv))));
+            }
+            const V vrn = _mm512_loadu_si512(rn);
+#define LDN(col) (contiguous ? _mm512_loadu_si512(perm_lde + (size_t)(col) * m + rn[0]) : _mm512_i32gather_epi32(vrn, perm_lde + (size_t)(col) * m, 4))
+            V4 acc, sum = v4_bcast((bb4_t){{0, 0, 0, 0}}), sum_next = sum;
+            for (int l = 0; l < 4; l++) acc.c[l] = v_mul(_mm512_loadu_si512(acc4 + (size_t)l * m + (size_t)r0), vr2);
+            const V4 va = v4_bcast(a_m);
+            for (size_t c = 0; c < n_chunks; c++) {
+                V4 pc, pn;
+                for (int l = 0; l < 4; l++) {
+                    pc.c[l] = v_mul(_mm512_loadu_si512(perm_lde + (4 * c + l) * m + (size_t)r0), vr2);
+                    pn.c[l] = v_mul(LDN(4 * c + l), vr2);
+                }
+                sum = v4_add(sum, pc);
+                sum_next = v4_add(sum_next, pn);
+                acc = v4_add(v4_mul(acc, va), v4_sub(v4_mul(pc, Dc[c]), Nc[c]));
+            }
+            V4 phi, phn;
+            for (int l = 0; l < 4; l++) {
+                phi.c[l] = v_mul(_mm512_loadu_si512(perm_lde + (4 * n_chunks + l) * m + (size_t)r0), vr2);
+                phn.c[l] = v_mul(LDN(4 * n_chunks + l), vr2);
+            }
+#undef LDN
+            acc = v4_add(v4_mul(acc, va), v4_scale(v4_sub(phi, sum), _mm512_loadu_si512(sel[0])));
+            acc = v4_add(v4_mul(acc, va), v4_scale(v4_sub(v4_sub(phn, phi), sum_next), _mm512_loadu_si512(sel[1])));
+            acc = v4_add(v4_mul(acc, va), v4_scale(v4_sub(phi, v4_bcast(cs_m)), _mm512_loadu_si512(sel[2])));
+            for (int l = 0; l < 4; l++) _mm512_storeu_si512(acc4 + (size_t)l * m + (size_t)r0, v_mul(acc.c[l], one));
+        }
+        free(mv); free(dv); free(Nc); free(Dc);
+    }
+    lu_ctx_free(&L);
+}

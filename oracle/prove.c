@@ -30,9 +30,15 @@ typedef struct {
     void (*eval_at_point)(const uint32_t*, unsigned, size_t, uint32_t, const uint32_t[4], uint32_t*);
     void (*deep_groups)(const uint32_t* const*, const uint32_t*, size_t, const uint32_t*, size_t, unsigned, uint32_t, const uint32_t[4],
                         const uint32_t*, uint32_t*);
+    void (*logup_perm_trace)(const uint32_t*, unsigned, const uint32_t*, const orc_span_t*, const orc_interaction_t*, size_t, const uint32_t*, size_t,
+                             const uint32_t[4], const uint32_t[4], uint32_t*, uint32_t[4]);
+    void (*logup_fold)(const uint32_t*, const uint32_t*, unsigned, uint32_t, const uint32_t*, const orc_span_t*, const orc_interaction_t*, size_t,
+                       const uint32_t*, size_t, const uint32_t[4], const uint32_t[4], const uint32_t[4], const uint32_t[4], uint32_t*);
 } ops_t;
-static const ops_t OPS_SLOW = {orc_lde_batch, orc_merkle_commit, orc_constraint_fold, orc_eval_at_point, orc_deep_quotient_groups};
-static const ops_t OPS_FAST = {orcf_lde_batch, orcf_merkle_commit, orcf_constraint_fold, orcf_eval_at_point, orcf_deep_quotient_groups};
+static const ops_t OPS_SLOW = {orc_lde_batch, orc_merkle_commit, orc_constraint_fold, orc_eval_at_point, orc_deep_quotient_groups,
+                               orc_logup_perm_trace, orc_logup_fold};
+static const ops_t OPS_FAST = {orcf_lde_batch, orcf_merkle_commit, orcf_constraint_fold, orcf_eval_at_point, orcf_deep_quotient_groups,
+                               orcf_logup_perm_trace, orcf_logup_fold};
 
 /* Merkle tree (all layers, node-major) of a row-major matrix; returns malloc'ed [2h-1][8] */
 static uint32_t* merkle_tree_rowmajor(const uint32_t* mat, size_t width, unsigned log_h) {
@@ -132,7 +138,7 @@ void orc_prove_segment(const uint32_t* trace, unsigned log_n, size_t width, cons
         orc_challenger_sample_ext(&ch, proof->logup_alpha);
         orc_challenger_sample_ext(&ch, proof->logup_beta);
         perm = (uint32_t*)malloc(wp * n * sizeof(uint32_t));
-        orc_logup_perm_trace(trace, log_n, air->ibc, air->ispans, air->ints, air->n_ints, chunk_start, n_chunks, proof->logup_alpha,
+        ops->logup_perm_trace(trace, log_n, air->ibc, air->ispans, air->ints, air->n_ints, chunk_start, n_chunks, proof->logup_alpha,
                              proof->logup_beta, perm, proof->cumulative_sum);
         double t3 = now_s();
         st[2] = t3 - t2;
@@ -156,7 +162,7 @@ void orc_prove_segment(const uint32_t* trace, unsigned log_n, size_t width, cons
         uint32_t* acc4 = (uint32_t*)malloc(4 * m * sizeof(uint32_t));
         ops->constraint_fold(air->bc, air->spans, air->n_constraints, lde, m, proof->alpha, acc4);
         if (air->n_ints)
-            orc_logup_fold(lde, perm_lde, log_n, BB_GENERATOR, air->ibc, air->ispans, air->ints, air->n_ints, chunk_start, n_chunks,
+            ops->logup_fold(lde, perm_lde, log_n, BB_GENERATOR, air->ibc, air->ispans, air->ints, air->n_ints, chunk_start, n_chunks,
                            proof->logup_alpha, proof->logup_beta, proof->cumulative_sum, proof->alpha, acc4);
         uint32_t sn = bb_pow(BB_GENERATOR, n);
         uint32_t zinv[2] = {bb_inv(bb_sub(sn, 1)), bb_inv(bb_sub(bb_neg(sn), 1))};

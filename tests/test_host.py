@@ -239,7 +239,7 @@ def test_bench_reference_arm_prints_one_contract_line():
     import subprocess
     import sys
     r = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--steps", "1", "--warmup", "1", "--log-n", "12",
-                        "--width", "24", "--constraints", "5", "--cpu-sample-log-n", "8"], capture_output=True, text=True, timeout=300)
+                        "--width", "24", "--constraints", "5", "--interactions", "9", "--queries", "10", "--pow-bits", "6"], capture_output=True, text=True, timeout=300)
     assert r.returncode == 0, r.stderr[-2000:]
     lines = [ln for ln in r.stdout.splitlines() if ln.strip()]
     assert len(lines) == 1
@@ -248,6 +248,8 @@ def test_bench_reference_arm_prints_one_contract_line():
               "data", "config", "cpu_baseline", "e2e"):
         assert k in d, k
     assert d["impl"] == "reference" and d["higher_is_better"] is False and d["value"] > 0
+    cb = d["cpu_baseline"]
+    assert cb["kind"] == "port" and cb["cores"] >= 1 and "full configuration" in cb["sample"] and cb["stages_s"]["logup_gen"] > 0
     assert d["cpu_baseline"]["kind"] == "port" and d["e2e"]["h2d_bytes_per_step"] == 0 and d["e2e"]["value"] == d["value"]
 
 
