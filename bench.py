@@ -46,9 +46,10 @@ def parse():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-sharded", action="store_true", help="skip the one-segment-on-all-GPUs (strong scaling) measurement at N > 1")
-    ap.add_argument("--workload", default="keccak", choices=["keccak", "multichip"],
+    ap.add_argument("--workload", default="keccak", choices=["keccak", "multichip", "pairing"],
                     help="keccak: one APC chip per segment (the BASELINE metric); multichip: 50 independent chips of one segment "
-                         "sharded over the ranks by LPT (BASELINE.json configs[3] shape, strong scaling)")
+                         "sharded over the ranks by LPT (BASELINE.json configs[3] shape, strong scaling); pairing: ONE wide segment "
+                         "(default 2^20 x 16384, BASELINE.json configs[4]) column-sharded over all ranks -- the case that needs sharding")
     return ap.parse_args()
 
 
@@ -136,6 +137,13 @@ def _mem_available_gb():
 def cpu_prepare(a):
     """pins OpenMP before the CPU library loads; returns (orc, threads)"""
     n_cpu = os.cpu_count() or 1
+    try:        # one OpenMP thread per PHYSICAL core: the AVX-512 kernels do not gain from the second hyperthread
+        sib = set()
+        for i in range(n_cpu):
+            sib.add(open("/sys/devices/system/cpu/cpu%d/topology/thread_siblings_list" % i).read().strip())
+        n_cpu = max(1, len(sib))
+    except Exception:
+        pass
     os.environ.setdefault("OMP_PROC_BIND", "close")
     os.environ.setdefault("OMP_PLACES", "cores")
     os.environ.setdefault("OMP_NUM_THREADS", str(n_cpu))
@@ -149,7 +157,9 @@ def cpu_run(a, orc, mach, bc, spans, bus, log_n):
     Montgomery primitives of oracle/fast.c; falls back to the scalar ones without AVX-512) -> (seconds, stage seconds)"""
     import numpy as np
     rng = np.random.default_rng(0xB2000001)
-    trace = rng.integers(0, P, size=(mach.width, 1 << log_n), dtype=np.uint32)
+    trace = orc.big_array((mach.width, 1 << log_n))                 # huge-page backed like the prover's own buffers
+    for c0 in range(0, mach.width, 64):
+        trace[c0:c0 + 64] = rng.integers(0, P, size=trace[c0:c0 + 64].shape, dtype=np.uint32)
     air = orc.Air(bc, spans, bus)
     t0 = time.time()
     _, _, _, st = orc.prove(trace, bc, spans, air, n_queries=a.queries, pow_bits=a.pow_bits, fast=True)
@@ -516,11 +526,91 @@ def run_multichip(a):
     ctx.close()
 
 
+def run_pairing(a):
+    """BASELINE.json configs[4]: one segment too wide for one GPU's comfort (2^20 x 16384 = 68.7 GB of trace, 137 GB of LDE)
+    proved by all ranks together (pb_prove_segment_sharded).  Every rank generates only its own column block; the proofs of
+    all ranks must be identical.  Constraints only (the sharded prover has no LogUp phase yet)."""
+    import torch
+    import torch.distributed as dist
+    import powdr_b200
+    from powdr_b200 import machine as M
+    from powdr_b200.sharded import TorchComm, shard_columns
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    assert world > 1, "--workload pairing shards one segment over the ranks: launch with torchrun, N >= 2"
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
+    dist.init_process_group("nccl", device_id=dev)
+    stream = torch.cuda.current_stream()
+    ctx = powdr_b200.Context(local, stream.cuda_stream)
+    ctx.set_fri_params(a.queries, a.pow_bits)
+    width = a.width if a.width != 2022 else 16384
+    ncons = a.constraints if a.constraints != 187 else 4096
+    mach = M.synthetic_machine(width, ncons, seed=0xB2000005)
+    bc, spans = M.compile_constraints(mach)
+    t_key = time.time()
+    air = ctx.air(bc, spans, mach.width)
+    keygen_s = time.time() - t_key
+    n, w = 1 << a.log_n, mach.width
+    first, count = shard_columns(w, world, rank)
+    gen = torch.Generator(device=dev)
+    gen.manual_seed(0xB2000500 + rank)
+    mine = torch.randint(0, P, (max(1, count), n), dtype=torch.int32, device=dev, generator=gen)
+    comm = TorchComm()
+
+    def sync_all():
+        torch.cuda.synchronize()
+        dist.barrier()
+        torch.cuda.synchronize()
+
+    def step():
+        return ctx.prove_segment_sharded(air, mine.data_ptr() if count else 0, a.log_n, w, comm, on_device=True)
+
+    for _ in range(a.warmup):
+        step()
+    sync_all()
+    l0 = ctx.launch_count()
+    c0, b0 = comm.calls, comm.bytes
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    t0 = time.time()
+    e0.record(stream)
+    for _ in range(a.steps):
+        proof = step()
+    e1.record(stream)
+    sync_all()
+    wall = (time.time() - t0) / a.steps
+    t = torch.tensor([max(e0.elapsed_time(e1) / 1e3 / a.steps, wall)], dtype=torch.float64, device=dev)
+    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    sig = torch.tensor(proof["trace_root"] + proof["quotient_root"] + proof["final_poly"][0] + [proof["pow_witness"]], dtype=torch.int64, device=dev)
+    lo, hi = sig.clone(), sig.clone()
+    dist.all_reduce(lo, op=dist.ReduceOp.MIN)
+    dist.all_reduce(hi, op=dist.ReduceOp.MAX)
+    same = bool((lo == hi).all().item())
+    if rank == 0:
+        print(json.dumps({
+            "metric": "proof-gen sec for ONE wide APC segment (guest-pairing shape) column-sharded over N B200", "value": float(t.item()), "unit": "s",
+            "n_gpus": world, "steps": a.steps, "warmup": a.warmup, "ms_per_step": float(t.item()) * 1e3, "higher_is_better": False, "scaling": "strong",
+            "vs_baseline": None, "dtype": "u32 (BabyBear, Montgomery)", "data": "synthetic",
+            "config": {"workload": "2^%d rows x %d cols, %d constraints deg<=3, no bus interactions (sharded prover), log_blowup 1; trace %.1f GB, LDE %.1f GB "
+                                   "in total, column block per rank resident in HBM" % (a.log_n, w, ncons, 4.0 * n * w / 1e9, 8.0 * n * w / 1e9),
+                       "parallelism": "column-sharded trace -> one all-to-all -> row-sharded LDE/Merkle/quotient/FRI; NCCL over NVLink"},
+            "proof_identical_on_all_ranks": same, "final_poly_constant": proof["final_poly"][0] == proof["final_poly"][1],
+            "stages_ms": ctx.last_stage_ms(), "keygen_s": keygen_s, "gpu_launches": ctx.launch_count() - l0,
+            "collectives_per_segment": (comm.calls - c0) // a.steps, "collective_bytes_per_rank_per_segment": (comm.bytes - b0) // a.steps}))
+    dist.barrier()
+    dist.destroy_process_group()
+    ctx.close()
+
+
 if __name__ == "__main__":
     args = parse()
     if args.impl == "reference":
         run_reference(args)
     elif args.workload == "multichip":
         run_multichip(args)
+    elif args.workload == "pairing":
+        run_pairing(args)
     else:
         run_native(args)

@@ -128,23 +128,49 @@ static void ntt_scalar_stage(uint32_t* a, size_t n, size_t half, const uint32_t*
             else { uint32_t t = m_mul(v, tw[half + j]); a[blk + j] = s_add(u, t); a[blk + j + half] = s_sub(u, t); }
         }
 }
-/* DIT: bit-reversed in -> natural out.  DIF: natural in -> bit-reversed out.  Data canonical, twiddles Montgomery. */
+/* DIT: bit-reversed in -> natural out.  DIF: natural in -> bit-reversed out.  Data canonical, twiddles Montgomery.
+   Cache blocking: a radix-2 stage of span `half` splits the array into independent blocks of 2*half elements, so all stages
+   with 2*half <= 2^BLK_LOG are run block by block (a block = 1 MB stays in L2) and only the few larger stages stream the
+   whole column from memory: ~5 passes over a 2^21-point column instead of 21. */
+#define BLK_LOG 18
+static inline void one_stage(uint32_t* a, size_t n, size_t half, const uint32_t* tw, int dif) {
+    if (n < 16) ntt_scalar_stage(a, n, half, tw, dif);
+    else if (half < 16) stage_small(a, n, (unsigned)half, tw, dif);
+    else stage_big(a, n, half, tw, dif);
+}
 static void ntt_dit(uint32_t* a, unsigned log_n, const uint32_t* tw) {
-    size_t n = (size_t)1 << log_n;
-    for (unsigned s = 0; s < log_n; s++) {
-        size_t half = (size_t)1 << s;
-        if (n < 16) ntt_scalar_stage(a, n, half, tw, 0);
-        else if (half < 16) stage_small(a, n, (unsigned)half, tw, 0);
-        else stage_big(a, n, half, tw, 0);
-    }
+    const size_t n = (size_t)1 << log_n;
+    const unsigned lb = log_n < BLK_LOG ? log_n : BLK_LOG;
+    for (size_t b0 = 0; b0 < n; b0 += (size_t)1 << lb)
+        for (unsigned s = 0; s < lb; s++) one_stage(a + b0, (size_t)1 << lb, (size_t)1 << s, tw, 0);
+    for (unsigned s = lb; s < log_n; s++) one_stage(a, n, (size_t)1 << s, tw, 0);
 }
 static void ntt_dif(uint32_t* a, unsigned log_n, const uint32_t* tw) {
-    size_t n = (size_t)1 << log_n;
-    for (unsigned s = log_n; s-- > 0;) {
-        size_t half = (size_t)1 << s;
-        if (n < 16) ntt_scalar_stage(a, n, half, tw, 1);
-        else if (half < 16) stage_small(a, n, (unsigned)half, tw, 1);
-        else stage_big(a, n, half, tw, 1);
+    const size_t n = (size_t)1 << log_n;
+    const unsigned lb = log_n < BLK_LOG ? log_n : BLK_LOG;
+    for (unsigned s = log_n; s-- > lb;) one_stage(a, n, (size_t)1 << s, tw, 1);
+    for (size_t b0 = 0; b0 < n; b0 += (size_t)1 << lb)
+        for (unsigned s = lb; s-- > 0;) one_stage(a + b0, (size_t)1 << lb, (size_t)1 << s, tw, 1);
+}
+
+/* dst[bitrev(i)] = src[i], cache-blocked: index = (a : 5 top bits, b : middle, c : 5 low bits) -> (rev c, rev b, rev a); for a fixed b
+   the 32x32 tile {a, c} is read as 32 runs of 128 B and written as 32 runs of 128 B through a 4 KB buffer (a plain gather does one
+   cache miss per element: ~100 ms per 2^20-point column) */
+static void bitrev_copy(const uint32_t* src, uint32_t* dst, unsigned log_n, const uint32_t* rev_mid /* bitrev over log_n - 10 bits */) {
+    if (log_n < 10) {
+        for (size_t i = 0; i < ((size_t)1 << log_n); i++) dst[bitrev32((uint32_t)i, log_n)] = src[i];
+        return;
+    }
+    static const uint8_t r5[32] = {0, 16, 8, 24, 4, 20, 12, 28, 2, 18, 10, 26, 6, 22, 14, 30, 1, 17, 9, 25, 5, 21, 13, 29, 3, 19, 11, 27, 7, 23, 15, 31};
+    const unsigned mid = log_n - 10;
+    uint32_t t[32][32];
+    for (size_t b = 0; b < ((size_t)1 << mid); b++) {
+        for (unsigned a = 0; a < 32; a++) {
+            const uint32_t* p = src + ((size_t)a << (log_n - 5)) + (b << 5);
+            for (unsigned c = 0; c < 32; c++) t[r5[c]][r5[a]] = p[c];
+        }
+        const size_t rb = rev_mid[b];
+        for (unsigned rc = 0; rc < 32; rc++) memcpy(dst + ((size_t)rc << (log_n - 5)) + (rb << 5), t[rc], 128);
     }
 }
 
@@ -155,19 +181,19 @@ void orcf_lde_batch(const uint32_t* trace, unsigned log_n, size_t width, unsigne
     uint32_t* tw_fwd = make_twiddles(log_m, 0);
     /* scale[k] = shift^k / N in Montgomery form; rev[i] = bitrev_n(i) */
     uint32_t* scale = (uint32_t*)aligned_alloc(64, (n < 16 ? 16 : n) * sizeof(uint32_t));
-    uint32_t* rev = (uint32_t*)malloc(n * sizeof(uint32_t));
+    const unsigned mid = log_n >= 10 ? log_n - 10 : 0;
+    uint32_t* rev = (uint32_t*)malloc(((size_t)1 << mid) * sizeof(uint32_t));
     {
         uint32_t sm = to_m(shift % P), x = to_m(bb_inv((uint32_t)(n % P)));
         for (size_t k = 0; k < n; k++) { scale[k] = x; x = m_mul(x, sm); }
-        for (size_t i = 0; i < n; i++) rev[i] = bitrev32((uint32_t)i, log_n);
+        for (size_t i = 0; i < ((size_t)1 << mid); i++) rev[i] = bitrev32((uint32_t)i, mid);
     }
 #pragma omp parallel
     {
         uint32_t* buf = (uint32_t*)aligned_alloc(64, (m < 16 ? 16 : m) * sizeof(uint32_t));
 #pragma omp for schedule(dynamic, 1)
         for (long c = 0; c < (long)width; c++) {
-            const uint32_t* src = trace + (size_t)c * n;
-            for (size_t i = 0; i < n; i++) buf[i] = src[rev[i]];
+            bitrev_copy(trace + (size_t)c * n, buf, log_n, rev);
             ntt_dit(buf, log_n, tw_inv);
             if (n >= 16)
                 for (size_t k = 0; k < n; k += 16) _mm512_storeu_si512(buf + k, v_mul(_mm512_loadu_si512(buf + k), _mm512_loadu_si512(scale + k)));
@@ -229,6 +255,35 @@ static inline void v_permute(V s[16]) {
         v_external(s);
     }
 }
+/* NB independent permutations interleaved step by step: the 13 internal rounds are one serial S-box chain each (4 dependent
+   products of ~20 cycles latency), which a single permutation cannot hide on an out-of-order core */
+#define P2_NB 4
+static inline __attribute__((always_inline)) void v_permute_nb(V s[P2_NB][16]) {
+    for (int b = 0; b < P2_NB; b++) v_external(s[b]);
+    for (int r = 0; r < 4; r++) {
+        for (int i = 0; i < 16; i++) for (int b = 0; b < P2_NB; b++) s[b][i] = v_sbox(v_add(s[b][i], VSET(g_p2.rc_ext[r][i])));
+        for (int b = 0; b < P2_NB; b++) v_external(s[b]);
+    }
+    for (int r = 0; r < 13; r++) {
+        V x[P2_NB], x2[P2_NB], x3[P2_NB], x4[P2_NB];
+        for (int b = 0; b < P2_NB; b++) x[b] = v_add(s[b][0], VSET(g_p2.rc_int[r]));
+        for (int b = 0; b < P2_NB; b++) x2[b] = v_mul(x[b], x[b]);
+        for (int b = 0; b < P2_NB; b++) x3[b] = v_mul(x2[b], x[b]);
+        for (int b = 0; b < P2_NB; b++) x4[b] = v_mul(x2[b], x2[b]);
+        for (int b = 0; b < P2_NB; b++) s[b][0] = v_mul(x3[b], x4[b]);
+        for (int b = 0; b < P2_NB; b++) {
+            V* t = s[b];
+            V a = v_add(v_add(t[0], t[1]), v_add(t[2], t[3])), bb_ = v_add(v_add(t[4], t[5]), v_add(t[6], t[7]));
+            V c = v_add(v_add(t[8], t[9]), v_add(t[10], t[11])), d = v_add(v_add(t[12], t[13]), v_add(t[14], t[15]));
+            V sum = v_add(v_add(a, bb_), v_add(c, d));
+            for (int i = 0; i < 16; i++) t[i] = v_add(sum, v_mul(t[i], VSET(g_p2.diag[i])));
+        }
+    }
+    for (int r = 4; r < 8; r++) {
+        for (int i = 0; i < 16; i++) for (int b = 0; b < P2_NB; b++) s[b][i] = v_sbox(v_add(s[b][i], VSET(g_p2.rc_ext[r][i])));
+        for (int b = 0; b < P2_NB; b++) v_external(s[b]);
+    }
+}
 
 void orcf_merkle_commit(const uint32_t* const* mats, const size_t* widths, size_t n_mats, unsigned log_h, uint32_t* layers) {
     const size_t h = (size_t)1 << log_h;
@@ -242,18 +297,38 @@ void orcf_merkle_commit(const uint32_t* const* mats, const size_t* widths, size_
         for (size_t i = 0; i < n_mats; i++) for (size_t c = 0; c < widths[i]; c++) cols[k++] = mats[i] + c * h;
     }
     const V vr2 = VSET(R2), one = VSET(1);
+    if (h >= 16 * P2_NB) {
+        /* 16*P2_NB rows per visit of a column group: P2_NB interleaved sponges, and P2_NB consecutive cache lines per column touched
+           (a row block walks total_w columns that are megabytes apart: one TLB miss per column visit) */
 #pragma omp parallel for schedule(static)
-    for (long r0 = 0; r0 < (long)h; r0 += 16) {
-        V s[16];
-        for (int i = 0; i < 16; i++) s[i] = _mm512_setzero_si512();
-        for (size_t c0 = 0; c0 < total_w; c0 += 8) {
-            const size_t k = total_w - c0 < 8 ? total_w - c0 : 8;
-            for (size_t j = 0; j < k; j++) s[j] = v_mul(_mm512_loadu_si512(cols[c0 + j] + r0), vr2);     /* overwrite-mode absorb */
-            v_permute(s);
+        for (long r0 = 0; r0 < (long)h; r0 += 16 * P2_NB) {
+            V s[P2_NB][16];
+            for (int b = 0; b < P2_NB; b++) for (int i = 0; i < 16; i++) s[b][i] = _mm512_setzero_si512();
+            for (size_t c0 = 0; c0 < total_w; c0 += 8) {
+                const size_t k = total_w - c0 < 8 ? total_w - c0 : 8;
+                for (size_t j = 0; j < k; j++)
+                    for (int b = 0; b < P2_NB; b++) s[b][j] = v_mul(_mm512_loadu_si512(cols[c0 + j] + r0 + 16 * b), vr2);     /* overwrite-mode absorb */
+                v_permute_nb(s);
+            }
+            for (int b = 0; b < P2_NB; b++) {
+                uint32_t tmp[8][16];
+                for (int i = 0; i < 8; i++) _mm512_storeu_si512(tmp[i], v_mul(s[b][i], one));
+                for (int l = 0; l < 16; l++) for (int i = 0; i < 8; i++) layers[8 * ((size_t)r0 + 16 * b + l) + i] = tmp[i][l];
+            }
         }
-        uint32_t tmp[8][16];
-        for (int i = 0; i < 8; i++) _mm512_storeu_si512(tmp[i], v_mul(s[i], one));
-        for (int l = 0; l < 16; l++) for (int i = 0; i < 8; i++) layers[8 * ((size_t)r0 + l) + i] = tmp[i][l];
+    } else {
+        for (size_t r0 = 0; r0 < h; r0 += 16) {
+            V s[16];
+            for (int i = 0; i < 16; i++) s[i] = _mm512_setzero_si512();
+            for (size_t c0 = 0; c0 < total_w; c0 += 8) {
+                const size_t k = total_w - c0 < 8 ? total_w - c0 : 8;
+                for (size_t j = 0; j < k; j++) s[j] = v_mul(_mm512_loadu_si512(cols[c0 + j] + r0), vr2);
+                v_permute(s);
+            }
+            uint32_t tmp[8][16];
+            for (int i = 0; i < 8; i++) _mm512_storeu_si512(tmp[i], v_mul(s[i], one));
+            for (int l = 0; l < 16; l++) for (int i = 0; i < 8; i++) layers[8 * (r0 + l) + i] = tmp[i][l];
+        }
     }
     free(cols);
     uint32_t* prev = layers;

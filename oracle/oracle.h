@@ -162,6 +162,8 @@ void orcf_logup_fold(const uint32_t* lde, const uint32_t* perm_lde, unsigned log
 void orcf_deep_quotient_groups(const uint32_t* const* cols, const uint32_t* group_of_col, size_t n_cols, const uint32_t* zs, size_t n_groups,
                                unsigned log_m, uint32_t shift, const uint32_t gamma[4], const uint32_t* ys, uint32_t* out);
 int orc_num_threads(void);
+void* orc_big_alloc(size_t bytes);   /* 2 MB aligned, MADV_HUGEPAGE */
+void orc_big_free(void* p);
 #ifdef __cplusplus
 }
 #endif

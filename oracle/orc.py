@@ -460,3 +460,12 @@ def fast_deep_quotient(mats, shift, zeta, gamma, ys):
     out = np.empty((m, 4), dtype=np.uint32)
     lib().orcf_deep_quotient(ptrs, widths, C.c_size_t(len(mats)), C.c_uint(m.bit_length() - 1), C.c_uint32(shift), _p(z), _p(g), _p(y), _p(out))
     return out
+
+
+def big_array(shape):
+    """uint32 array backed by orc_big_alloc (2 MB aligned, transparent huge pages advised) -- for the full-size CPU run"""
+    n = int(np.prod(shape))
+    lib().orc_big_alloc.restype = C.c_void_p
+    ptr = lib().orc_big_alloc(C.c_size_t(4 * n))
+    buf = (C.c_uint32 * n).from_address(ptr)
+    return np.frombuffer(buf, dtype=np.uint32).reshape(shape)

@@ -21,6 +21,21 @@
 #include <string.h>
 #include <time.h>
 
+/* big working buffers: 2 MB aligned and advised to transparent huge pages -- the per-row kernels walk thousands of columns that are
+   megabytes apart, which thrashes the TLB with 4 KB pages */
+#include <sys/mman.h>
+void* orc_big_alloc(size_t bytes) {
+    const size_t al = (size_t)2 << 20;
+    bytes = (bytes + al - 1) / al * al;
+    void* p = aligned_alloc(al, bytes ? bytes : al);
+#ifdef MADV_HUGEPAGE
+    if (p) madvise(p, bytes ? bytes : al, MADV_HUGEPAGE);
+#endif
+    return p;
+}
+void orc_big_free(void* p) { free(p); }
+#define BIG(n_words) ((uint32_t*)orc_big_alloc((size_t)(n_words) * sizeof(uint32_t)))
+
 static double now_s(void) { struct timespec t; clock_gettime(CLOCK_MONOTONIC, &t); return t.tv_sec + 1e-9 * t.tv_nsec; }
 
 typedef struct {
@@ -113,11 +128,11 @@ void orc_prove_segment(const uint32_t* trace, unsigned log_n, size_t width, cons
 
     /* stage 1 + 3a: main trace commit */
     double t0 = now_s();
-    uint32_t* lde = (uint32_t*)malloc(width * m * sizeof(uint32_t));
+    uint32_t* lde = BIG(width * m);
     ops->lde_batch(trace, log_n, width, log_blowup, BB_GENERATOR, lde);
     double t1 = now_s();
     st[0] = t1 - t0;
-    uint32_t* layers = (uint32_t*)malloc((2 * m) * 8 * sizeof(uint32_t));
+    uint32_t* layers = BIG((2 * m) * 8);
     const uint32_t* mats1[1] = {lde};
     ops->merkle_commit(mats1, &width, 1, log_m, layers);
     memcpy(proof->trace_root, layers + 8 * (2 * m - 2), 32);
@@ -137,14 +152,14 @@ void orc_prove_segment(const uint32_t* trace, unsigned log_n, size_t width, cons
         wp = 4 * (n_chunks + 1);
         orc_challenger_sample_ext(&ch, proof->logup_alpha);
         orc_challenger_sample_ext(&ch, proof->logup_beta);
-        perm = (uint32_t*)malloc(wp * n * sizeof(uint32_t));
+        perm = BIG(wp * n);
         ops->logup_perm_trace(trace, log_n, air->ibc, air->ispans, air->ints, air->n_ints, chunk_start, n_chunks, proof->logup_alpha,
                              proof->logup_beta, perm, proof->cumulative_sum);
         double t3 = now_s();
         st[2] = t3 - t2;
-        perm_lde = (uint32_t*)malloc(wp * m * sizeof(uint32_t));
+        perm_lde = BIG(wp * m);
         ops->lde_batch(perm, log_n, wp, log_blowup, BB_GENERATOR, perm_lde);
-        layers_p = (uint32_t*)malloc((2 * m) * 8 * sizeof(uint32_t));
+        layers_p = BIG((2 * m) * 8);
         const uint32_t* matsp[1] = {perm_lde};
         ops->merkle_commit(matsp, &wp, 1, log_m, layers_p);
         memcpy(proof->perm_root, layers_p + 8 * (2 * m - 2), 32);
@@ -159,7 +174,7 @@ void orc_prove_segment(const uint32_t* trace, unsigned log_n, size_t width, cons
     double t4 = now_s();
     uint32_t* q = (uint32_t*)malloc(8 * n * sizeof(uint32_t));
     {
-        uint32_t* acc4 = (uint32_t*)malloc(4 * m * sizeof(uint32_t));
+        uint32_t* acc4 = BIG(4 * m);
         ops->constraint_fold(air->bc, air->spans, air->n_constraints, lde, m, proof->alpha, acc4);
         if (air->n_ints)
             ops->logup_fold(lde, perm_lde, log_n, BB_GENERATOR, air->ibc, air->ispans, air->ints, air->n_ints, chunk_start, n_chunks,
@@ -177,7 +192,7 @@ void orc_prove_segment(const uint32_t* trace, unsigned log_n, size_t width, cons
     st[4] = t5 - t4;
 
     /* quotient commit: chunk b holds evals over g*w_{2N}^b*H in bit-reversed order -> natural, LDE with shift g/s_b */
-    uint32_t* qlde = (uint32_t*)malloc(8 * m * sizeof(uint32_t));
+    uint32_t* qlde = BIG(8 * m);
     uint32_t w2n = bb_root_of_unity(log_n + 1);
     uint32_t* nat = (uint32_t*)malloc(8 * n * sizeof(uint32_t));
     for (int b = 0; b < 2; b++) {
@@ -189,7 +204,7 @@ void orc_prove_segment(const uint32_t* trace, unsigned log_n, size_t width, cons
     free(q);
     const uint32_t* mats2[2] = {qlde, qlde + 4 * m};
     size_t w2[2] = {4, 4};
-    uint32_t* layers_q = (uint32_t*)malloc((2 * m) * 8 * sizeof(uint32_t));
+    uint32_t* layers_q = BIG((2 * m) * 8);
     ops->merkle_commit(mats2, w2, 2, log_m, layers_q);
     memcpy(proof->quotient_root, layers_q + 8 * (2 * m - 2), 32);
     orc_challenger_observe(&ch, proof->quotient_root, 8);
@@ -219,7 +234,7 @@ void orc_prove_segment(const uint32_t* trace, unsigned log_n, size_t width, cons
     orc_challenger_sample_ext(&ch, proof->gamma);
 
     /* stage 3b: FRI commit phase on the reduced opening over g*H' */
-    uint32_t* f = (uint32_t*)malloc(4 * m * sizeof(uint32_t));
+    uint32_t* f = BIG(4 * m);
     {
         const uint32_t** cols = (const uint32_t**)malloc(n_open * sizeof(*cols));
         uint32_t* grp = (uint32_t*)malloc(n_open * sizeof(uint32_t));

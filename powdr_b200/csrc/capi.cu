@@ -21,6 +21,7 @@
 #include "logup_jit.cuh"
 #include "ntt.cuh"
 #include "ntt_fast.cuh"
+#include "ntt_tma.cuh"
 #include "poseidon2.cuh"
 #include "tracegen.cuh"
 
@@ -493,7 +494,9 @@ void ntt_inverse_cols(pb_ctx* ctx, const NttGeom& g, const TwiddleSet* tw, const
     }
     const size_t total_blocks = (size_t)nb << g.n_hi;
     const unsigned gx = (unsigned)((total_blocks + ((size_t)1 << g.log_lc_lo) - 1) >> g.log_lc_lo);
-    if (!g.fast || !nttf::launch_transposed(true, g.n, g.n_lo, dim3(gx), ctx->stream, src, N, coef, 0, total_blocks, tw->d_inv, tw->ninv))
+    // n_lo == 10: the TMA-staged kernel (ntt_tma.cuh); otherwise the LDG/STS-staged specialisations, then the generic pass
+    if (g.fast && ntttma::launch_transposed(true, g.n, g.n_lo, ctx->stream, src, coef, 0, total_blocks, (size_t)nb * N, (size_t)nb * N, tw->d_inv, tw->ninv)) {
+    } else if (!g.fast || !nttf::launch_transposed(true, g.n, g.n_lo, dim3(gx), ctx->stream, src, N, coef, 0, total_blocks, tw->d_inv, tw->ninv))
         ntt::transposed_pass_kernel<true><<<dim3(gx), ntt::THREADS, g.smem_lo, ctx->stream>>>(src, N, coef, g.n, g.n_lo, g.log_lc_lo, 0,
                                                                                              total_blocks, tw->d_inv, tw->ninv, g.r_inv_lo);
     LAUNCHED(ctx);
@@ -507,7 +510,9 @@ void ntt_forward_cols(pb_ctx* ctx, const NttGeom& g, const TwiddleSet* tw, int l
     const int cosets = 1 << log_blowup;
     const size_t total_blocks = (size_t)nb << g.n_hi;
     const unsigned gx = (unsigned)((total_blocks + ((size_t)1 << g.log_lc_lo) - 1) >> g.log_lc_lo);
-    if (!g.fast || !nttf::launch_transposed(false, g.n, g.n_lo, dim3(gx, 1, (unsigned)cosets), ctx->stream, coef, N, scratch, log_blowup,
+    if (g.fast && ntttma::launch_transposed(false, g.n, g.n_lo, ctx->stream, coef, scratch, log_blowup, total_blocks, (size_t)nb * N,
+                                            (size_t)nb * N * cosets, tw->d_fwd, make_uint2(0u, 0u))) {
+    } else if (!g.fast || !nttf::launch_transposed(false, g.n, g.n_lo, dim3(gx, 1, (unsigned)cosets), ctx->stream, coef, N, scratch, log_blowup,
                                             total_blocks, tw->d_fwd, make_uint2(0u, 0u)))
         ntt::transposed_pass_kernel<false><<<dim3(gx, 1, (unsigned)cosets), ntt::THREADS, g.smem_lo, ctx->stream>>>(
             coef, N, scratch, g.n, g.n_lo, g.log_lc_lo, log_blowup, total_blocks, tw->d_fwd, make_uint2(0u, 0u), g.r_fwd_lo);
@@ -868,29 +873,46 @@ static int deep_quotient_groups_m(pb_ctx* ctx, const std::vector<const uint32_t*
     if (rc) return rc;
     CK(cudaMemcpyAsync(ctx->ws_gp.p, gs.data(), gs.size() * sizeof(uint4), cudaMemcpyHostToDevice, ctx->stream));
     CK(cudaStreamSynchronize(ctx->stream));           // gs is a host temporary
-    for (size_t q = 0; q < zs.size(); q++) {
-        // runs of equally spaced columns of this group with consecutive exponents
-        deep::DeepSegs segs{};
-        for (size_t j = 0; j < n_cols;) {
-            if (grp[j] != q) { j++; continue; }
-            if (segs.n == deep::DQ_MAX_SEGS) return PB_ERR_UNSUPPORTED;
-            size_t k = j + 1;
-            const ptrdiff_t st = (k < n_cols && grp[k] == q) ? cols[k] - cols[j] : 0;
-            while (k < n_cols && grp[k] == q && st > 0 && cols[k] - cols[k - 1] == st) k++;
-            if (st <= 0) k = j + 1;
-            segs.base[segs.n] = cols[j];
-            segs.stride[segs.n] = st > 0 ? (size_t)st : 0;
-            segs.count[segs.n] = (uint32_t)(k - j);
-            segs.gp_off[segs.n] = (uint32_t)j;
-            segs.n++;
-            j = k;
-        }
-        if (segs.n == 0) continue;
-        deep::deep_quotient_kernel<<<(unsigned)((M + 255) / 256), 256, 0, ctx->stream>>>(segs, M, (int)log_m, row0, shift_m, h_root_of_unity_m((int)log_m),
-                                                                                        reinterpret_cast<const uint4*>(ctx->ws_gp.p), ysum[q], zs[q],
-                                                                                        reinterpret_cast<uint4*>(d_out), q > 0 ? 1 : 0);
-        LAUNCHED(ctx);
+    // one launch: columns of group 0 in runs of equal stride; a run of group-1 columns that repeats a group-0 run (same base, stride,
+    // count: the permutation trace opened at zeta and at zeta*w) is attached to it, so those columns are read from HBM once
+    if (zs.size() > 2) return PB_ERR_UNSUPPORTED;
+    deep::DeepSegs segs{};
+    for (size_t j = 0; j < n_cols;) {
+        if (grp[j] != 0) { j++; continue; }
+        if (segs.n == deep::DQ_MAX_SEGS) return PB_ERR_UNSUPPORTED;
+        size_t k = j + 1;
+        const ptrdiff_t st = (k < n_cols && grp[k] == 0) ? cols[k] - cols[j] : 0;
+        while (k < n_cols && grp[k] == 0 && st > 0 && cols[k] - cols[k - 1] == st) k++;
+        if (st <= 0) k = j + 1;
+        segs.base[segs.n] = cols[j];
+        segs.stride[segs.n] = st > 0 ? (size_t)st : 0;
+        segs.count[segs.n] = (uint32_t)(k - j);
+        segs.gp_off[segs.n] = (uint32_t)j;
+        segs.gp_off2[segs.n] = deep::DQ_NO_SECOND;
+        segs.n++;
+        j = k;
     }
+    for (size_t j = 0; j < n_cols;) {           // group-1 runs must mirror a group-0 run
+        if (grp[j] != 1) { j++; continue; }
+        size_t k = j + 1;
+        while (k < n_cols && grp[k] == 1) k++;
+        bool placed = false;
+        for (int sgi = 0; sgi < segs.n && !placed; sgi++)
+            if (segs.base[sgi] == cols[j] && segs.count[sgi] == (uint32_t)(k - j) && segs.gp_off2[sgi] == deep::DQ_NO_SECOND &&
+                (k - j < 2 || (size_t)(cols[j + 1] - cols[j]) == segs.stride[sgi])) {
+                bool same = true;
+                for (size_t t = j; t < k && same; t++) same = cols[t] == segs.base[sgi] + (t - j) * segs.stride[sgi];
+                if (same) { segs.gp_off2[sgi] = (uint32_t)j; placed = true; }
+            }
+        if (!placed) return PB_ERR_UNSUPPORTED;
+        j = k;
+    }
+    const bool two = zs.size() == 2;
+    deep::deep_quotient_kernel<<<(unsigned)((M + 255) / 256), 256, 0, ctx->stream>>>(segs, M, (int)log_m, row0, shift_m, h_root_of_unity_m((int)log_m),
+                                                                                    reinterpret_cast<const uint4*>(ctx->ws_gp.p), ysum[0], zs[0],
+                                                                                    two ? ysum[1] : ysum[0], two ? zs[1] : zs[0], two ? 1 : 0,
+                                                                                    reinterpret_cast<uint4*>(d_out));
+    LAUNCHED(ctx);
     CK(cudaGetLastError());
     return 0;
 }

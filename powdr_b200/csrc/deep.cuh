@@ -161,23 +161,48 @@ struct DeepSegs {
     size_t stride[DQ_MAX_SEGS];            // words between consecutive columns
     uint32_t count[DQ_MAX_SEGS];
     uint32_t gp_off[DQ_MAX_SEGS];          // gamma exponent of the run's first column
+    uint32_t gp_off2[DQ_MAX_SEGS];         // DQ_NO_SECOND, or the exponent under which the same columns are ALSO opened at the second point
     int n;
 };
+constexpr uint32_t DQ_NO_SECOND = 0xffffffffu;
 
 __device__ __forceinline__ void dq_mac(Acc96 (&acc)[4], uint32_t f, const uint4 g) {
     mac96(acc[0], f, g.x); mac96(acc[1], f, g.y); mac96(acc[2], f, g.z); mac96(acc[3], f, g.w);
 }
 
 __global__ void __launch_bounds__(256) deep_quotient_kernel(DeepSegs segs, size_t m, int log_m, size_t row0, uint32_t shift_m, uint32_t omega_m,
-                                                            const uint4* __restrict__ gpow, bb::E4 ysum, bb::E4 zeta,
-                                                            uint4* __restrict__ out, int accumulate) {
+                                                            const uint4* __restrict__ gpow, bb::E4 ysum, bb::E4 zeta, bb::E4 ysum2, bb::E4 zeta2,
+                                                            int two_points, uint4* __restrict__ out) {
     __shared__ uint4 sg[DQ_CHUNK];
     const size_t r = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     const bool live = r < m;
     const size_t rr = live ? r : m - 1;           // dead threads of the last CTA still take part in the staging barriers
     Acc96 acc[4] = {{0u, 0u, 0u}, {0u, 0u, 0u}, {0u, 0u, 0u}, {0u, 0u, 0u}};
+    Acc96 acc2[4] = {{0u, 0u, 0u}, {0u, 0u, 0u}, {0u, 0u, 0u}, {0u, 0u, 0u}};      // columns opened at the second point (read once, used twice)
     for (int sgi = 0; sgi < segs.n; sgi++) {
         const size_t jglob = segs.gp_off[sgi];
+        if (segs.gp_off2[sgi] != DQ_NO_SECOND) {
+            // run opened at both points: one load feeds both accumulators
+            const size_t stride2 = segs.stride[sgi], jglob2 = segs.gp_off2[sgi];
+            const uint32_t count2 = segs.count[sgi];
+            const uint32_t* p2 = segs.base[sgi] + rr;
+            for (uint32_t c0 = 0; c0 < count2; c0 += DQ_CHUNK / 2) {
+                const uint32_t nc = min((uint32_t)(DQ_CHUNK / 2), count2 - c0);
+                __syncthreads();
+                for (uint32_t i = threadIdx.x; i < nc; i += blockDim.x) { sg[i] = __ldg(gpow + jglob + c0 + i); sg[DQ_CHUNK / 2 + i] = __ldg(gpow + jglob2 + c0 + i); }
+                __syncthreads();
+                uint32_t j = 0;
+                for (; j + 8 <= nc; j += 8) {
+                    uint32_t f[8];
+#pragma unroll
+                    for (int u = 0; u < 8; u++) f[u] = __ldg(p2 + (size_t)(c0 + j + u) * stride2);
+#pragma unroll
+                    for (int u = 0; u < 8; u++) { dq_mac(acc, f[u], sg[j + u]); dq_mac(acc2, f[u], sg[DQ_CHUNK / 2 + j + u]); }
+                }
+                for (; j < nc; j++) { const uint32_t f = __ldg(p2 + (size_t)(c0 + j) * stride2); dq_mac(acc, f, sg[j]); dq_mac(acc2, f, sg[DQ_CHUNK / 2 + j]); }
+            }
+            continue;
+        }
         const size_t stride = segs.stride[sgi];
         const uint32_t count = segs.count[sgi];
         for (uint32_t c0 = 0; c0 < count; c0 += DQ_CHUNK) {
@@ -215,9 +240,12 @@ __global__ void __launch_bounds__(256) deep_quotient_kernel(DeepSegs segs, size_
     const uint32_t x = bb::mul(shift_m, bb::pow(omega_m, (uint64_t)(__brev((uint32_t)(row0 + r)) >> (32 - log_m))));
     bb::E4 d = {{bb::sub(x, zeta.c[0]), bb::neg(zeta.c[1]), bb::neg(zeta.c[2]), bb::neg(zeta.c[3])}};
     bb::E4 v = bb::e4_mul(a, e4_inv(d));
-    if (accumulate) {
-        const uint4 o = out[r];
-        v.c[0] = bb::add(v.c[0], o.x); v.c[1] = bb::add(v.c[1], o.y); v.c[2] = bb::add(v.c[2], o.z); v.c[3] = bb::add(v.c[3], o.w);
+    if (two_points) {
+        bb::E4 a2;
+#pragma unroll
+        for (int l = 0; l < 4; l++) a2.c[l] = bb::sub(acc96_mod(acc2[l]), ysum2.c[l]);
+        bb::E4 d2 = {{bb::sub(x, zeta2.c[0]), bb::neg(zeta2.c[1]), bb::neg(zeta2.c[2]), bb::neg(zeta2.c[3])}};
+        v = bb::e4_add(v, bb::e4_mul(a2, e4_inv(d2)));
     }
     out[r] = make_uint4(v.c[0], v.c[1], v.c[2], v.c[3]);
 }

@@ -179,122 +179,143 @@ inline Val emit_expr(std::string& src, const std::vector<uint32_t>& code, air::S
     return st.back();
 }
 
-constexpr size_t GROUP_CHUNKS = 8;
+constexpr size_t GROUP_CHUNKS_MAX = 8;
+// tuning knobs of the generated kernels (experiments: PB_LOGUP_GROUP / PB_LOGUP_BLOCK / PB_LOGUP_MINB)
+// chunks per generated function: measured on B200 at 2^18 rows x 1734 interactions (profiles/README.md): permutation kernel best at 2
+// (one inversion per 2 chunks), fold kernel at 1 -- fewer live Ext4 values beat the amortised inversion
+inline size_t group_chunks(bool for_perm) {
+    if (const char* e = getenv(for_perm ? "PB_LOGUP_GROUP_PERM" : "PB_LOGUP_GROUP_FOLD")) return std::min<size_t>(GROUP_CHUNKS_MAX, std::max<size_t>(1, (size_t)atol(e)));
+    if (const char* e = getenv("PB_LOGUP_GROUP")) return std::min<size_t>(GROUP_CHUNKS_MAX, std::max<size_t>(1, (size_t)atol(e)));
+    return for_perm ? 2 : 1;
+}
+inline unsigned block_threads() { if (const char* e = getenv("PB_LOGUP_BLOCK")) return (unsigned)std::min(1024l, std::max(32l, atol(e))); return 128; }
+inline unsigned min_blocks() { if (const char* e = getenv("PB_LOGUP_MINB")) return (unsigned)std::max(0l, atol(e)); return 0; }
 
-// source of one module covering chunks [c_begin, c_end): both kernels.  `record_lits`: fill p.lits (done once, on the first pass).
+// source of one module covering chunks [c_begin, c_end): both kernels.  lits_out: literal arguments found (recorded once per interaction).
 inline std::string generate(const std::vector<uint32_t>& code, const std::vector<air::Span>& spans, const std::vector<uint32_t>& pool, const Program& p,
                             size_t c_begin, size_t c_end, std::vector<LitArg>* lits_out) {
     std::string src = airjit::PRELUDE;
     src += LU_PRELUDE;
     char buf[512];
-    size_t n_groups = 0;
     std::string perm_calls, fold_calls;
-    for (size_t cb = c_begin; cb < c_end; cb += GROUP_CHUNKS, n_groups++) {
-        const size_t ce = std::min(c_end, cb + GROUP_CHUNKS);
-        // ---- shared: (m_i, d_i) of the group's interactions ----
-        std::string body, loads;
-        std::unordered_map<uint32_t, std::string> cols;
-        size_t vid = 0;
-        std::vector<std::string> m_name(p.chunk_start[ce] - p.chunk_start[cb]);
-        const uint32_t i0 = p.chunk_start[cb];
-        for (uint32_t i = i0; i < p.chunk_start[ce]; i++) {
-            const Interaction& it = p.ints[i];
-            Val mv = emit_expr(body, code, spans[it.span0], pool, vid, cols, loads);
-            snprintf(buf, sizeof buf, "0x%08xu", mv.mont);
-            m_name[i - i0] = mv.lit ? std::string(buf) : mv.name;
-            snprintf(buf, sizeof buf, " E4 d%u = ld4(kc + %u);\n", i, i);
-            body += buf;
-            std::vector<std::pair<uint32_t, std::string>> dyn;       // (j, value name)
-            for (uint32_t j = 0; j < it.num_args; j++) {
-                Val av = emit_expr(body, code, spans[it.span0 + 1 + j], pool, vid, cols, loads);
-                if (av.lit) { if (lits_out) lits_out->push_back(LitArg{i, j, av.mont}); }
-                else dyn.emplace_back(j, av.name);
-            }
-            size_t q = 0;
-            for (; q + 2 <= dyn.size(); q += 2) {
-                snprintf(buf, sizeof buf, " d%u = e_mac2(d%u, ld4(bt + %u), %s, ld4(bt + %u), %s);\n", i, i, dyn[q].first, dyn[q].second.c_str(),
-                         dyn[q + 1].first, dyn[q + 1].second.c_str());
+    const unsigned BT = block_threads(), MINB = min_blocks();
+    // one __noinline__ function per group of chunks; the two kernels use their own group size (the permutation kernel amortises one
+    // Ext4 inversion over the group, the fold kernel has nothing to share between chunks and runs best with the fewest live values)
+    for (int kind = 0; kind < 2; kind++) {
+        const bool for_perm = kind == 0;
+        const size_t GROUP = group_chunks(for_perm);
+        size_t n_groups = 0;
+        for (size_t cb = c_begin; cb < c_end; cb += GROUP, n_groups++) {
+            const size_t ce = std::min(c_end, cb + GROUP);
+            // ---- (m_i, d_i) of the group's interactions ----
+            std::string body, loads;
+            std::unordered_map<uint32_t, std::string> cols;
+            size_t vid = 0;
+            std::vector<std::string> m_name(p.chunk_start[ce] - p.chunk_start[cb]);
+            const uint32_t i0 = p.chunk_start[cb];
+            for (uint32_t i = i0; i < p.chunk_start[ce]; i++) {
+                const Interaction& it = p.ints[i];
+                Val mv = emit_expr(body, code, spans[it.span0], pool, vid, cols, loads);
+                snprintf(buf, sizeof buf, "0x%08xu", mv.mont);
+                m_name[i - i0] = mv.lit ? std::string(buf) : mv.name;
+                snprintf(buf, sizeof buf, " E4 d%u = ld4(kc + %u);\n", i, i);
                 body += buf;
-            }
-            if (q < dyn.size()) {
-                snprintf(buf, sizeof buf, " d%u = e_mac(d%u, ld4(bt + %u), %s);\n", i, i, dyn[q].first, dyn[q].second.c_str());
-                body += buf;
-            }
-        }
-        // per chunk: D<c>, N<c> (N is Ext4; for a one-interaction chunk the numerator is the base value m)
-        std::string chunks;
-        std::vector<bool> single(ce - cb);
-        for (size_t c = cb; c < ce; c++) {
-            const uint32_t a = p.chunk_start[c], e = p.chunk_start[c + 1];
-            single[c - cb] = e - a == 1;
-            if (e - a == 1) {
-                snprintf(buf, sizeof buf, " const E4 D%zu = d%u;\n", c, a);
-                chunks += buf;
-            } else {
-                snprintf(buf, sizeof buf, " E4 D%zu = e_mul(d%u, d%u); E4 N%zu = e_lin2(d%u, %s, d%u, %s);\n", c, a, a + 1, c, a + 1, m_name[a - i0].c_str(), a,
-                         m_name[a + 1 - i0].c_str());
-                chunks += buf;
-                for (uint32_t i = a + 2; i < e; i++) {
-                    snprintf(buf, sizeof buf, " N%zu = e_add(e_mul(N%zu, d%u), e_scale(D%zu, %s)); D%zu = e_mul(D%zu, d%u);\n", c, c, i, c, m_name[i - i0].c_str(), c, c, i);
-                    chunks += buf;
+                std::vector<std::pair<uint32_t, std::string>> dyn;       // (j, value name)
+                for (uint32_t j = 0; j < it.num_args; j++) {
+                    Val av = emit_expr(body, code, spans[it.span0 + 1 + j], pool, vid, cols, loads);
+                    if (av.lit) { if (lits_out && for_perm) lits_out->push_back(LitArg{i, j, av.mont}); }
+                    else dyn.emplace_back(j, av.name);
+                }
+                size_t q = 0;
+                for (; q + 2 <= dyn.size(); q += 2) {
+                    snprintf(buf, sizeof buf, " d%u = e_mac2(d%u, ld4(bt + %u), %s, ld4(bt + %u), %s);\n", i, i, dyn[q].first, dyn[q].second.c_str(),
+                             dyn[q + 1].first, dyn[q + 1].second.c_str());
+                    body += buf;
+                }
+                if (q < dyn.size()) {
+                    snprintf(buf, sizeof buf, " d%u = e_mac(d%u, ld4(bt + %u), %s);\n", i, i, dyn[q].first, dyn[q].second.c_str());
+                    body += buf;
                 }
             }
-        }
-        // ---- perm kernel group: batch inversion of D over the group's chunks ----
-        snprintf(buf, sizeof buf, "__device__ __noinline__ E4 pg%zu(const u32* __restrict__ b, u64 h, const uint4* __restrict__ kc, const uint4* __restrict__ bt, u32* __restrict__ perm) {\n", n_groups);
-        src += buf;
-        src += loads + body + chunks;
-        const size_t G = ce - cb;
-        for (size_t k = 1; k < G; k++) {
-            if (k == 1) snprintf(buf, sizeof buf, " E4 p1 = e_mul(D%zu, D%zu);\n", cb, cb + 1);
-            else snprintf(buf, sizeof buf, " E4 p%zu = e_mul(p%zu, D%zu);\n", k, k - 1, cb + k);
-            src += buf;
-        }
-        if (G == 1) snprintf(buf, sizeof buf, " E4 iv = e_inv(D%zu);\n", cb);
-        else snprintf(buf, sizeof buf, " E4 iv = e_inv(p%zu);\n", G - 1);
-        src += buf;
-        src += " E4 sum; sum.a = 0u; sum.b = 0u; sum.c = 0u; sum.d = 0u; E4 t;\n";
-        for (size_t k = G; k-- > 0;) {
-            const size_t c = cb + k;
-            // inverse of D_c = iv * prefix_{k-1};  then iv *= D_c
-            std::string invname;
-            if (k == 0) invname = "iv";
-            else {
-                if (k == 1) snprintf(buf, sizeof buf, " t = e_mul(iv, D%zu); iv = e_mul(iv, D%zu);\n", cb, c);
-                else snprintf(buf, sizeof buf, " t = e_mul(iv, p%zu); iv = e_mul(iv, D%zu);\n", k - 1, c);
-                src += buf;
-                invname = "t";
+            // per chunk: D<c>, N<c> (N is Ext4; for a one-interaction chunk the numerator is the base value m)
+            std::string chunks;
+            std::vector<bool> single(ce - cb);
+            for (size_t c = cb; c < ce; c++) {
+                const uint32_t a = p.chunk_start[c], e = p.chunk_start[c + 1];
+                single[c - cb] = e - a == 1;
+                if (e - a == 1) {
+                    snprintf(buf, sizeof buf, " const E4 D%zu = d%u;\n", c, a);
+                    chunks += buf;
+                } else {
+                    snprintf(buf, sizeof buf, " E4 D%zu = e_mul(d%u, d%u); E4 N%zu = e_lin2(d%u, %s, d%u, %s);\n", c, a, a + 1, c, a + 1, m_name[a - i0].c_str(), a,
+                             m_name[a + 1 - i0].c_str());
+                    chunks += buf;
+                    for (uint32_t i = a + 2; i < e; i++) {
+                        snprintf(buf, sizeof buf, " N%zu = e_add(e_mul(N%zu, d%u), e_scale(D%zu, %s)); D%zu = e_mul(D%zu, d%u);\n", c, c, i, c, m_name[i - i0].c_str(), c, c, i);
+                        chunks += buf;
+                    }
+                }
             }
-            if (single[k]) snprintf(buf, sizeof buf, " t = e_scale(%s, %s);\n", invname.c_str(), m_name[p.chunk_start[c] - i0].c_str());
-            else snprintf(buf, sizeof buf, " t = e_mul(N%zu, %s);\n", c, invname.c_str());
-            src += buf;
-            snprintf(buf, sizeof buf, " perm[%zuull * h] = t.a; perm[%zuull * h] = t.b; perm[%zuull * h] = t.c; perm[%zuull * h] = t.d; sum = e_add(sum, t);\n",
-                     4 * c, 4 * c + 1, 4 * c + 2, 4 * c + 3);
-            src += buf;
+            if (for_perm) {
+                // ---- perm kernel group: batch inversion of D over the group's chunks ----
+                snprintf(buf, sizeof buf, "__device__ __noinline__ E4 pg%zu(const u32* __restrict__ b, u64 h, const uint4* __restrict__ kc, const uint4* __restrict__ bt, u32* __restrict__ perm) {\n", n_groups);
+                src += buf;
+                src += loads + body + chunks;
+                const size_t G = ce - cb;
+                for (size_t k = 1; k < G; k++) {
+                    if (k == 1) snprintf(buf, sizeof buf, " E4 p1 = e_mul(D%zu, D%zu);\n", cb, cb + 1);
+                    else snprintf(buf, sizeof buf, " E4 p%zu = e_mul(p%zu, D%zu);\n", k, k - 1, cb + k);
+                    src += buf;
+                }
+                if (G == 1) snprintf(buf, sizeof buf, " E4 iv = e_inv(D%zu);\n", cb);
+                else snprintf(buf, sizeof buf, " E4 iv = e_inv(p%zu);\n", G - 1);
+                src += buf;
+                src += " E4 sum; sum.a = 0u; sum.b = 0u; sum.c = 0u; sum.d = 0u; E4 t;\n";
+                for (size_t k = G; k-- > 0;) {
+                    const size_t c = cb + k;
+                    // inverse of D_c = iv * prefix_{k-1};  then iv *= D_c
+                    std::string invname;
+                    if (k == 0) invname = "iv";
+                    else {
+                        if (k == 1) snprintf(buf, sizeof buf, " t = e_mul(iv, D%zu); iv = e_mul(iv, D%zu);\n", cb, c);
+                        else snprintf(buf, sizeof buf, " t = e_mul(iv, p%zu); iv = e_mul(iv, D%zu);\n", k - 1, c);
+                        src += buf;
+                        invname = "t";
+                    }
+                    if (single[k]) snprintf(buf, sizeof buf, " t = e_scale(%s, %s);\n", invname.c_str(), m_name[p.chunk_start[c] - i0].c_str());
+                    else snprintf(buf, sizeof buf, " t = e_mul(N%zu, %s);\n", c, invname.c_str());
+                    src += buf;
+                    snprintf(buf, sizeof buf, " perm[%zuull * h] = t.a; perm[%zuull * h] = t.b; perm[%zuull * h] = t.c; perm[%zuull * h] = t.d; sum = e_add(sum, t);\n",
+                             4 * c, 4 * c + 1, 4 * c + 2, 4 * c + 3);
+                    src += buf;
+                }
+                src += " return sum;\n}\n";
+                snprintf(buf, sizeof buf, "    rs = e_add(rs, pg%zu(b, n, kc, bt, pr));\n", n_groups);
+                perm_calls += buf;
+            } else {
+                // ---- fold kernel group ----
+                snprintf(buf, sizeof buf, "__device__ __noinline__ void fg%zu(const u32* __restrict__ b, u64 h, const u32* __restrict__ pl, const uint4* __restrict__ kc, const uint4* __restrict__ bt, const uint4* __restrict__ apl, E4& acc, E4& S) {\n", n_groups);
+                src += buf;
+                src += loads + body + chunks;
+                for (size_t c = cb; c < ce; c++) {
+                    if (single[c - cb])
+                        snprintf(buf, sizeof buf, " { E4 pc = ldp(pl, %zuull, h); S = e_add(S, pc); E4 L = e_mul(pc, D%zu); L.a = sub(L.a, %s); acc = e_add(acc, e_mul(ld4(apl + %zu), L)); }\n",
+                                 c, c, m_name[p.chunk_start[c] - i0].c_str(), c);
+                    else
+                        snprintf(buf, sizeof buf, " { E4 pc = ldp(pl, %zuull, h); S = e_add(S, pc); E4 L = e_sub(e_mul(pc, D%zu), N%zu); acc = e_add(acc, e_mul(ld4(apl + %zu), L)); }\n", c, c, c, c);
+                    src += buf;
+                }
+                src += "}\n";
+                snprintf(buf, sizeof buf, "    fg%zu(b, m, pl, kc, bt, apl, acc, S);\n", n_groups);
+                fold_calls += buf;
+            }
         }
-        src += " return sum;\n}\n";
-        snprintf(buf, sizeof buf, "    rs = e_add(rs, pg%zu(b, n, kc, bt, pr));\n", n_groups);
-        perm_calls += buf;
-        // ---- fold kernel group ----
-        snprintf(buf, sizeof buf, "__device__ __noinline__ void fg%zu(const u32* __restrict__ b, u64 h, const u32* __restrict__ pl, const uint4* __restrict__ kc, const uint4* __restrict__ bt, const uint4* __restrict__ apl, E4& acc, E4& S) {\n", n_groups);
-        src += buf;
-        src += loads + body + chunks;
-        for (size_t c = cb; c < ce; c++) {
-            if (single[c - cb])
-                snprintf(buf, sizeof buf, " { E4 pc = ldp(pl, %zuull, h); S = e_add(S, pc); E4 L = e_mul(pc, D%zu); L.a = sub(L.a, %s); acc = e_add(acc, e_mul(ld4(apl + %zu), L)); }\n",
-                         c, c, m_name[p.chunk_start[c] - i0].c_str(), c);
-            else
-                snprintf(buf, sizeof buf, " { E4 pc = ldp(pl, %zuull, h); S = e_add(S, pc); E4 L = e_sub(e_mul(pc, D%zu), N%zu); acc = e_add(acc, e_mul(ld4(apl + %zu), L)); }\n", c, c, c, c);
-            src += buf;
-        }
-        src += "}\n";
-        snprintf(buf, sizeof buf, "    fg%zu(b, m, pl, kc, bt, apl, acc, S);\n", n_groups);
-        fold_calls += buf;
     }
-    src += R"(
-extern "C" __global__ void __launch_bounds__(128) pbl_perm(const u32* __restrict__ mat, u64 n, const uint4* __restrict__ kc, const uint4* __restrict__ bt,
+    char lb[64];
+    if (MINB) snprintf(lb, sizeof lb, "__launch_bounds__(%u, %u)", BT, MINB); else snprintf(lb, sizeof lb, "__launch_bounds__(%u)", BT);
+    src += std::string("\nextern \"C\" __global__ void ") + lb + R"( pbl_perm(const u32* __restrict__ mat, u64 n, const uint4* __restrict__ kc, const uint4* __restrict__ bt,
                                                             u32* __restrict__ perm, u32* __restrict__ rowsum, int first) {
-    const u64 r = (u64)blockIdx.x * 128ull + threadIdx.x;
+    const u64 r = (u64)blockIdx.x * blockDim.x + threadIdx.x;
     if (r >= n) return;
     const u32* b = mat + r;
     u32* pr = perm + r;
@@ -304,10 +325,11 @@ extern "C" __global__ void __launch_bounds__(128) pbl_perm(const u32* __restrict
     src += perm_calls;
     src += R"(    rowsum[r] = rs.a; rowsum[n + r] = rs.b; rowsum[2 * n + r] = rs.c; rowsum[3 * n + r] = rs.d;
 }
-extern "C" __global__ void __launch_bounds__(128) pbl_fold(const u32* __restrict__ lde, const u32* __restrict__ plde, u64 m, const uint4* __restrict__ kc,
+)";
+    src += std::string("extern \"C\" __global__ void ") + lb + R"( pbl_fold(const u32* __restrict__ lde, const u32* __restrict__ plde, u64 m, const uint4* __restrict__ kc,
                                                             const uint4* __restrict__ bt, const uint4* __restrict__ apl, u32* __restrict__ raw,
                                                             u32* __restrict__ Ssum, int first) {
-    const u64 r = (u64)blockIdx.x * 128ull + threadIdx.x;
+    const u64 r = (u64)blockIdx.x * blockDim.x + threadIdx.x;
     if (r >= m) return;
     const u32* b = lde + r;
     const u32* pl = plde + r;
@@ -328,8 +350,10 @@ inline int build(const std::vector<uint32_t>& code, const std::vector<air::Span>
                  size_t* cubin_bytes = nullptr) {
     airjit::Api& a = airjit::api();
     if (!a.nvrtc_ok || (out && !a.ok)) return 3;
-    size_t mod_chunks = 64;      // 8 groups of 8 chunks per module
-    if (const char* e = getenv("PB_LOGUP_JIT_CHUNKS")) mod_chunks = std::max<size_t>(GROUP_CHUNKS, ((size_t)atol(e) / GROUP_CHUNKS) * GROUP_CHUNKS);
+    // chunks per module = per kernel launch: the generated code is straight-line, every warp streams through all of it once, so a
+    // module must fit the instruction cache (ncu: `no_instruction` was the top stall with 64-chunk modules = 460 KB of SASS)
+    size_t mod_chunks = 16;
+    if (const char* e = getenv("PB_LOGUP_JIT_CHUNKS")) mod_chunks = std::max<size_t>(1, (size_t)atol(e));
     const size_t nc = p.n_chunks(), n_mods = (nc + mod_chunks - 1) / mod_chunks;
     std::vector<std::vector<char>> cubins(n_mods);
     std::vector<std::vector<LitArg>> lits(n_mods);
@@ -388,7 +412,8 @@ inline int launch_perm(const Kernels& k, cudaStream_t st, const uint32_t* mat, u
     for (size_t c = 0; c < k.perm_fns.size(); c++) {
         int first = c == 0;
         void* args[] = {(void*)&mat, (void*)&n, (void*)&kc, (void*)&bt, (void*)&perm, (void*)&rowsum, (void*)&first};
-        CUresult rc = airjit::api().LaunchKernel(k.perm_fns[c], (unsigned)((n + 127) / 128), 1, 1, 128, 1, 1, 0, (CUstream)st, args, nullptr);
+        const unsigned bt = block_threads();
+        CUresult rc = airjit::api().LaunchKernel(k.perm_fns[c], (unsigned)((n + bt - 1) / bt), 1, 1, bt, 1, 1, 0, (CUstream)st, args, nullptr);
         if (rc != CUDA_SUCCESS) return 700 + (int)rc;
     }
     return 0;
@@ -398,7 +423,8 @@ inline int launch_fold(const Kernels& k, cudaStream_t st, const uint32_t* lde, c
     for (size_t c = 0; c < k.fold_fns.size(); c++) {
         int first = c == 0;
         void* args[] = {(void*)&lde, (void*)&plde, (void*)&m, (void*)&kc, (void*)&bt, (void*)&apl, (void*)&raw, (void*)&ssum, (void*)&first};
-        CUresult rc = airjit::api().LaunchKernel(k.fold_fns[c], (unsigned)((m + 127) / 128), 1, 1, 128, 1, 1, 0, (CUstream)st, args, nullptr);
+        const unsigned bt = block_threads();
+        CUresult rc = airjit::api().LaunchKernel(k.fold_fns[c], (unsigned)((m + bt - 1) / bt), 1, 1, bt, 1, 1, 0, (CUstream)st, args, nullptr);
         if (rc != CUDA_SUCCESS) return 700 + (int)rc;
     }
     return 0;

@@ -66,6 +66,14 @@ __device__ __forceinline__ uint32_t mul_const(uint32_t a, uint32_t w, uint32_t w
     return bb::reduce_2p(a * w - q * bb::P);
 }
 __device__ __forceinline__ uint32_t halve(uint32_t x) { return (x >> 1) + (x & 1u) * ((bb::P + 1) / 2); }
+// x * 2^-K mod p for x in [0,p), K <= 27, WITHOUT a modular product: p = 15*2^27 + 1 is 1 mod 2^K, so the Montgomery-style
+// quotient digit is m = (-x) mod 2^K and (x + m p) / 2^K = ((x + m) >> K) + m * 15 * 2^(27-K) < p.  One IMAD (2 FMA-pipe cycles)
+// and three ALU instructions instead of a Shoup product (IMAD.HI + 2 IMAD = 8 cycles) and its correction.
+template <int K>
+__device__ __forceinline__ uint32_t div_2k(uint32_t x) {
+    const uint32_t m = (0u - x) & ((1u << K) - 1u);
+    return ((x + m) >> K) + m * (15u << (27 - K));
+}
 
 __device__ __forceinline__ void internal_round(uint32_t (&s)[16], int r) {
     s[0] = sbox_rc(s[0], c_p2.rc_int_mp[r]);
@@ -74,6 +82,29 @@ __device__ __forceinline__ void internal_round(uint32_t (&s)[16], int r) {
     uint32_t c = bb::add(bb::add(s[8], s[9]), bb::add(s[10], s[11]));
     uint32_t d = bb::add(bb::add(s[12], s[13]), bb::add(s[14], s[15]));
     uint32_t sum = bb::add(bb::add(a, b), bb::add(c, d));
+#ifndef PB_V_DIAG_SHOUP      // default since round 2: +2 % leaf-hashing rate (profiles/README.md); -DPB_V_DIAG_SHOUP restores the Shoup products
+    if (c_p2.p3_diag) {
+        // every entry of the Plonky3 diagonal [-2,1,2,1/2,3,4,-1/2,-3,-4,2^-8,1/4,1/8,2^-27,-2^-8,-1/16,-2^-27] without a modular
+        // product: small multiples as add chains, the 2^-K entries through div_2k -- the multiplier pipe is the binding one
+        const uint32_t x4 = bb::dbl(s[4]), x5 = bb::dbl(bb::dbl(s[5])), x7 = bb::dbl(s[7]), x8 = bb::dbl(bb::dbl(s[8]));
+        s[0] = bb::sub(bb::sub(sum, s[0]), s[0]);          // -2
+        s[1] = bb::add(sum, s[1]);                         //  1
+        s[2] = bb::add(sum, bb::dbl(s[2]));                //  2
+        s[3] = bb::add(sum, halve(s[3]));                  //  1/2
+        s[4] = bb::add(sum, bb::add(x4, s[4]));            //  3
+        s[5] = bb::add(sum, x5);                           //  4
+        s[6] = bb::sub(sum, halve(s[6]));                  // -1/2
+        s[7] = bb::sub(sum, bb::add(x7, s[7]));            // -3
+        s[8] = bb::sub(sum, x8);                           // -4
+        s[9] = bb::add(sum, div_2k<8>(s[9]));              //  2^-8
+        s[10] = bb::add(sum, div_2k<2>(s[10]));            //  1/4
+        s[11] = bb::add(sum, div_2k<3>(s[11]));            //  1/8
+        s[12] = bb::add(sum, div_2k<27>(s[12]));           //  2^-27
+        s[13] = bb::sub(sum, div_2k<8>(s[13]));            // -2^-8
+        s[14] = bb::sub(sum, div_2k<4>(s[14]));            // -1/16
+        s[15] = bb::sub(sum, div_2k<27>(s[15]));           // -2^-27
+    } else
+#else
     if (c_p2.p3_diag) {
         // the cheap entries of the Plonky3 diagonal go to the ALU pipe (which has slack), the rest to Shoup products
         s[0] = bb::sub(bb::sub(sum, s[0]), s[0]);          // -2
@@ -85,7 +116,9 @@ __device__ __forceinline__ void internal_round(uint32_t (&s)[16], int r) {
         s[5] = bb::add(sum, mul_const(s[5], c_p2.diag_w[5], c_p2.diag_wp[5]));
 #pragma unroll
         for (int i = 7; i < 16; i++) s[i] = bb::add(sum, mul_const(s[i], c_p2.diag_w[i], c_p2.diag_wp[i]));
-    } else {
+    } else
+#endif
+    {
 #pragma unroll
         for (int i = 0; i < 16; i++) s[i] = bb::add(sum, mul_const(s[i], c_p2.diag_w[i], c_p2.diag_wp[i]));
     }

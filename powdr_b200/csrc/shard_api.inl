@@ -40,6 +40,61 @@ __global__ void __launch_bounds__(256) coef_fold_kernel(const uint32_t* __restri
     }
 }
 
+// column blocks -> row blocks (the transpose that gives a rank whole trace rows for the LogUp phase):
+// out[(dest * per + i) * rows + r] = cols[i * N + dest * rows + r]   for i < w_my, zero for the pad columns i >= w_my
+__global__ void __launch_bounds__(256) pack_rows_kernel(const uint32_t* __restrict__ cols, size_t w_my, size_t per, size_t N, size_t rows, int G,
+                                                        uint32_t* __restrict__ out) {
+    const size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= (size_t)G * per * rows) return;
+    const size_t r = idx % rows, i = (idx / rows) % per, dest = idx / (rows * per);
+    out[idx] = i < w_my ? __ldg(cols + i * N + dest * rows + r) : 0u;
+}
+// row blocks of my columns -> whole columns:  out[i * N + src * rows + r] = in[(src * per + i) * rows + r]
+__global__ void __launch_bounds__(256) unpack_cols_kernel(const uint32_t* __restrict__ in, size_t per, size_t N, size_t rows, int G, uint32_t* __restrict__ out) {
+    const size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= (size_t)G * per * rows) return;
+    const size_t r = idx % rows, i = (idx / rows) % per, src = idx / (rows * per);
+    out[i * N + src * rows + r] = in[idx];
+}
+// a[l * n + i] += off[l]   (the running sum's offset of this rank's row block)
+__global__ void __launch_bounds__(256) add_limb_offsets_kernel(uint32_t* __restrict__ a, size_t n, uint4 off) {
+    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    a[i] = bb::add(a[i], off.x); a[n + i] = bb::add(a[n + i], off.y); a[2 * n + i] = bb::add(a[2 * n + i], off.z); a[3 * n + i] = bb::add(a[3 * n + i], off.w);
+}
+// logup::finish_kernel for a row block: the next-row values of S and phi live on another rank, so every rank's (S, phi) block is
+// gathered first: sp[(blk * 8 + k) * Ms + r], k < 4: S limb k, k >= 4: phi limb k-4.  Writes the quotient VALUES of my rows, [4][Ms].
+__global__ void __launch_bounds__(256) finish_block_kernel(const uint32_t* __restrict__ raw, const uint32_t* __restrict__ sp, size_t Ms, size_t row0, int log_n,
+                                                           uint32_t shift_m, uint32_t omega_m_m, uint32_t w_n_inv_m, uint32_t sn_m, bb::E4 alpha, bb::E4 alpha2,
+                                                           bb::E4 cumsum, uint32_t zinv, uint32_t* __restrict__ out) {
+    const size_t r = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (r >= Ms) return;
+    const int log_m = log_n + 1;
+    const size_t m = (size_t)1 << log_m, R = row0 + r, blk = row0 / Ms;
+    const uint32_t i_nat = __brev((uint32_t)R) >> (32 - log_m);
+    const size_t Rn = __brev((uint32_t)((i_nat + 2) & (uint32_t)(m - 1))) >> (32 - log_m);
+    const size_t bn = Rn / Ms, rn = Rn % Ms;
+    const uint32_t x = bb::mul(shift_m, bb::pow(omega_m_m, (uint64_t)i_nat));
+    const uint32_t zh = bb::sub((i_nat & 1) ? bb::neg(sn_m) : sn_m, bb::R1);
+    const uint32_t is_first = bb::mul(zh, bb::inv(bb::sub(x, bb::R1)));
+    const uint32_t is_last = bb::mul(zh, bb::inv(bb::sub(x, w_n_inv_m)));
+    const uint32_t is_trans = bb::sub(x, w_n_inv_m);
+    bb::E4 acc, S, Sn, ph, phn;
+#pragma unroll
+    for (int l = 0; l < 4; l++) {
+        acc.c[l] = raw[(size_t)l * Ms + r];
+        S.c[l] = sp[(blk * 8 + l) * Ms + r];
+        ph.c[l] = sp[(blk * 8 + 4 + l) * Ms + r];
+        Sn.c[l] = sp[(bn * 8 + l) * Ms + rn];
+        phn.c[l] = sp[(bn * 8 + 4 + l) * Ms + rn];
+    }
+    acc = bb::e4_add(acc, bb::e4_mul(alpha2, bb::e4_scale(bb::e4_sub(ph, S), is_first)));
+    acc = bb::e4_add(acc, bb::e4_mul(alpha, bb::e4_scale(bb::e4_sub(bb::e4_sub(phn, ph), Sn), is_trans)));
+    acc = bb::e4_add(acc, bb::e4_scale(bb::e4_sub(ph, cumsum), is_last));
+#pragma unroll
+    for (int l = 0; l < 4; l++) out[(size_t)l * Ms + r] = bb::mul(acc.c[l], zinv);
+}
+
 __global__ void __launch_bounds__(256) scale_kernel(uint32_t* __restrict__ a, size_t n, uint32_t k) {
     const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i < n) a[i] = bb::mul(a[i], k);
@@ -185,12 +240,15 @@ int pb_prove_segment_sharded(pb_ctx_t* ctx, const pb_air_t* a, const uint32_t* t
                              const pb_comm_t* comm, pb_segment_proof_t* proof) {
     if (!ctx || !a || !proof || !comm || !comm->all_gather || !comm->all_to_all) return PB_ERR_INVALID_ARG;
     if (log_n < 1 || log_n > 24 || width == 0 || width != a->width) return PB_ERR_INVALID_ARG;
-    if (a->has_lu) return PB_ERR_UNSUPPORTED;      // the LogUp phase needs whole trace rows: not sharded yet
+    if (a->has_lu && ((size_t)1 << log_n) % (size_t)comm->world != 0) return PB_ERR_UNSUPPORTED;
     ShardGeom s;
     if (!make_shard_geom(log_n, comm->world, &s) || comm->rank < 0 || comm->rank >= comm->world) return PB_ERR_UNSUPPORTED;
     const int G = s.G, rho = comm->rank;
     const size_t N = s.N, Ms = s.Ms, log_m = log_n + 1, log_ms = (size_t)s.np;
     const size_t per = (width + (size_t)G - 1) / (size_t)G;
+    const size_t n_chunks = a->has_lu ? a->lu.n_chunks() : 0, wp = a->has_lu ? a->lu.perm_width() : 0;
+    const size_t perp = (wp + (size_t)G - 1) / (size_t)G, rows_t = N / (size_t)G;      // perm columns per rank; trace rows per rank
+    const size_t pmax = std::max(per, perp);
     size_t c_first, w_my;
     pb_shard_columns(width, G, rho, &c_first, &w_my);
     if (w_my && !trace_cols) return PB_ERR_INVALID_ARG;
@@ -198,13 +256,22 @@ int pb_prove_segment_sharded(pb_ctx_t* ctx, const pb_air_t* a, const uint32_t* t
     memset(proof, 0, sizeof *proof);
     proof->pow_bits = ctx->pow_bits;
     proof->n_queries = ctx->n_queries;
+    proof->perm_width = (uint32_t)(a->has_lu ? a->lu.perm_width() : 0);
     cudaStream_t st = ctx->stream;
     ctx->seg.valid = false;
 #define RC(x) do { rc = (x); if (rc) return rc; } while (0)
 #define COMM(fn, send, recv, bytes) do { CK(cudaStreamSynchronize(st)); if (comm->fn(comm->user, (send), (recv), (bytes))) return PB_ERR_COMM; } while (0)
     CK(cudaEventRecord(ctx->ev[0], st));
-    RC(ctx->ws_shard_send.ensure((size_t)G * per * Ms));
-    RC(ctx->ws_shard_recv.ensure((size_t)G * per * Ms));
+    RC(ctx->ws_shard_send.ensure((size_t)G * pmax * Ms));
+    RC(ctx->ws_shard_recv.ensure((size_t)G * pmax * Ms));
+    if (wp) {
+        RC(ctx->ws_perm.ensure((size_t)G * perp * rows_t + 4 * rows_t));      // my trace rows x all perm columns (padded to G*perp), + row sums
+        RC(ctx->ws_perm_lde.ensure(wp * Ms));
+        RC(ctx->ws_layers_p.ensure(8 * (2 * Ms)));
+        RC(ctx->ws_rowsum.ensure(perp * N));                                   // my perm columns, whole (column-sharded copy)
+        RC(ctx->ws_lu_raw.ensure(4 * Ms));
+        RC(ctx->ws_lu_s.ensure(8 * Ms + (size_t)G * 8 * Ms));
+    }
     RC(ctx->ws_lde.ensure(width * Ms));
     RC(ctx->ws_layers.ensure(8 * (2 * Ms)));
     RC(ctx->ws_layers_q.ensure(8 * (2 * Ms)));
@@ -243,6 +310,74 @@ int pb_prove_segment_sharded(pb_ctx_t* ctx, const pb_air_t* a, const uint32_t* t
     RC(combine_roots(ctx, comm, root_ptr(ctx->ws_layers.p, log_ms), root_m));
     for (int i = 0; i < 8; i++) proof->trace_root[i] = h_from_m(root_m[i]);
     ch.observe(root_m, 8);
+
+    // ---- LogUp phase.  The permutation trace needs whole trace ROWS: transpose my column block into row blocks (all-to-all), generate
+    //      the permutation columns of my rows, scan the running sum (local scan + offsets from the gathered block totals), transpose the
+    //      permutation trace back into column blocks (all-to-all) and push it through the same LDE / Merkle path as the main trace ----
+    bb::E4 cumsum = {{0u, 0u, 0u, 0u}};
+    size_t wp_first = 0, wp_my = 0;
+    if (wp) {
+        pb_shard_columns(wp, G, rho, &wp_first, &wp_my);
+        const bb::E4 al = ch.sample_ext(), be = ch.sample_ext();
+        for (int i = 0; i < 4; i++) { proof->logup_alpha[i] = h_from_m(al.c[i]); proof->logup_beta[i] = h_from_m(be.c[i]); }
+        RC(upload_logup_consts(ctx, a, al, be));
+        const size_t tot_t = (size_t)G * per * rows_t;
+        shard::pack_rows_kernel<<<(unsigned)((tot_t + 255) / 256), 256, 0, st>>>(d_my, w_my, per, N, rows_t, G, ctx->ws_shard_send.p);
+        LAUNCHED(ctx);
+        COMM(all_to_all, ctx->ws_shard_send.p, ctx->ws_shard_recv.p, per * rows_t * 4);
+        // recv = [source][per][rows_t] = column-major, column j = source * per + i: my rows of every trace column
+        uint32_t* perm_rows = ctx->ws_perm.p;                           // [G * perp][rows_t], the first wp columns are real
+        uint32_t* rowsum = ctx->ws_perm.p + (size_t)G * perp * rows_t;  // [4][rows_t]
+        if ((size_t)G * perp > wp) CK(cudaMemsetAsync(perm_rows + wp * rows_t, 0, ((size_t)G * perp - wp) * rows_t * 4, st));
+        RC(logup::launch_perm(a->lujit, st, ctx->ws_shard_recv.p, rows_t, a->d_kc, a->d_bt, perm_rows, rowsum));
+        LAUNCHED(ctx);
+        {
+            const unsigned nb = (unsigned)((rows_t + logup::SCAN_THREADS * logup::SCAN_ITEMS - 1) / (logup::SCAN_THREADS * logup::SCAN_ITEMS));
+            RC(ctx->ws_scan_tot.ensure(4 * (size_t)nb + 8 + 8 * (size_t)G));
+            uint32_t* phi = perm_rows + 4 * n_chunks * rows_t;
+            logup::scan_local_kernel<<<dim3(nb, 4), logup::SCAN_THREADS, 0, st>>>(rowsum, phi, rows_t, ctx->ws_scan_tot.p);
+            logup::scan_totals_kernel<<<1, 32, 0, st>>>(ctx->ws_scan_tot.p, nb);
+            logup::scan_add_kernel<<<dim3((unsigned)((rows_t + 255) / 256), 4), 256, 0, st>>>(phi, rows_t, ctx->ws_scan_tot.p, nb);
+            ctx->launches += 3;
+            // block totals (last row of the local scan) of every rank -> my offset and the cumulative sum
+            uint32_t* tot_my = ctx->ws_scan_tot.p + 4 * (size_t)nb;       // 8 words (4 used; 32-byte exchange unit)
+            uint32_t* tot_all = tot_my + 8;
+            CK(cudaMemsetAsync(tot_my, 0, 32, st));
+            for (int l = 0; l < 4; l++) CK(cudaMemcpyAsync(tot_my + l, phi + (size_t)l * rows_t + (rows_t - 1), 4, cudaMemcpyDeviceToDevice, st));
+            COMM(all_gather, tot_my, tot_all, 32);
+            uint32_t th[16 * 8];
+            CK(cudaMemcpyAsync(th, tot_all, 32 * (size_t)G, cudaMemcpyDeviceToHost, st));
+            CK(cudaStreamSynchronize(st));
+            bb::E4 off = {{0u, 0u, 0u, 0u}};
+            for (int b = 0; b < G; b++)
+                for (int l = 0; l < 4; l++) {
+                    if (b < rho) off.c[l] = bb::add(off.c[l], th[8 * b + l]);
+                    cumsum.c[l] = bb::add(cumsum.c[l], th[8 * b + l]);
+                }
+            shard::add_limb_offsets_kernel<<<(unsigned)((rows_t + 255) / 256), 256, 0, st>>>(phi, rows_t, make_uint4(off.c[0], off.c[1], off.c[2], off.c[3]));
+            LAUNCHED(ctx);
+            for (int l = 0; l < 4; l++) proof->cumulative_sum[l] = h_from_m(cumsum.c[l]);
+        }
+        // row blocks -> column blocks: destination d gets columns [d * perp, (d + 1) * perp) of my rows = a contiguous slice of perm_rows
+        COMM(all_to_all, perm_rows, ctx->ws_shard_recv.p, perp * rows_t * 4);
+        uint32_t* perm_cols = ctx->ws_rowsum.p;                         // [perp][N]: my permutation columns, whole
+        shard::unpack_cols_kernel<<<(unsigned)(((size_t)G * perp * rows_t + 255) / 256), 256, 0, st>>>(ctx->ws_shard_recv.p, perp, N, rows_t, G, perm_cols);
+        LAUNCHED(ctx);
+        // LDE of the permutation trace, row-sharded like the main one
+        if (wp_my < perp)
+            for (int b = 0; b < G; b++) CK(cudaMemsetAsync(ctx->ws_shard_send.p + ((size_t)b * perp + wp_my) * Ms, 0, (perp - wp_my) * Ms * 4, st));
+        RC(inverse_and_fold(ctx, s, perm_cols, log_n, wp_my, bb::GEN, 0, G, ctx->ws_shard_send.p, perp * Ms));
+        COMM(all_to_all, ctx->ws_shard_send.p, ctx->ws_shard_recv.p, perp * Ms * 4);
+        RC(forward_block(ctx, s, ctx->ws_shard_recv.p, log_n, wp, bb::GEN, rho, ctx->ws_perm_lde.p));
+        {
+            const uint32_t* matsp[1] = {ctx->ws_perm_lde.p};
+            RC(pb_merkle_commit(ctx, matsp, &wp, 1, log_ms, ctx->ws_layers_p.p, nullptr));
+        }
+        RC(combine_roots(ctx, comm, root_ptr(ctx->ws_layers_p.p, log_ms), root_m));
+        for (int i = 0; i < 8; i++) proof->perm_root[i] = h_from_m(root_m[i]);
+        ch.observe(root_m, 8);
+        ch.observe(cumsum.c, 4);
+    }
     const bb::E4 alpha = ch.sample_ext();
     for (int i = 0; i < 4; i++) proof->alpha[i] = h_from_m(alpha.c[i]);
 
@@ -250,11 +385,32 @@ int pb_prove_segment_sharded(pb_ctx_t* ctx, const pb_air_t* a, const uint32_t* t
     {
         uint32_t* q_my = ctx->ws_shard_coef.p;                 // [4][Ms]
         uint32_t* q_all = ctx->ws_f0.p;                        // [G][4][Ms]  (ws_f0 is free until FRI)
-        RC(pb_constraint_fold(ctx, a, ctx->ws_lde.p, Ms, proof->alpha, q_my));
         const uint32_t sn = bb::pow(h_to_m(bb::GEN), (uint64_t)1 << log_n);
         const uint32_t zinv = (rho >> s.g1) ? bb::inv(bb::sub(bb::neg(sn), bb::R1)) : bb::inv(bb::sub(sn, bb::R1));
-        shard::scale_kernel<<<(unsigned)((4 * Ms + 255) / 256), 256, 0, st>>>(q_my, 4 * Ms, zinv);
-        LAUNCHED(ctx);
+        if (!wp) {
+            RC(pb_constraint_fold(ctx, a, ctx->ws_lde.p, Ms, proof->alpha, q_my));
+            shard::scale_kernel<<<(unsigned)((4 * Ms + 255) / 256), 256, 0, st>>>(q_my, 4 * Ms, zinv);
+            LAUNCHED(ctx);
+        } else {
+            RC(constraint_fold_m(ctx, a, ctx->ws_lde.p, Ms, alpha, n_chunks + 3, ctx->ws_lu_raw.p));
+            {
+                std::vector<bb::E4> apl(std::max<size_t>(1, n_chunks));
+                bb::E4 cur = bb::e4_mul(alpha, alpha);
+                for (size_t c = n_chunks; c-- > 0;) { cur = bb::e4_mul(cur, alpha); apl[c] = cur; }
+                CK(cudaMemcpyAsync(a->d_apl, apl.data(), n_chunks * 16, cudaMemcpyHostToDevice, st));
+                CK(cudaStreamSynchronize(st));
+            }
+            uint32_t* sp_my = ctx->ws_lu_s.p;                 // [8][Ms]: S limbs then phi limbs of my rows
+            uint32_t* sp_all = ctx->ws_lu_s.p + 8 * Ms;       // [G][8][Ms]
+            RC(logup::launch_fold(a->lujit, st, ctx->ws_lde.p, ctx->ws_perm_lde.p, Ms, a->d_kc, a->d_bt, a->d_apl, ctx->ws_lu_raw.p, sp_my));
+            LAUNCHED(ctx);
+            CK(cudaMemcpyAsync(sp_my + 4 * Ms, ctx->ws_perm_lde.p + 4 * n_chunks * Ms, 4 * Ms * 4, cudaMemcpyDeviceToDevice, st));
+            COMM(all_gather, sp_my, sp_all, 8 * Ms * 4);
+            shard::finish_block_kernel<<<(unsigned)((Ms + 255) / 256), 256, 0, st>>>(ctx->ws_lu_raw.p, sp_all, Ms, (size_t)rho * Ms, (int)log_n, h_to_m(bb::GEN),
+                                                                                    h_root_of_unity_m((int)log_m), bb::inv(h_root_of_unity_m((int)log_n)), sn, alpha,
+                                                                                    bb::e4_mul(alpha, alpha), cumsum, zinv, q_my);
+            LAUNCHED(ctx);
+        }
         CK(cudaEventRecord(ctx->ev[4], st));
         COMM(all_gather, q_my, q_all, 4 * Ms * 4);
         for (int b = 0; b < G; b++) {
@@ -286,19 +442,28 @@ int pb_prove_segment_sharded(pb_ctx_t* ctx, const pb_air_t* a, const uint32_t* t
     for (int i = 0; i < 4; i++) proof->zeta[i] = h_from_m(zeta.c[i]);
 
     // ---- openings at zeta: my trace columns, gathered; the 8 quotient columns on every rank; every value observed ----
-    const size_t n_open = width + 8;
-    RC(ctx->ws_ys.ensure(4 * ((size_t)G * per + 8)));
-    RC(ctx->ws_gather2.ensure(4 * per + 4 * (size_t)G * per));
+    const size_t n_open = width + 2 * wp + 8;
+    RC(ctx->ws_ys.ensure(4 * (n_open + (size_t)G * pmax)));
+    RC(ctx->ws_gather2.ensure(4 * pmax + 4 * (size_t)G * pmax));
     {
-        uint32_t* ys_my = ctx->ws_gather2.p;                    // [per][4]
-        uint32_t* ys_all = ctx->ws_gather2.p + 4 * per;        // [G*per][4]
+        uint32_t* ys_my = ctx->ws_gather2.p;                    // [pmax][4]
+        uint32_t* ys_all = ctx->ws_gather2.p + 4 * pmax;       // [G*pmax][4]
         CK(cudaMemsetAsync(ys_my, 0, 16 * per, st));
         if (w_my) RC(eval_at_point_m(ctx, d_my, log_n, w_my, h_to_m(1u), zeta, ys_my));
         COMM(all_gather, ys_my, ys_all, 16 * per);
         CK(cudaMemcpyAsync(ctx->ws_ys.p, ys_all, 16 * width, cudaMemcpyDeviceToDevice, st));
+        if (wp) {       // my permutation columns at zeta and at zeta*w
+            const bb::E4 zeta_next = bb::e4_scale(zeta, h_root_of_unity_m((int)log_n));
+            for (int pt = 0; pt < 2; pt++) {
+                CK(cudaMemsetAsync(ys_my, 0, 16 * perp, st));
+                if (wp_my) RC(eval_at_point_m(ctx, ctx->ws_rowsum.p, log_n, wp_my, h_to_m(1u), pt ? zeta_next : zeta, ys_my));
+                COMM(all_gather, ys_my, ys_all, 16 * perp);
+                CK(cudaMemcpyAsync(ctx->ws_ys.p + 4 * (width + (size_t)pt * wp), ys_all, 16 * wp, cudaMemcpyDeviceToDevice, st));
+            }
+        }
         const uint32_t g_c = bb::GEN, gw_c = h_from_m(bb::mul(h_to_m(bb::GEN), h_root_of_unity_m((int)log_n + 1)));
-        RC(eval_at_point_m(ctx, ctx->ws_qnat.p, log_n, 4, h_to_m(g_c), zeta, ctx->ws_ys.p + 4 * width));
-        RC(eval_at_point_m(ctx, ctx->ws_qnat.p + 4 * N, log_n, 4, h_to_m(gw_c), zeta, ctx->ws_ys.p + 4 * (width + 4)));
+        RC(eval_at_point_m(ctx, ctx->ws_qnat.p, log_n, 4, h_to_m(g_c), zeta, ctx->ws_ys.p + 4 * (width + 2 * wp)));
+        RC(eval_at_point_m(ctx, ctx->ws_qnat.p + 4 * N, log_n, 4, h_to_m(gw_c), zeta, ctx->ws_ys.p + 4 * (width + 2 * wp + 4)));
     }
     std::vector<uint32_t>& ys_h = ctx->seg.ys;
     ys_h.assign(4 * n_open, 0u);
@@ -313,9 +478,15 @@ int pb_prove_segment_sharded(pb_ctx_t* ctx, const pb_air_t* a, const uint32_t* t
     uint32_t* f_next = ctx->ws_f1.p;
     {
         std::vector<const uint32_t*> cols(n_open);
-        for (size_t c = 0; c < width; c++) cols[c] = ctx->ws_lde.p + c * Ms;
-        for (size_t c = 0; c < 8; c++) cols[width + c] = ctx->ws_qlde.p + c * Ms;
-        RC(deep_quotient_m(ctx, cols, log_m, h_to_m(bb::GEN), zeta, gamma, ys_h.data(), f, (size_t)rho * Ms, Ms));
+        std::vector<uint32_t> grp(n_open, 0u);
+        size_t k = 0;
+        for (size_t c = 0; c < width; c++) cols[k++] = ctx->ws_lde.p + c * Ms;
+        for (size_t c = 0; c < wp; c++) cols[k++] = ctx->ws_perm_lde.p + c * Ms;
+        for (size_t c = 0; c < wp; c++) { grp[k] = 1; cols[k++] = ctx->ws_perm_lde.p + c * Ms; }
+        for (size_t c = 0; c < 8; c++) cols[k++] = ctx->ws_qlde.p + c * Ms;
+        std::vector<bb::E4> zs{zeta};
+        if (wp) zs.push_back(bb::e4_scale(zeta, h_root_of_unity_m((int)log_n)));
+        RC(deep_quotient_groups_m(ctx, cols, grp, zs, log_m, h_to_m(bb::GEN), gamma, ys_h.data(), f, (size_t)rho * Ms, Ms));
     }
     CK(cudaEventRecord(ctx->ev[8], st));
 

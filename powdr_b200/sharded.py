@@ -126,7 +126,7 @@ class ThreadComm(Comm):
         g.barrier.wait(timeout=120)
 
 
-def prove_segment_threads(world, trace, bytecode, spans, device=0, on_device=True, fri_params=(8, 4)):
+def prove_segment_threads(world, trace, bytecode, spans, device=0, on_device=True, fri_params=(8, 4), bus=None):
     """Prove one segment with `world` thread-ranks on one GPU (parity harness).  trace: canonical (W, N) uint32.
     -> list of per-rank proof dicts (all equal)."""
     from .capi import Context
@@ -140,7 +140,7 @@ def prove_segment_threads(world, trace, bytecode, spans, device=0, on_device=Tru
         try:
             ctx = Context(device)
             ctx.set_fri_params(*fri_params)
-            air = ctx.air(bytecode, spans, width)
+            air = ctx.air(bytecode, spans, width, bus)
             first, count = shard_columns(width, world, rank)
             comm = ThreadComm(group, rank, ctx)
             if on_device:

@@ -21,11 +21,14 @@ KEYS = [
     "sm__inst_issued.avg.pct_of_peak_sustained_active", "smsp__issue_active.avg.pct_of_peak_sustained_active",
     "sm__throughput.avg.pct_of_peak_sustained_elapsed", "smsp__cycles_active.avg", "sm__cycles_elapsed.max",
     "l1tex__t_bytes.sum", "smsp__inst_executed.avg.per_cycle_active", "sm__cycles_active.avg",
+    "sm__pipe_fmaheavy_cycles_active.avg.pct_of_peak_sustained_elapsed", "sass__inst_executed_local_loads", "sass__inst_executed_local_stores",
+    "sm__issue_active.avg.pct_of_peak_sustained_elapsed",
 ]
 
 
 def rep(path):
-    out = subprocess.run(["ncu", "-i", path, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
+    # a .ncu-rep, or the CSV that `ncu -i x.ncu-rep --page raw --csv` printed on the GPU box (the reports themselves are too big to bring back)
+    out = open(path).read() if path.endswith(".csv") else subprocess.run(["ncu", "-i", path, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
     rows = list(csv.reader(io.StringIO(out)))
     hdr = rows[0]
     res = []

@@ -72,6 +72,27 @@ def test_lde_restricts_to_trace_on_subgroup(ctx, log_n):
     assert (got[:, :n][:, perm] == trace).all()
 
 
+@pytest.mark.parametrize("log_n,width", [(19, 5), (20, 37)])
+def test_tma_staged_passes_equal_the_ldg_staged_ones(ctx, monkeypatch, log_n, width):
+    """n_lo = 10 geometries run the two transposed passes on the TMA-staged kernels (ntt_tma.cuh: cp.async.bulk.tensor tiles, 128 B
+    swizzle, mbarrier completion); PB_LDE_NO_TMA=1 selects the LDG/STS-staged specialisations.  Same LDE bit for bit, and the
+    first coset restricted to H is the trace (shift 1)."""
+    rng = np.random.default_rng(log_n)
+    n = 1 << log_n
+    trace = rand_field(rng, (width, n))
+    d_in = ctx.to_device(trace)
+    d_a, d_b = ctx.alloc(4 * width * 2 * n), ctx.alloc(4 * width * 2 * n)
+    ctx.lde_batch(d_in.ptr, log_n, width, d_a.ptr, 1, 31)
+    monkeypatch.setenv("PB_LDE_NO_TMA", "1")
+    ctx.lde_batch(d_in.ptr, log_n, width, d_b.ptr, 1, 31)
+    monkeypatch.delenv("PB_LDE_NO_TMA")
+    a, b = ctx.to_host(d_a, (width, 2 * n)), ctx.to_host(d_b, (width, 2 * n))
+    assert (a == b).all()
+    ctx.lde_batch(d_in.ptr, log_n, width, d_a.ptr, 1, 1)
+    got = ctx.to_host(d_a, (width, 2 * n))
+    assert (got[:, :n][:, bitrev_perm(log_n)] == trace).all()
+
+
 # ---------------------------------------------------------------- stage 3a
 def test_poseidon2_permutation(ctx, orc):
     rng = np.random.default_rng(11)
