@@ -17,6 +17,8 @@
 #include <stdint.h>
 #include <stdio.h>
 #include <stdlib.h>
+#include <sys/stat.h>
+#include <unistd.h>
 #include <string>
 #include <vector>
 
@@ -226,8 +228,33 @@ extern "C" __global__ void __launch_bounds__(256) pbq(const u32* __restrict__ ma
     return src;
 }
 
+// on-disk cubin cache (PB_JIT_CACHE=<dir>, default /tmp/powdr_b200_jit; PB_JIT_CACHE=off disables): key generation is seconds of NVRTC
+// per AIR, and the ranks of a multi-GPU job (or repeated runs) compile identical modules
+inline std::string cache_path(const std::string& src) {
+    const char* dir = getenv("PB_JIT_CACHE");
+    if (dir && std::string(dir) == "off") return "";
+    std::string d = dir ? dir : "/tmp/powdr_b200_jit";
+    mkdir(d.c_str(), 0777);
+    uint64_t h1 = 1469598103934665603ull, h2 = 0x9e3779b97f4a7c15ull;
+    for (unsigned char c : src) { h1 = (h1 ^ c) * 1099511628211ull; h2 = (h2 + c) * 0xff51afd7ed558ccdull; h2 ^= h2 >> 29; }
+    char name[96];
+    snprintf(name, sizeof name, "/sm100a_%016llx%016llx_%zu.cubin", (unsigned long long)h1, (unsigned long long)h2, src.size());
+    return d + name;
+}
+
 // one chunk: source -> cubin (thread-safe: distinct NVRTC programs)
 inline int compile_chunk(const std::string& src, std::vector<char>& cubin) {
+    const std::string cpath = cache_path(src);
+    if (!cpath.empty())
+        if (FILE* f = fopen(cpath.c_str(), "rb")) {
+            fseek(f, 0, SEEK_END);
+            const long n = ftell(f);
+            fseek(f, 0, SEEK_SET);
+            cubin.resize(n > 0 ? (size_t)n : 0);
+            const bool ok = n > 0 && fread(cubin.data(), 1, (size_t)n, f) == (size_t)n;
+            fclose(f);
+            if (ok) return 0;
+        }
     Api& a = api();
     nvrtcProgram prog;
     if (a.CreateProgram(&prog, src.c_str(), "pb_air.cu", 0, nullptr, nullptr) != NVRTC_SUCCESS) return 4;
@@ -249,6 +276,14 @@ inline int compile_chunk(const std::string& src, std::vector<char>& cubin) {
     cubin.resize(sz);
     a.GetCUBIN(prog, cubin.data());
     a.DestroyProgram(&prog);
+    if (!cpath.empty()) {                      // write-then-rename: a concurrent reader never sees a partial file
+        const std::string tmp = cpath + "." + std::to_string((long)getpid()) + "." + std::to_string((unsigned long)(uintptr_t)&cubin);
+        if (FILE* f = fopen(tmp.c_str(), "wb")) {
+            const bool ok = fwrite(cubin.data(), 1, cubin.size(), f) == cubin.size();
+            fclose(f);
+            if (ok) rename(tmp.c_str(), cpath.c_str()); else remove(tmp.c_str());
+        }
+    }
     return 0;
 }
 

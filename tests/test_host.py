@@ -280,3 +280,38 @@ def test_entry_points_reject_null_arguments_before_touching_the_device():
     assert lib.pb_air_set_interactions(z, z, z, n0, z, n0, z, n0) == INVALID
     assert lib.pb_allgather_caps(z, z, z, z) == INVALID
     assert lib.pb_ctx_set_fri_params(z, C.c_uint32(8), C.c_uint32(4)) == INVALID
+
+
+def test_v1_metrics_json_is_consumed_by_the_reference_tooling(tmp_path):
+    """the per-stage times go out under the OpenVM-1 metric names; the reference's own basic_metrics.py must be able to
+    read the file (run only where /root/reference exists: the GPU box has no copy)"""
+    import json
+    import sys
+    from powdr_b200 import metrics
+    stage = {"h2d": 0.1, "lde": 34.0, "merkle": 130.0, "logup_gen": 46.0, "logup_commit": 270.0, "quotient": 60.0, "qlde": 0.3, "qmerkle": 1.3,
+             "open": 25.0, "fri": 3.9, "pow": 0.3, "total": 571.0}
+    m = metrics.segment_metrics(stage, 1 << 20, 2022, 3348, 187, 1734, trace_gen_ms=12.0, query_ms=0.5)
+    path = tmp_path / "metrics.json"
+    metrics.write(str(path), m)
+    doc = json.load(open(path))
+    names = {g["metric"] for g in doc["gauge"]}
+    for k in ("main_trace_commit_time_ms", "perm_trace_commit_time_ms", "quotient_poly_compute_time_ms", "quotient_poly_commit_time_ms",
+              "pcs_opening_time_ms", "stark_prove_excluding_trace_time_ms", "total_proof_time_ms", "trace_gen_time_ms"):
+        assert k in names
+    scripts = "/root/reference/openvm-riscv/scripts"
+    if not os.path.isdir(scripts):
+        return
+    sys.path.insert(0, scripts)
+    try:
+        import matplotlib                      # noqa: F401  (basic_metrics imports it at module level)
+        import basic_metrics
+    except Exception:
+        import metrics_utils
+        app, leaf, internal = metrics_utils.load_metrics_dataframes(str(path))
+        assert len(app) > 0
+        return
+    finally:
+        sys.path.remove(scripts)
+    out = basic_metrics.extract_metrics(str(path))
+    assert out["num_segments"] == 1 and out["powdr_ratio"] == 1.0 and out["powdr_rows"] == 1 << 20
+    assert abs(out["app_proof_time_excluding_trace_ms"] - 571.5) < 1e-6 and out["app_proof_cols"] == 2022 + 3348
