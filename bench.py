@@ -332,7 +332,9 @@ def run_native(a):
         achieved = (leaf_bytes / 1e9) / (leaf_ms / 1e3) if leaf_ms > 0 else 0.0
         traffic = None
         try:
-            traffic = json.load(open(os.path.join(ROOT, "profiles", "leaf_kernel_traffic.json")))["dram_bytes_per_launch"]
+            # one `ncu --set full` capture of this kernel gives DRAM bytes / algorithmic bytes of a launch; the timed launches differ in
+            # width (main, permutation, quotient matrices), so the ratio is applied to their average algorithmic size
+            traffic = json.load(open(os.path.join(ROOT, "profiles", "leaf_kernel_traffic.json")))["dram_over_algorithmic"] * leaf_bytes / max(1, n_leaf)
         except Exception:
             pass
         nn, ww, wpp = float(n), float(w), float(wp)

@@ -41,7 +41,9 @@ int pb_ctx_create(pb_ctx_t** out, int device, void* cuda_stream);
 int pb_ctx_destroy(pb_ctx_t* ctx);
 int pb_ctx_synchronize(pb_ctx_t* ctx);
 /* Poseidon2 instantiation as data (canonical values): 8x16 external round constants (4 initial then 4 terminal),
- * 13 internal, 16-entry internal diagonal V (matrix 1 + diag(V)).  Default = include/pb_poseidon2_constants.h. */
+ * 13 internal, 16-entry internal diagonal V (matrix 1 + diag(V)).  Default = include/pb_poseidon2_constants.h (Plonky3's
+ * default BabyBear width-16 instance).  The DEVICE copy is one __constant__ bank per process and GPU: setting it on one context
+ * changes the hashing of every context of this process on that GPU -- use one instantiation per process. */
 int pb_ctx_set_poseidon2(pb_ctx_t* ctx, const uint32_t rc_ext[8][16], const uint32_t rc_int[13], const uint32_t diag_m1[16]);
 
 /* pinned host memory + representation helpers */
@@ -171,7 +173,11 @@ int pb_shard_columns(size_t width, int world, int rank, size_t* first, size_t* c
 /* rows [blk*2N/world, (blk+1)*2N/world) of pb_lde_batch(.., log_blowup 1, shift)'s result for every column, computed without
  * the other rows (sub-coset evaluation); d_out column-major [width][2N/world] */
 int pb_lde_shard(pb_ctx_t* ctx, const uint32_t* d_trace, size_t log_n, size_t width, uint32_t shift, int world, int blk, uint32_t* d_out);
-/* trace_cols: this rank's column block [count][2^log_n] (device if PB_TRACE_ON_DEVICE, else host); width: the whole trace's */
+/* trace_cols: this rank's column block [count][2^log_n] (device if PB_TRACE_ON_DEVICE, else host); width: the whole trace's.
+ * Bus interactions attached to the AIR are proved here too (the LogUp phase runs on row / column shards); the query
+ * phase is not sharded.  FAILURE SEMANTICS: arguments and workspace sizes are checked before the first collective, but a rank that
+ * fails later (a CUDA error, a collective reporting failure) returns at once while its peers are still inside a collective -- the
+ * caller's collectives must carry the abort (NCCL: a communicator timeout / ncclCommAbort on the failing rank's error path). */
 int pb_prove_segment_sharded(pb_ctx_t* ctx, const pb_air_t* air, const uint32_t* trace_cols, size_t log_n, size_t width, uint32_t flags,
                              const pb_comm_t* comm, pb_segment_proof_t* proof);
 

@@ -358,6 +358,7 @@ int pb_prove_segment_sharded(pb_ctx_t* ctx, const pb_air_t* a, const uint32_t* t
             LAUNCHED(ctx);
             for (int l = 0; l < 4; l++) proof->cumulative_sum[l] = h_from_m(cumsum.c[l]);
         }
+        CK(cudaEventRecord(ctx->ev[12], st));
         // row blocks -> column blocks: destination d gets columns [d * perp, (d + 1) * perp) of my rows = a contiguous slice of perm_rows
         COMM(all_to_all, perm_rows, ctx->ws_shard_recv.p, perp * rows_t * 4);
         uint32_t* perm_cols = ctx->ws_rowsum.p;                         // [perp][N]: my permutation columns, whole
@@ -377,7 +378,10 @@ int pb_prove_segment_sharded(pb_ctx_t* ctx, const pb_air_t* a, const uint32_t* t
         for (int i = 0; i < 8; i++) proof->perm_root[i] = h_from_m(root_m[i]);
         ch.observe(root_m, 8);
         ch.observe(cumsum.c, 4);
+    } else {
+        CK(cudaEventRecord(ctx->ev[12], st));
     }
+    CK(cudaEventRecord(ctx->ev[13], st));
     const bb::E4 alpha = ch.sample_ext();
     for (int i = 0; i < 4; i++) proof->alpha[i] = h_from_m(alpha.c[i]);
 
@@ -554,7 +558,10 @@ int pb_prove_segment_sharded(pb_ctx_t* ctx, const pb_air_t* a, const uint32_t* t
     cudaEventElapsedTime(&t[6], ctx->ev[6], ctx->ev[8]);
     cudaEventElapsedTime(&t[7], ctx->ev[8], ctx->ev[7]);
     memset(ctx->stage_ms, 0, sizeof ctx->stage_ms);
-    ctx->stage_ms[0] = t[0]; ctx->stage_ms[1] = t[1]; ctx->stage_ms[2] = t[2]; ctx->stage_ms[5] = t[3]; ctx->stage_ms[6] = t[4];
+    ctx->stage_ms[0] = t[0]; ctx->stage_ms[1] = t[1]; ctx->stage_ms[2] = t[2]; ctx->stage_ms[6] = t[4];
+    cudaEventElapsedTime(&ctx->stage_ms[3], ctx->ev[3], ctx->ev[12]);      // LogUp: trace transpose + permutation rows + running sum
+    cudaEventElapsedTime(&ctx->stage_ms[4], ctx->ev[12], ctx->ev[13]);     // transpose back + LDE + Merkle of the permutation trace
+    cudaEventElapsedTime(&ctx->stage_ms[5], ctx->ev[13], ctx->ev[4]);      // quotient
     ctx->stage_ms[7] = t[5]; ctx->stage_ms[8] = t[6]; ctx->stage_ms[9] = t[7];
     cudaEventElapsedTime(&ctx->stage_ms[10], ctx->ev[7], ctx->ev[9]);
     cudaEventElapsedTime(&ctx->stage_ms[11], ctx->ev[0], ctx->ev[9]);
