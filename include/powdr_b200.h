@@ -167,7 +167,13 @@ typedef struct pb_comm {
     pb_collective_fn all_gather;      /* d_recv[r * bytes ..] = rank r's d_send[0 .. bytes) */
     pb_collective_fn all_to_all;      /* d_recv[r * bytes ..] = rank r's d_send[rank * bytes ..) */
     void* user;
+    uint32_t flags;                   /* PB_COMM_STREAM_ORDERED or 0 */
 } pb_comm_t;
+/* the collectives are enqueued on (or ordered after) the context's CUDA stream and complete in stream order, like ncclAllGather /
+ * ncclSend+ncclRecv on that stream: the library then neither drains the stream before a collective nor waits after it (it still
+ * synchronises where the HOST needs a result: roots, opened values).  Without the flag the contract is the conservative one:
+ * called with the stream idle, returns once d_recv is complete. */
+#define PB_COMM_STREAM_ORDERED 1u
 /* the column block of `rank`: first = min(width, rank*ceil(width/world)), count = min(ceil(width/world), width - first) */
 int pb_shard_columns(size_t width, int world, int rank, size_t* first, size_t* count);
 /* rows [blk*2N/world, (blk+1)*2N/world) of pb_lde_batch(.., log_blowup 1, shift)'s result for every column, computed without
@@ -224,6 +230,17 @@ int _apc_apply_bus(const uint32_t* d_output, int num_apc_calls, const uint32_t* 
                    uint32_t var_range_bus_id, uint32_t* d_var_hist, size_t var_num_bins,
                    uint32_t tuple2_bus_id, uint32_t* d_tuple2_hist, uint32_t tuple2_sz0, uint32_t tuple2_sz1,
                    uint32_t bitwise_bus_id, uint32_t* d_bitwise_hist);
+
+/* ---- stage 0, periphery histograms with a per-AIR GENERATED kernel: same result as _apc_apply_bus (which stays the drop-in with the
+ * reference's shape), built at key-generation time from the same interaction table with COLUMN-INDEX operands (host pointers);
+ * pb_bus_apply enqueues on the context's stream.  d_trace: the APC trace, column-major, height H, Montgomery words. */
+typedef struct pb_bus pb_bus_t;
+int pb_bus_compile(pb_ctx_t* ctx, const uint32_t* bytecode, size_t n_words, const ExprSpan* arg_spans, size_t n_arg_spans,
+                   const DevInteraction* interactions, size_t n_interactions, uint32_t width, uint32_t var_range_bus_id, uint32_t tuple2_bus_id,
+                   uint32_t bitwise_bus_id, pb_bus_t** out);
+int pb_bus_free(pb_bus_t* bus);
+int pb_bus_apply(pb_ctx_t* ctx, const pb_bus_t* bus, const uint32_t* d_trace, size_t H, int num_apc_calls, uint32_t* d_var_hist, size_t var_num_bins,
+                 uint32_t* d_tuple2_hist, uint32_t tuple2_sz0, uint32_t tuple2_sz1, uint32_t* d_bitwise_hist);
 
 #ifdef __cplusplus
 }

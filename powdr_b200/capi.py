@@ -16,7 +16,7 @@ EXPORTS = [
     "pb_device_alloc", "pb_device_free", "pb_copy_h2d", "pb_copy_d2h", "pb_memset_zero", "pb_to_monty", "pb_from_monty",
     "pb_lde_batch", "pb_air_compile", "pb_air_free", "pb_air_is_jit", "pb_air_jit_compile_only", "pb_quotient", "pb_constraint_fold", "pb_merkle_commit",
     "pb_merkle_commit_rows8", "pb_poseidon2_permute", "pb_fri_fold", "pb_eval_at_point", "pb_deep_quotient", "pb_prove_segment", "pb_query_words", "pb_query_segment", "pb_last_openings", "pb_last_stage_ms",
-    "pb_ctx_set_fri_params", "pb_air_set_interactions", "pb_air_perm_width", "pb_air_logup_compile_only", "pb_allgather_caps",
+    "pb_ctx_set_fri_params", "pb_air_set_interactions", "pb_air_perm_width", "pb_air_logup_compile_only", "pb_allgather_caps", "pb_bus_compile", "pb_bus_free", "pb_bus_apply",
     "pb_shard_columns", "pb_lde_shard", "pb_prove_segment_sharded",
     "pb_launch_count", "pb_leaf_kernel_profile", "_apc_tracegen", "_apc_apply_derived_expr", "_apc_apply_bus",
 ]
@@ -326,6 +326,29 @@ class Context:
 
     def host_free(self, ptr):
         self.lib.pb_host_free(C.c_void_p(ptr))
+
+    # ---- stage 0, generated periphery kernel ----
+    def bus_compile(self, bus, width, var_bus=3, tuple2_bus=7, bitwise_bus=6):
+        """bus = machine.compile_bus(machine, 1) -> opaque handle for bus_apply"""
+        ints, isp, ibc = bus
+        ibc = _u32(ibc)
+        spn = (Span * max(1, len(isp)))()
+        for i, (o, l) in enumerate(isp):
+            spn[i].off, spn[i].len = o, l
+        di = (DevInteraction * max(1, len(ints)))()
+        for i, (b, n, o) in enumerate(ints):
+            di[i].bus_id, di[i].num_args, di[i].args_index_off = b, n, o
+        h = C.c_void_p()
+        _chk(self.lib.pb_bus_compile(self.h, ibc.ctypes.data_as(C.c_void_p), C.c_size_t(ibc.size), spn, C.c_size_t(len(isp)), di, C.c_size_t(len(ints)),
+                                     C.c_uint32(width), C.c_uint32(var_bus), C.c_uint32(tuple2_bus), C.c_uint32(bitwise_bus), C.byref(h)), "pb_bus_compile")
+        return h
+
+    def bus_apply(self, handle, d_trace_ptr, H, num_calls, d_var, var_bins, d_t2, sz0, sz1, d_bw):
+        _chk(self.lib.pb_bus_apply(self.h, handle, C.c_void_p(d_trace_ptr), C.c_size_t(H), C.c_int(num_calls), C.c_void_p(d_var), C.c_size_t(var_bins),
+                                   C.c_void_p(d_t2), C.c_uint32(sz0), C.c_uint32(sz1), C.c_void_p(d_bw)), "pb_bus_apply")
+
+    def bus_free(self, handle):
+        self.lib.pb_bus_free(handle)
 
     # ---- stage 0 (reference symbols) ----
     def apc_tracegen(self, d_out_ptr, H, d_airs_ptr, d_subs_ptr, n_subs, num_calls):

@@ -19,6 +19,7 @@
 #include "deep.cuh"
 #include "fri.cuh"
 #include "logup_jit.cuh"
+#include "bus_jit.cuh"
 #include "ntt.cuh"
 #include "ntt_fast.cuh"
 #include "ntt_tma.cuh"
@@ -162,6 +163,11 @@ struct pb_air {
     uint4* d_kc = nullptr;              // [n_ints]   alpha_lu + beta^k (bus+1) + literal arguments
     uint4* d_bt = nullptr;              // [max_args + 1] beta powers
     uint4* d_apl = nullptr;             // [n_chunks] alpha^(n_chunks + 2 - c)
+};
+
+struct pb_bus {
+    busjit::Kernel k;
+    std::vector<unsigned> grid_y;
 };
 
 struct pb_ctx {
@@ -999,6 +1005,53 @@ int _apc_apply_bus(const uint32_t* d_output, int num_apc_calls, const uint32_t* 
         reinterpret_cast<const tg::ExprSpan*>(d_arg_spans), var_range_bus_id, d_var_hist, var_num_bins, tuple2_bus_id, d_tuple2_hist,
         sz0, sz1, bitwise_bus_id, d_bitwise_hist);
     return (int)cudaGetLastError();
+}
+
+// ---- stage 0, generated periphery kernel (bus_jit.cuh): same histograms as _apc_apply_bus, straight-line code per AIR ----
+int pb_bus_compile(pb_ctx_t* ctx, const uint32_t* bc, size_t n_words, const ExprSpan* arg_spans, size_t n_arg_spans, const DevInteraction* ints, size_t n_ints,
+                   uint32_t width, uint32_t var_range_bus_id, uint32_t tuple2_bus_id, uint32_t bitwise_bus_id, pb_bus_t** out) {
+    // ctx == NULL && out == NULL: host-only check of the code generator (packs, generates, compiles for sm_100a; no device needed)
+    const bool compile_only = !ctx && !out;
+    if ((!compile_only && (!ctx || !out)) || (!bc && n_words) || (!arg_spans && n_arg_spans) || (!ints && n_ints)) return PB_ERR_INVALID_ARG;
+    std::vector<uint32_t> code, pool;
+    std::vector<air::Span> spans;
+    std::vector<pb_expr_span_t> sp(n_arg_spans);
+    for (size_t i = 0; i < n_arg_spans; i++) { sp[i].off = arg_spans[i].off; sp[i].len = arg_spans[i].len; }
+    int rc = pack_program(bc, n_words, sp.data(), n_arg_spans, width, code, pool, spans);
+    if (rc) return rc;
+    std::vector<logup::Interaction> all;
+    for (size_t i = 0; i < n_ints; i++) {
+        if ((size_t)ints[i].args_index_off + ints[i].num_args + 1 > n_arg_spans) return PB_ERR_BAD_BYTECODE;
+        all.push_back(logup::Interaction{ints[i].bus_id, ints[i].num_args, ints[i].args_index_off});
+    }
+    if (compile_only) return busjit::build(code, spans, pool, all, var_range_bus_id, tuple2_bus_id, bitwise_bus_id, nullptr, nullptr) ? PB_ERR_UNSUPPORTED : 0;
+    pb_bus* b = new pb_bus();
+    if (busjit::build(code, spans, pool, all, var_range_bus_id, tuple2_bus_id, bitwise_bus_id, &b->k, &b->grid_y)) { busjit::destroy(b->k); delete b; return PB_ERR_UNSUPPORTED; }
+    *out = b;
+    return 0;
+}
+
+int pb_bus_free(pb_bus_t* b) {
+    if (!b) return 0;
+    busjit::destroy(b->k);
+    delete b;
+    return 0;
+}
+
+int pb_bus_apply(pb_ctx_t* ctx, const pb_bus_t* b, const uint32_t* d_trace, size_t H, int num_apc_calls, uint32_t* d_var_hist, size_t var_num_bins,
+                 uint32_t* d_tuple2_hist, uint32_t sz0, uint32_t sz1, uint32_t* d_bitwise_hist) {
+    if (!ctx || !b || !d_trace) return PB_ERR_INVALID_ARG;
+    if (num_apc_calls <= 0) return 0;
+    unsigned long long h = H;
+    uint32_t vb = (uint32_t)var_num_bins;
+    for (size_t k = 0; k < b->k.fns.size(); k++) {
+        void* args[] = {(void*)&d_trace, (void*)&h, (void*)&num_apc_calls, (void*)&d_var_hist, (void*)&vb, (void*)&d_tuple2_hist, (void*)&sz0, (void*)&sz1,
+                        (void*)&d_bitwise_hist};
+        CUresult rc = airjit::api().LaunchKernel(b->k.fns[k], (unsigned)((num_apc_calls + 127) / 128), b->grid_y[k], 1, 128, 1, 1, 0, (CUstream)ctx->stream, args, nullptr);
+        if (rc != CUDA_SUCCESS) return 700 + (int)rc;
+        LAUNCHED(ctx);
+    }
+    return 0;
 }
 
 #include "shard_api.inl"

@@ -191,15 +191,25 @@ __global__ void __launch_bounds__(256) deep_quotient_kernel(DeepSegs segs, size_
                 __syncthreads();
                 for (uint32_t i = threadIdx.x; i < nc; i += blockDim.x) { sg[i] = __ldg(gpow + jglob + c0 + i); sg[DQ_CHUNK / 2 + i] = __ldg(gpow + jglob2 + c0 + i); }
                 __syncthreads();
+                // software-pipelined like the single-point path: the 8 loads of the next step are in flight during the 64 MACs of this one
                 uint32_t j = 0;
-                for (; j + 8 <= nc; j += 8) {
-                    uint32_t f[8];
+                if (nc >= 8) {
+                    uint32_t f[8], fn[8];
 #pragma unroll
-                    for (int u = 0; u < 8; u++) f[u] = __ldg(p2 + (size_t)(c0 + j + u) * stride2);
+                    for (int u = 0; u < 8; u++) f[u] = __ldg(p2 + (size_t)(c0 + u) * stride2);
+                    for (; j + 16 <= nc; j += 8) {
+#pragma unroll
+                        for (int u = 0; u < 8; u++) fn[u] = __ldg(p2 + (size_t)(c0 + j + 8 + u) * stride2);
+#pragma unroll
+                        for (int u = 0; u < 8; u++) { dq_mac(acc, f[u], sg[j + u]); dq_mac(acc2, f[u], sg[DQ_CHUNK / 2 + j + u]); }
+#pragma unroll
+                        for (int u = 0; u < 8; u++) f[u] = fn[u];
+                    }
 #pragma unroll
                     for (int u = 0; u < 8; u++) { dq_mac(acc, f[u], sg[j + u]); dq_mac(acc2, f[u], sg[DQ_CHUNK / 2 + j + u]); }
+                    j += 8;
                 }
-                for (; j < nc; j++) { const uint32_t f = __ldg(p2 + (size_t)(c0 + j) * stride2); dq_mac(acc, f, sg[j]); dq_mac(acc2, f, sg[DQ_CHUNK / 2 + j]); }
+                for (; j < nc; j++) { const uint32_t f1 = __ldg(p2 + (size_t)(c0 + j) * stride2); dq_mac(acc, f1, sg[j]); dq_mac(acc2, f1, sg[DQ_CHUNK / 2 + j]); }
             }
             continue;
         }

@@ -74,7 +74,7 @@ int pb_air_set_interactions(pb_ctx_t* ctx, pb_air_t* a, const uint32_t* bc, size
 
 int pb_allgather_caps(pb_ctx_t* ctx, const pb_comm_t* comm, const uint32_t* d_local_cap, uint32_t* d_all_caps) {
     if (!ctx || !comm || !comm->all_gather || !d_local_cap || !d_all_caps) return PB_ERR_INVALID_ARG;
-    CK(cudaStreamSynchronize(ctx->stream));
+    if (!(comm->flags & PB_COMM_STREAM_ORDERED)) CK(cudaStreamSynchronize(ctx->stream));
     return comm->all_gather(comm->user, d_local_cap, d_all_caps, 32) ? PB_ERR_COMM : 0;
 }
 

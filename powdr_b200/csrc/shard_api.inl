@@ -194,7 +194,7 @@ inline void host_compress(const P2Host& k, const uint32_t l[8], const uint32_t r
 int combine_roots(pb_ctx* ctx, const pb_comm_t* comm, const uint32_t* d_my_root, uint32_t root_m[8]) {
     int rc = ctx->ws_gather.ensure(8 * (size_t)comm->world);
     if (rc) return rc;
-    CK(cudaStreamSynchronize(ctx->stream));
+    if (!(comm->flags & PB_COMM_STREAM_ORDERED)) CK(cudaStreamSynchronize(ctx->stream));
     rc = comm->all_gather(comm->user, d_my_root, ctx->ws_gather.p, 32);
     if (rc) return PB_ERR_COMM;
     uint32_t nodes[16][8];
@@ -260,7 +260,7 @@ int pb_prove_segment_sharded(pb_ctx_t* ctx, const pb_air_t* a, const uint32_t* t
     cudaStream_t st = ctx->stream;
     ctx->seg.valid = false;
 #define RC(x) do { rc = (x); if (rc) return rc; } while (0)
-#define COMM(fn, send, recv, bytes) do { CK(cudaStreamSynchronize(st)); if (comm->fn(comm->user, (send), (recv), (bytes))) return PB_ERR_COMM; } while (0)
+#define COMM(fn, send, recv, bytes) do { if (!(comm->flags & PB_COMM_STREAM_ORDERED)) CK(cudaStreamSynchronize(st)); if (comm->fn(comm->user, (send), (recv), (bytes))) return PB_ERR_COMM; } while (0)
     CK(cudaEventRecord(ctx->ev[0], st));
     RC(ctx->ws_shard_send.ensure((size_t)G * pmax * Ms));
     RC(ctx->ws_shard_recv.ensure((size_t)G * pmax * Ms));

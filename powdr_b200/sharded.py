@@ -16,7 +16,11 @@ COLLECTIVE_FN = C.CFUNCTYPE(C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_siz
 
 
 class PbComm(C.Structure):
-    _fields_ = [("rank", C.c_int), ("world", C.c_int), ("all_gather", COLLECTIVE_FN), ("all_to_all", COLLECTIVE_FN), ("user", C.c_void_p)]
+    _fields_ = [("rank", C.c_int), ("world", C.c_int), ("all_gather", COLLECTIVE_FN), ("all_to_all", COLLECTIVE_FN), ("user", C.c_void_p),
+                ("flags", C.c_uint32)]
+
+
+PB_COMM_STREAM_ORDERED = 1
 
 
 def shard_columns(width, world, rank):
@@ -29,7 +33,7 @@ def shard_columns(width, world, rank):
 class Comm:
     """Base: wraps two python callables (send_ptr, recv_ptr, nbytes) into a pb_comm_t; exceptions become PB_ERR_COMM."""
 
-    def __init__(self, rank, world):
+    def __init__(self, rank, world, flags=0):
         self.rank, self.world = rank, world
         self.error = None
 
@@ -44,7 +48,7 @@ class Comm:
             return COLLECTIVE_FN(cb)
 
         self._ag, self._a2a = wrap(self.all_gather), wrap(self.all_to_all)      # keep the thunks alive
-        self.c = PbComm(rank, world, self._ag, self._a2a, None)
+        self.c = PbComm(rank, world, self._ag, self._a2a, None, flags)
 
     def all_gather(self, send, recv, nbytes):
         raise NotImplementedError
@@ -61,13 +65,16 @@ class _DevBytes:
 
 
 class TorchComm(Comm):
-    """torch.distributed process group (backend nccl), one rank per GPU."""
+    """torch.distributed process group (backend nccl), one rank per GPU.  STREAM-ORDERED (PB_COMM_STREAM_ORDERED): the context must
+    have been created on torch's current stream; a synchronous torch NCCL collective waits for the work already on that stream and
+    makes the stream wait for the collective, so no host synchronisation is needed on either side."""
 
-    def __init__(self, group=None):
+    def __init__(self, group=None, stream_ordered=True):
         import torch
         import torch.distributed as dist
         self.torch, self.dist, self.group = torch, dist, group
-        super().__init__(dist.get_rank(group), dist.get_world_size(group))
+        self.stream_ordered = stream_ordered
+        super().__init__(dist.get_rank(group), dist.get_world_size(group), PB_COMM_STREAM_ORDERED if stream_ordered else 0)
         self.calls, self.bytes = 0, 0
 
     def _t(self, ptr, nbytes):
@@ -75,13 +82,15 @@ class TorchComm(Comm):
 
     def all_gather(self, send, recv, nbytes):
         self.dist.all_gather_into_tensor(self._t(recv, nbytes * self.world), self._t(send, nbytes), group=self.group)
-        self.torch.cuda.synchronize()
+        if not self.stream_ordered:
+            self.torch.cuda.synchronize()
         self.calls += 1
         self.bytes += nbytes * self.world
 
     def all_to_all(self, send, recv, nbytes):
         self.dist.all_to_all_single(self._t(recv, nbytes * self.world), self._t(send, nbytes * self.world), group=self.group)
-        self.torch.cuda.synchronize()
+        if not self.stream_ordered:
+            self.torch.cuda.synchronize()
         self.calls += 1
         self.bytes += nbytes * self.world
 

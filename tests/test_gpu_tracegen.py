@@ -102,6 +102,15 @@ def _bus_case(ctx, orc, mach, trace, num_calls, var=(3, 1 << 18), tuple2=(7, 256
     got = (d_var.download(var[1]), d_t2.download(tuple2[1] * tuple2[2]), d_bw.download(1 << 17))
     for g, e in zip(got, exp):
         assert (g == e).all()
+    # the per-AIR generated kernel (pb_bus_compile / pb_bus_apply, column-index bytecode) must fill the same histograms
+    handle = ctx.bus_compile(M.compile_bus(mach, 1), mach.width, var[0], tuple2[0], bitwise)
+    d_var.zero(); d_t2.zero(); d_bw.zero()
+    ctx.bus_apply(handle, d_tr.ptr, H, num_calls, d_var.ptr, var[1], d_t2.ptr, tuple2[1], tuple2[2], d_bw.ptr)
+    ctx.synchronize()
+    got = (d_var.download(var[1]), d_t2.download(tuple2[1] * tuple2[2]), d_bw.download(1 << 17))
+    for g, e in zip(got, exp):
+        assert (g == e).all()
+    ctx.bus_free(handle)
     return exp
 
 

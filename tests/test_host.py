@@ -185,8 +185,11 @@ def test_logup_codegen_compiles_for_sm100a_without_a_device():
     assert lib.pb_air_logup_compile_only(*args, C.byref(cb), C.byref(wp)) == 0
     # 21 interactions, every 5th with a degree-2 argument (own chunk): 4 singles + ceil-pairs of the runs of 4 -> 4 + 4*2 + 1 = 13 chunks
     assert wp.value == 4 * (13 + 1) and cb.value > 10000
+    # the generated stage-0 periphery kernel compiles from the same table (ctx = out = NULL: host-only check)
+    assert lib.pb_bus_compile(None, *args, C.c_uint32(3), C.c_uint32(7), C.c_uint32(6), None) == 0
     di[3].args_index_off = len(isp)              # spans out of range
     assert lib.pb_air_logup_compile_only(*args, C.byref(cb), C.byref(wp)) == -4
+    assert lib.pb_bus_compile(None, *args, C.c_uint32(3), C.c_uint32(7), C.c_uint32(6), None) == -4
 
 
 def test_chunked_jit_compiles_a_9168_constraint_machine_in_parallel():
