@@ -72,6 +72,8 @@ typedef struct { uint32_t off; uint32_t len; } pb_expr_span_t;   /* == ExprSpan,
 int pb_air_compile(pb_ctx_t* ctx, const uint32_t* bytecode, size_t n_words, const pb_expr_span_t* constraints,
                    size_t n_constraints, uint32_t width, pb_air_t** out);
 int pb_air_free(pb_air_t* air);
+/* NOTE: a pb_air_t owns small per-proof device buffers (alpha powers, LogUp constants): one proof at a time per handle -- concurrent
+ * provers (e.g. one per GPU) compile their own handle, which is also what binds the kernels to their device's CUDA context. */
 /* 1 when the AIR runs on its NVRTC-generated straight-line kernel, 0 when on the bytecode interpreter kernel */
 int pb_air_is_jit(const pb_air_t* air);
 /* host-only check of the code generator: packs the program, generates CUDA C and compiles it for sm_100a (no device needed) */
