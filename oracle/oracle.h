@@ -142,6 +142,30 @@ int orc_verify_segment(const orc_air_t* air, unsigned log_n, size_t width, const
 /* proof-of-work grinding on a challenger state: smallest witness w with (observe(w); sample() & (2^bits - 1)) == 0 */
 uint32_t orc_grind(const orc_challenger_t* c, unsigned bits);
 
+/* ---- multi-chip segment under ONE transcript (prove.c, verify.c): mixed-height MMCS commitments, shared challenges, one FRI ---- */
+typedef struct { const orc_air_t* air; const uint32_t* trace; unsigned log_n; size_t width; } orc_chip_t;
+typedef struct {
+    uint32_t main_root[8], perm_root[8], quotient_root[8];
+    uint32_t logup_alpha[4], logup_beta[4], alpha[4], zeta[4], gamma[4];
+    uint32_t n_fri_layers;
+    uint32_t fri_roots[32][8];
+    uint32_t fri_betas[32][4];
+    uint32_t final_poly[8][4];
+    uint32_t final_len;
+    uint32_t pow_witness;
+    uint32_t pow_bits, n_queries, n_chips, log_max;       /* log_max: log2 of the tallest LDE */
+} orc_chips_proof_t;
+size_t orc_chips_num_opened(const orc_chip_t* chips, size_t n_chips);
+size_t orc_chips_query_words(const orc_chip_t* chips, size_t n_chips);
+/* cumsums: [n_chips][4] (zero for chips without interactions); ys_out: [orc_chips_num_opened][4]; queries_out: [n_queries][orc_chips_query_words].
+   query layout: [ r | main rows of all chips (row r >> (log_max - log_m_chip)) | main path (log_max x 8) | perm rows of the chips with
+   interactions | perm path | quotient rows (8 per chip) | quotient path | per FRI layer: pair (8), path ] */
+void orc_prove_chips(const orc_chip_t* chips, size_t n_chips, const orc_params_t* prm, orc_chips_proof_t* proof, uint32_t* cumsums, uint32_t* ys_out,
+                     uint32_t* queries_out);
+/* 0 = accept; codes as orc_verify_segment (8/9/10 = main/perm/quotient MMCS opening) */
+int orc_verify_chips(const orc_chip_t* chips_without_traces, size_t n_chips, const orc_chips_proof_t* proof, const uint32_t* cumsums, const uint32_t* ys,
+                     const uint32_t* queries, int check_constraints);
+
 /* ---- AVX-512 Montgomery implementations of the heavy primitives (fast.c), same semantics ---- */
 int orcf_available(void);
 void orcf_lde_batch(const uint32_t* trace, unsigned log_n, size_t width, unsigned log_blowup, uint32_t shift, uint32_t* lde);

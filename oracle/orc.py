@@ -469,3 +469,88 @@ def big_array(shape):
     ptr = lib().orc_big_alloc(C.c_size_t(4 * n))
     buf = (C.c_uint32 * n).from_address(ptr)
     return np.frombuffer(buf, dtype=np.uint32).reshape(shape)
+
+
+# ---- multi-chip segment under one transcript ----
+class ChipC(C.Structure):
+    _fields_ = [("air", C.c_void_p), ("trace", C.c_void_p), ("log_n", C.c_uint), ("width", C.c_size_t)]
+
+
+class ChipsProof(C.Structure):
+    _fields_ = [("main_root", C.c_uint32 * 8), ("perm_root", C.c_uint32 * 8), ("quotient_root", C.c_uint32 * 8),
+                ("logup_alpha", C.c_uint32 * 4), ("logup_beta", C.c_uint32 * 4), ("alpha", C.c_uint32 * 4), ("zeta", C.c_uint32 * 4), ("gamma", C.c_uint32 * 4),
+                ("n_fri_layers", C.c_uint32), ("fri_roots", (C.c_uint32 * 8) * 32), ("fri_betas", (C.c_uint32 * 4) * 32),
+                ("final_poly", (C.c_uint32 * 4) * 8), ("final_len", C.c_uint32), ("pow_witness", C.c_uint32),
+                ("pow_bits", C.c_uint32), ("n_queries", C.c_uint32), ("n_chips", C.c_uint32), ("log_max", C.c_uint32)]
+    VEC = ("main_root", "perm_root", "quotient_root", "logup_alpha", "logup_beta", "alpha", "zeta", "gamma")
+    SCALAR = ("n_fri_layers", "final_len", "pow_witness", "pow_bits", "n_queries", "n_chips", "log_max")
+
+    def as_dict(self):
+        n = self.n_fri_layers
+        d = {k: list(getattr(self, k)) for k in self.VEC}
+        d.update({k: int(getattr(self, k)) for k in self.SCALAR})
+        d["fri_roots"] = [list(self.fri_roots[i]) for i in range(n)]
+        d["fri_betas"] = [list(self.fri_betas[i]) for i in range(n)]
+        d["final_poly"] = [list(self.final_poly[i]) for i in range(self.final_len)]
+        return d
+
+    @classmethod
+    def from_dict(cls, d):
+        p = cls()
+        for k in cls.VEC:
+            for i, v in enumerate(d[k]):
+                getattr(p, k)[i] = v
+        for k in cls.SCALAR:
+            setattr(p, k, d[k])
+        for i in range(d["n_fri_layers"]):
+            for j in range(8):
+                p.fri_roots[i][j] = d["fri_roots"][i][j]
+            for j in range(4):
+                p.fri_betas[i][j] = d["fri_betas"][i][j]
+        for i in range(d["final_len"]):
+            for j in range(4):
+                p.final_poly[i][j] = d["final_poly"][i][j]
+        return p
+
+
+def _chips_array(chips):
+    """chips: list of (trace (W, N) or None, bc, spans, bus) -> (ctypes array, keep-alive list)"""
+    arr = (ChipC * len(chips))()
+    keep = []
+    for i, (trace, bc, spans, bus) in enumerate(chips):
+        air = Air(bc, spans, bus)
+        t = _u32(trace) if trace is not None else None
+        keep.append((air, t))
+        arr[i].air = C.addressof(air.c)
+        arr[i].trace = t.ctypes.data if t is not None else None
+        w, n = (t.shape if t is not None else (0, 0))
+        arr[i].log_n = (n.bit_length() - 1) if t is not None else 0
+        arr[i].width = w
+    return arr, keep
+
+
+def prove_chips(chips, n_queries=8, pow_bits=4, fast=False):
+    """chips: list of (trace, bc, spans, bus) -> (proof dict, cumulative sums (K, 4), opened values (n_open, 4), queries (n_queries, words))"""
+    arr, keep = _chips_array(chips)
+    K = len(chips)
+    L = lib()
+    L.orc_chips_num_opened.restype = C.c_size_t
+    L.orc_chips_query_words.restype = C.c_size_t
+    n_open = L.orc_chips_num_opened(arr, C.c_size_t(K))
+    wpq = L.orc_chips_query_words(arr, C.c_size_t(K))
+    proof = ChipsProof()
+    cs = np.zeros((K, 4), dtype=np.uint32)
+    ys = np.empty((n_open, 4), dtype=np.uint32)
+    q = np.empty((n_queries, wpq), dtype=np.uint32)
+    prm = ParamsC(n_queries, pow_bits, 1 if fast else 0, 0)
+    L.orc_prove_chips(arr, C.c_size_t(K), C.byref(prm), C.byref(proof), _p(cs), _p(ys), _p(q))
+    return proof.as_dict(), cs, ys, q
+
+
+def verify_chips(chips, proof, cumsums, ys, queries, check_constraints=False):
+    """chips: list of (trace-or-shape, bc, spans, bus); only the shape of the trace is used"""
+    arr, keep = _chips_array(chips)
+    p = ChipsProof.from_dict(proof)
+    cs, ys, q = _u32(cumsums), _u32(ys), _u32(queries)
+    lib().orc_verify_chips.restype = C.c_int
+    return lib().orc_verify_chips(arr, C.c_size_t(len(chips)), C.byref(p), _p(cs), _p(ys), _p(q), C.c_int(1 if check_constraints else 0))

@@ -320,3 +320,328 @@ void orc_prove_segment(const uint32_t* trace, unsigned log_n, size_t width, cons
     free(lde); free(qlde); free(layers); free(layers_q);
     free(perm); free(perm_lde); free(layers_p); free(chunk_start);
 }
+
+/* =====================================================================================================================
+ * MULTI-CHIP SEGMENT, ONE TRANSCRIPT (/root/reference/openvm/src/trace_generation.rs:113-140 builds ONE
+ * proving context for all chips of a segment, engine.prove at /root/reference/openvm-riscv/src/lib.rs:327-332).  Chips of different
+ * heights share every challenge, three mixed-height MMCS commitments (main, permutation, quotient) and one FRI instance:
+ *   MMCS (Plonky3 MerkleTreeMmcs): matrices sorted by height (descending, stable); leaves = sponge of the concatenated rows of the
+ *     tallest matrices; going up, a level whose size equals the height of further matrices gets them injected:
+ *     node = compress(compress(left, right), sponge(rows of those matrices)).  Opening index r: matrix of height 2^h opens row r >> (h0 - h).
+ *   FRI: one reduced-opening codeword per distinct LDE height; folding starts from the tallest, and after the fold that reaches a
+ *     height with its own codeword that codeword is added index-wise.
+ *   Opened values / gamma exponents in observation order: main at zeta (chip order) | per chip with interactions perm at zeta, perm at
+ *     zeta*w_chip | quotient chunks at zeta (chip order).
+ * Per chip everything else is the single-chip pipeline above (same LDE, LogUp, quotient, openings primitives). */
+typedef struct { const uint32_t* mat; size_t width; unsigned log_h; } mc_mat_t;
+
+static void hash_rows_of(const mc_mat_t* ms, size_t n, unsigned log_h, size_t r, uint32_t digest[8]) {
+    size_t tot = 0;
+    for (size_t i = 0; i < n; i++) if (ms[i].log_h == log_h) tot += ms[i].width;
+    uint32_t* row = (uint32_t*)malloc((tot ? tot : 1) * sizeof(uint32_t));
+    size_t k = 0;
+    for (size_t i = 0; i < n; i++)
+        if (ms[i].log_h == log_h)
+            for (size_t c = 0; c < ms[i].width; c++) row[k++] = ms[i].mat[(c << log_h) + r];
+    orc_hash_row(row, tot, digest);
+    free(row);
+}
+static int has_height(const mc_mat_t* ms, size_t n, unsigned log_h) {
+    for (size_t i = 0; i < n; i++) if (ms[i].log_h == log_h) return 1;
+    return 0;
+}
+/* mixed-height tree, node-major layers back to back (2^(h0+1) - 1 nodes); returns malloc'ed, *log_h0 = tallest */
+static uint32_t* mmcs_commit(const mc_mat_t* ms, size_t n, unsigned* log_h0) {
+    unsigned h0 = 0;
+    for (size_t i = 0; i < n; i++) if (ms[i].log_h > h0) h0 = ms[i].log_h;
+    *log_h0 = h0;
+    const size_t H = (size_t)1 << h0;
+    uint32_t* t = (uint32_t*)malloc(8 * (2 * H) * sizeof(uint32_t));
+#pragma omp parallel for schedule(static) if (H >= 1024)
+    for (long r = 0; r < (long)H; r++) hash_rows_of(ms, n, h0, (size_t)r, t + 8 * (size_t)r);
+    uint32_t* prev = t;
+    unsigned lh = h0;
+    for (size_t cnt = H >> 1; cnt >= 1; cnt >>= 1) {
+        uint32_t* cur = prev + 16 * cnt;
+        lh--;
+        const int inj = has_height(ms, n, lh);
+#pragma omp parallel for schedule(static) if (cnt >= 1024)
+        for (long j = 0; j < (long)cnt; j++) {
+            orc_compress(prev + 16 * (size_t)j, prev + 16 * (size_t)j + 8, cur + 8 * (size_t)j);
+            if (inj) {
+                uint32_t d[8], o[8];
+                hash_rows_of(ms, n, lh, (size_t)j, d);
+                orc_compress(cur + 8 * (size_t)j, d, o);
+                memcpy(cur + 8 * (size_t)j, o, 32);
+            }
+        }
+        prev = cur;
+        if (cnt == 1) break;
+    }
+    return t;
+}
+
+size_t orc_chips_num_opened(const orc_chip_t* chips, size_t K) {
+    size_t n = 0;
+    for (size_t c = 0; c < K; c++) n += chips[c].width + 2 * orc_perm_width(chips[c].air) + 8;
+    return n;
+}
+size_t orc_chips_query_words(const orc_chip_t* chips, size_t K) {
+    unsigned hmax = 0, hperm = 0;
+    size_t wm = 0, wp = 0;
+    for (size_t c = 0; c < K; c++) {
+        const unsigned lm = chips[c].log_n + 1;
+        const size_t p = orc_perm_width(chips[c].air);
+        if (lm > hmax) hmax = lm;
+        if (p && lm > hperm) hperm = lm;
+        wm += chips[c].width;
+        wp += p;
+    }
+    size_t w = 1 + wm + 8 * hmax + (wp ? wp + 8 * hperm : 0) + 8 * K + 8 * hmax;
+    for (unsigned i = 0; i + 1 < hmax; i++) w += 8 + 8 * (hmax - 1 - i);
+    return w;
+}
+
+void orc_prove_chips(const orc_chip_t* chips, size_t K, const orc_params_t* prm, orc_chips_proof_t* proof, uint32_t* cumsums, uint32_t* ys_out,
+                     uint32_t* queries_out) {
+    const ops_t* ops = (prm->fast && orcf_available()) ? &OPS_FAST : &OPS_SLOW;
+    memset(proof, 0, sizeof *proof);
+    proof->pow_bits = prm->pow_bits;
+    proof->n_queries = prm->n_queries;
+    proof->n_chips = (uint32_t)K;
+    orc_challenger_t ch;
+    orc_challenger_init(&ch);
+    uint32_t** lde = (uint32_t**)calloc(K, sizeof(void*));
+    uint32_t** perm = (uint32_t**)calloc(K, sizeof(void*));
+    uint32_t** plde = (uint32_t**)calloc(K, sizeof(void*));
+    uint32_t** qlde = (uint32_t**)calloc(K, sizeof(void*));
+    uint32_t** nat = (uint32_t**)calloc(K, sizeof(void*));
+    uint32_t** cstart = (uint32_t**)calloc(K, sizeof(void*));
+    size_t* wp = (size_t*)calloc(K, sizeof(size_t));
+    size_t* nch = (size_t*)calloc(K, sizeof(size_t));
+    mc_mat_t* mm = (mc_mat_t*)calloc(2 * K, sizeof(mc_mat_t));
+    unsigned hmax = 0, hperm = 0, hq = 0;
+    int any_lu = 0;
+
+    /* main commit */
+    for (size_t c = 0; c < K; c++) {
+        const size_t m = (size_t)2 << chips[c].log_n;
+        lde[c] = (uint32_t*)malloc(chips[c].width * m * sizeof(uint32_t));
+        ops->lde_batch(chips[c].trace, chips[c].log_n, chips[c].width, 1, BB_GENERATOR, lde[c]);
+        mm[c] = (mc_mat_t){lde[c], chips[c].width, chips[c].log_n + 1};
+    }
+    uint32_t* tree_m = mmcs_commit(mm, K, &hmax);
+    memcpy(proof->main_root, tree_m + 8 * (((size_t)2 << hmax) - 2), 32);
+    orc_challenger_observe(&ch, proof->main_root, 8);
+    proof->log_max = hmax;
+
+    /* LogUp: shared challenges, one permutation trace per chip with interactions, one commitment */
+    for (size_t c = 0; c < K; c++) if (chips[c].air->n_ints) any_lu = 1;
+    uint32_t* tree_p = NULL;
+    if (any_lu) {
+        orc_challenger_sample_ext(&ch, proof->logup_alpha);
+        orc_challenger_sample_ext(&ch, proof->logup_beta);
+        size_t np = 0;
+        for (size_t c = 0; c < K; c++) {
+            const orc_air_t* a = chips[c].air;
+            if (!a->n_ints) continue;
+            const size_t n = (size_t)1 << chips[c].log_n, m = n << 1;
+            cstart[c] = (uint32_t*)malloc((a->n_ints + 1) * sizeof(uint32_t));
+            int k = orc_logup_chunks(a->ibc, a->ispans, a->ints, a->n_ints, 3, cstart[c]);
+            if (k < 0) abort();
+            nch[c] = (size_t)k;
+            wp[c] = 4 * (nch[c] + 1);
+            perm[c] = (uint32_t*)malloc(wp[c] * n * sizeof(uint32_t));
+            ops->logup_perm_trace(chips[c].trace, chips[c].log_n, a->ibc, a->ispans, a->ints, a->n_ints, cstart[c], nch[c], proof->logup_alpha, proof->logup_beta,
+                                  perm[c], cumsums + 4 * c);
+            plde[c] = (uint32_t*)malloc(wp[c] * m * sizeof(uint32_t));
+            ops->lde_batch(perm[c], chips[c].log_n, wp[c], 1, BB_GENERATOR, plde[c]);
+            mm[np++] = (mc_mat_t){plde[c], wp[c], chips[c].log_n + 1};
+        }
+        tree_p = mmcs_commit(mm, np, &hperm);
+        memcpy(proof->perm_root, tree_p + 8 * (((size_t)2 << hperm) - 2), 32);
+        orc_challenger_observe(&ch, proof->perm_root, 8);
+        for (size_t c = 0; c < K; c++) if (wp[c]) orc_challenger_observe(&ch, cumsums + 4 * c, 4);
+    }
+    for (size_t c = 0; c < K; c++) if (!wp[c]) memset(cumsums + 4 * c, 0, 16);
+    orc_challenger_sample_ext(&ch, proof->alpha);
+
+    /* quotients: the same alpha for every chip, one commitment */
+    for (size_t c = 0; c < K; c++) {
+        const orc_air_t* a = chips[c].air;
+        const unsigned ln = chips[c].log_n;
+        const size_t n = (size_t)1 << ln, m = n << 1;
+        uint32_t* acc4 = (uint32_t*)malloc(4 * m * sizeof(uint32_t));
+        ops->constraint_fold(a->bc, a->spans, a->n_constraints, lde[c], m, proof->alpha, acc4);
+        if (wp[c]) ops->logup_fold(lde[c], plde[c], ln, BB_GENERATOR, a->ibc, a->ispans, a->ints, a->n_ints, cstart[c], nch[c], proof->logup_alpha, proof->logup_beta,
+                                   cumsums + 4 * c, proof->alpha, acc4);
+        const uint32_t sn = bb_pow(BB_GENERATOR, n);
+        const uint32_t zinv[2] = {bb_inv(bb_sub(sn, 1)), bb_inv(bb_sub(bb_neg(sn), 1))};
+        nat[c] = (uint32_t*)malloc(8 * n * sizeof(uint32_t));
+        for (size_t r = 0; r < m; r++) {
+            const size_t chunk = r >> ln, j = r & (n - 1);
+            for (int l = 0; l < 4; l++) nat[c][(chunk * 4 + l) * n + bitrev32((uint32_t)j, ln)] = bb_mul(acc4[(size_t)l * m + r], zinv[chunk]);
+        }
+        free(acc4);
+        qlde[c] = (uint32_t*)malloc(8 * m * sizeof(uint32_t));
+        const uint32_t w2n = bb_root_of_unity(ln + 1);
+        ops->lde_batch(nat[c], ln, 4, 1, 1, qlde[c]);
+        ops->lde_batch(nat[c] + 4 * n, ln, 4, 1, bb_inv(w2n), qlde[c] + 4 * m);
+        mm[c] = (mc_mat_t){qlde[c], 8, ln + 1};
+    }
+    uint32_t* tree_q = mmcs_commit(mm, K, &hq);
+    memcpy(proof->quotient_root, tree_q + 8 * (((size_t)2 << hq) - 2), 32);
+    orc_challenger_observe(&ch, proof->quotient_root, 8);
+    orc_challenger_sample_ext(&ch, proof->zeta);
+
+    /* openings, in observation order; remember where each block of a chip starts (its gamma exponent) */
+    const size_t n_open = orc_chips_num_opened(chips, K);
+    uint32_t* ys = (uint32_t*)calloc(4 * n_open, sizeof(uint32_t));
+    size_t* e_main = (size_t*)calloc(K, sizeof(size_t));
+    size_t* e_perm = (size_t*)calloc(K, sizeof(size_t));
+    size_t* e_q = (size_t*)calloc(K, sizeof(size_t));
+    size_t pos = 0;
+    for (size_t c = 0; c < K; c++) { e_main[c] = pos; ops->eval_at_point(chips[c].trace, chips[c].log_n, chips[c].width, 1, proof->zeta, ys + 4 * pos); pos += chips[c].width; }
+    for (size_t c = 0; c < K; c++) {
+        if (!wp[c]) continue;
+        bb4_t zn = {{proof->zeta[0], proof->zeta[1], proof->zeta[2], proof->zeta[3]}};
+        zn = bb4_scale(zn, bb_root_of_unity(chips[c].log_n));
+        e_perm[c] = pos;
+        ops->eval_at_point(perm[c], chips[c].log_n, wp[c], 1, proof->zeta, ys + 4 * pos);
+        ops->eval_at_point(perm[c], chips[c].log_n, wp[c], 1, zn.c, ys + 4 * (pos + wp[c]));
+        pos += 2 * wp[c];
+    }
+    for (size_t c = 0; c < K; c++) {
+        const size_t n = (size_t)1 << chips[c].log_n;
+        const uint32_t w2n = bb_root_of_unity(chips[c].log_n + 1);
+        e_q[c] = pos;
+        ops->eval_at_point(nat[c], chips[c].log_n, 4, BB_GENERATOR, proof->zeta, ys + 4 * pos);
+        ops->eval_at_point(nat[c] + 4 * n, chips[c].log_n, 4, bb_mul(BB_GENERATOR, w2n), proof->zeta, ys + 4 * (pos + 4));
+        pos += 8;
+    }
+    orc_challenger_observe(&ch, ys, 4 * n_open);
+    orc_challenger_sample_ext(&ch, proof->gamma);
+    if (ys_out) memcpy(ys_out, ys, 16 * n_open);
+
+    /* one reduced-opening codeword per LDE height */
+    uint32_t* ro[32] = {0};
+    {
+        bb4_t g = {{proof->gamma[0], proof->gamma[1], proof->gamma[2], proof->gamma[3]}};
+        for (size_t c = 0; c < K; c++) {
+            const unsigned lm = chips[c].log_n + 1;
+            const size_t m = (size_t)1 << lm;
+            if (!ro[lm]) ro[lm] = (uint32_t*)calloc(4 * m, sizeof(uint32_t));
+            uint32_t* tmp = (uint32_t*)malloc(4 * m * sizeof(uint32_t));
+            bb4_t zn = {{proof->zeta[0], proof->zeta[1], proof->zeta[2], proof->zeta[3]}};
+            zn = bb4_scale(zn, bb_root_of_unity(chips[c].log_n));
+            uint32_t zs[8];
+            memcpy(zs, proof->zeta, 16);
+            memcpy(zs + 4, zn.c, 16);
+            for (int part = 0; part < 3; part++) {
+                const size_t w = part == 0 ? chips[c].width : part == 1 ? 2 * wp[c] : 8;
+                if (!w) continue;
+                const size_t e0 = part == 0 ? e_main[c] : part == 1 ? e_perm[c] : e_q[c];
+                const uint32_t** cols = (const uint32_t**)malloc(w * sizeof(*cols));
+                uint32_t* grp = (uint32_t*)calloc(w, sizeof(uint32_t));
+                for (size_t j = 0; j < w; j++) {
+                    if (part == 0) cols[j] = lde[c] + j * m;
+                    else if (part == 1) { cols[j] = plde[c] + (j % wp[c]) * m; grp[j] = j >= wp[c]; }
+                    else cols[j] = qlde[c] + j * m;
+                }
+                ops->deep_groups(cols, grp, w, zs, part == 1 ? 2 : 1, lm, BB_GENERATOR, proof->gamma, ys + 4 * e0, tmp);
+                const bb4_t sc = bb4_pow(g, e0);               /* this block's exponents start at e0 */
+                for (size_t r = 0; r < m; r++) {
+                    bb4_t v, acc;
+                    memcpy(v.c, tmp + 4 * r, 16);
+                    memcpy(acc.c, ro[lm] + 4 * r, 16);
+                    acc = bb4_add(acc, bb4_mul(v, sc));
+                    memcpy(ro[lm] + 4 * r, acc.c, 16);
+                }
+                free(cols); free(grp);
+            }
+            free(tmp);
+        }
+    }
+
+    /* FRI: fold from the tallest codeword, adding the codeword of each height when the fold reaches it */
+    uint32_t* f = ro[hmax];
+    ro[hmax] = NULL;
+    unsigned log_len = hmax;
+    uint32_t shift = BB_GENERATOR;
+    uint32_t layer_i = 0;
+    uint32_t* words[32];
+    uint32_t* trees[32];
+    while (log_len > 1) {
+        words[layer_i] = f;
+        trees[layer_i] = merkle_tree_rowmajor(f, 8, log_len - 1);
+        memcpy(proof->fri_roots[layer_i], trees[layer_i] + 8 * (((size_t)2 << (log_len - 1)) - 2), 32);
+        orc_challenger_observe(&ch, proof->fri_roots[layer_i], 8);
+        orc_challenger_sample_ext(&ch, proof->fri_betas[layer_i]);
+        uint32_t* nf = (uint32_t*)malloc(4 * ((size_t)1 << (log_len - 1)) * sizeof(uint32_t));
+        orc_fri_fold(f, log_len, shift, proof->fri_betas[layer_i], nf);
+        f = nf;
+        shift = bb_mul(shift, shift);
+        log_len--;
+        layer_i++;
+        if (log_len > 1 && ro[log_len]) {
+            for (size_t i = 0; i < ((size_t)4 << log_len); i++) f[i] = bb_add(f[i], ro[log_len][i]);
+            free(ro[log_len]);
+            ro[log_len] = NULL;
+        }
+    }
+    proof->n_fri_layers = layer_i;
+    proof->final_len = 2;
+    memcpy(proof->final_poly, f, 32);
+    free(f);
+    orc_challenger_observe(&ch, proof->final_poly[0], 4);
+    proof->pow_witness = orc_grind(&ch, prm->pow_bits);
+    orc_challenger_observe(&ch, &proof->pow_witness, 1);
+    (void)orc_challenger_sample(&ch);
+
+    /* queries */
+    if (prm->n_queries && queries_out) {
+        const size_t wpq = orc_chips_query_words(chips, K);
+        for (size_t qi = 0; qi < prm->n_queries; qi++) {
+            uint32_t* o = queries_out + qi * wpq;
+            const size_t r = orc_challenger_sample(&ch) & (((size_t)1 << hmax) - 1);
+            *o++ = (uint32_t)r;
+            for (size_t c = 0; c < K; c++) {
+                const unsigned lm = chips[c].log_n + 1;
+                const size_t m = (size_t)1 << lm, rr = r >> (hmax - lm);
+                for (size_t j = 0; j < chips[c].width; j++) *o++ = lde[c][j * m + rr];
+            }
+            copy_path(tree_m, hmax, r, o);
+            o += 8 * hmax;
+            if (any_lu) {
+                for (size_t c = 0; c < K; c++) {
+                    if (!wp[c]) continue;
+                    const unsigned lm = chips[c].log_n + 1;
+                    const size_t m = (size_t)1 << lm, rr = r >> (hmax - lm);
+                    for (size_t j = 0; j < wp[c]; j++) *o++ = plde[c][j * m + rr];
+                }
+                copy_path(tree_p, hperm, r >> (hmax - hperm), o);
+                o += 8 * hperm;
+            }
+            for (size_t c = 0; c < K; c++) {
+                const unsigned lm = chips[c].log_n + 1;
+                const size_t m = (size_t)1 << lm, rr = r >> (hmax - lm);
+                for (size_t j = 0; j < 8; j++) *o++ = qlde[c][j * m + rr];
+            }
+            copy_path(tree_q, hq, r, o);
+            o += 8 * hq;
+            for (unsigned i = 0; i < layer_i; i++) {
+                const unsigned lh = hmax - 1 - i;
+                const size_t j = r >> (i + 1);
+                memcpy(o, words[i] + 8 * j, 32);
+                o += 8;
+                copy_path(trees[i], lh, j, o);
+                o += 8 * lh;
+            }
+        }
+    }
+    for (unsigned i = 0; i < layer_i; i++) { free(words[i]); free(trees[i]); }
+    for (unsigned h = 0; h < 32; h++) free(ro[h]);
+    for (size_t c = 0; c < K; c++) { free(lde[c]); free(perm[c]); free(plde[c]); free(qlde[c]); free(nat[c]); free(cstart[c]); }
+    free(lde); free(perm); free(plde); free(qlde); free(nat); free(cstart); free(wp); free(nch); free(mm);
+    free(tree_m); free(tree_p); free(tree_q); free(ys); free(e_main); free(e_perm); free(e_q);
+}
