@@ -47,6 +47,8 @@ def parse():
     ap.add_argument("--metrics-out", default="", help="write the last step's stage times as an OpenVM-1 metrics JSON (basic_metrics.py schema)")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-sharded", action="store_true", help="skip the one-segment-on-all-GPUs (strong scaling) measurement at N > 1")
+    ap.add_argument("--one-transcript", action="store_true",
+                    help="multichip workload: prove all 50 chips under ONE transcript on one GPU (pb_prove_chips) instead of one proof per chip")
     ap.add_argument("--workload", default="keccak", choices=["keccak", "multichip", "pairing", "stage0"],
                     help="keccak: one APC chip per segment (the BASELINE metric); multichip: 50 independent chips of one segment "
                          "sharded over the ranks by LPT (BASELINE.json configs[3] shape, strong scaling); pairing: ONE wide segment "
@@ -512,8 +514,16 @@ def run_multichip(a):
         gen.manual_seed(0xEC100 + i)
         chips.append((ln, mach.width, air, torch.randint(0, P, (mach.width, 1 << ln), dtype=torch.int32, device=dev, generator=gen)))
     caps = torch.zeros((kmax, 8), dtype=torch.int32, device=dev)
+    one = bool(a.one_transcript)
+    if one and world > 1:
+        raise SystemExit("--one-transcript proves all chips of the segment on ONE GPU (pb_prove_chips); run it with --gpus 1")
+    chip_args = [(air, tr.data_ptr(), ln, w) for ln, w, air, tr in chips]
 
     def step():
+        if one:
+            # every chip under one transcript: three mixed-height commitments, shared challenges, ONE FRI instance, one PoW, one query set
+            ctx.prove_chips(chip_args)
+            return
         roots = []
         for ln, w, air, tr in chips:
             roots.append(ctx.prove_segment(air, tr.data_ptr(), ln, w, on_device=True)["trace_root"])
@@ -545,11 +555,14 @@ def run_multichip(a):
     if rank == 0:
         mx, mean = parallel.plan_summary(costs, world)
         print(json.dumps({
-            "metric": "proof-gen sec for a 50-chip APC segment (ecrecover-shaped), chips sharded over GPUs", "value": ms / 1e3, "unit": "s",
+            "metric": "proof-gen sec for a 50-chip APC segment (ecrecover-shaped), " + ("one transcript (pb_prove_chips)" if one else "chips sharded over GPUs"),
+            "value": ms / 1e3, "unit": "s",
             "n_gpus": world, "steps": a.steps, "warmup": a.warmup, "ms_per_step": ms, "higher_is_better": False, "scaling": "strong",
             "vs_baseline": None, "dtype": "u32 (BabyBear, Montgomery)", "data": "synthetic",
             "config": {"workload": "50 chips, widths sum 18508, constraints sum 10511, bus interactions ~0.86 per column (LogUp per chip), heights 2^12..2^18, "
-                                   "%d queries + %d PoW bits per chip; LPT by height*width" % (a.queries, a.pow_bits),
+                                   + ("%d queries + %d PoW bits for the segment; all chips in one proof: mixed-height MMCS x3, one FRI" if one else
+                                      "%d queries + %d PoW bits per chip; LPT by height*width") % (a.queries, a.pow_bits),
+                       "stages_ms": ctx.last_stage_ms() if one else None,
                        "lpt_max_over_mean": mx / mean, "chips_per_rank": [len(p) for p in plan]},
             "gpu_launches": ctx.launch_count() - l0}))
     if world > 1:

@@ -154,6 +154,42 @@ int pb_query_words(size_t log_n, size_t width, size_t perm_width, size_t* words_
 int pb_query_segment(pb_ctx_t* ctx, uint32_t* h_out, size_t out_capacity_words);
 int pb_last_openings(pb_ctx_t* ctx, uint32_t* h_ys, size_t capacity_words);
 
+/* ---- all chips of a segment under ONE transcript -----------------------------------------------------------------------
+ * Replaces engine.prove(pk, ProvingContext{per_air}) with SEVERAL AIRs: the reference collects one AirProvingContext per chip of
+ * the segment (/root/reference/openvm/src/powdr_extension/trace_generator/cuda/mod.rs:415-419 for the APC chip, the VM's other
+ * chips beside it) and proves them in one call (/root/reference/openvm-riscv/src/lib.rs:327-332).  Chips have different heights:
+ *   - three commitments (main, permutation, quotient), each a mixed-height MMCS (Plonky3 MerkleTreeMmcs): leaves hash the rows of
+ *     the tallest matrices; at the level whose size equals a shorter height, node = compress(compress(l, r), hash(rows there));
+ *   - LogUp challenges, alpha, zeta, gamma are shared; every chip with interactions exposes its own cumulative sum (the verifier
+ *     checks that they add up to zero over the segment);
+ *   - opened values in observation order: main at zeta (chip order) | per chip with interactions: perm at zeta, perm at zeta*w_chip |
+ *     quotient chunks at zeta (chip order); column j of that list is batched with gamma^j;
+ *   - ONE FRI: a reduced-opening codeword per distinct LDE height; folding starts from the tallest, and the codeword of a shorter
+ *     height is added to the folded codeword when the fold reaches that height; final polynomial, proof of work and queries as in
+ *     pb_prove_segment.  A query index r has log_max bits; the matrix of a chip with LDE height 2^h opens row r >> (log_max - h).
+ * With one chip the proof equals pb_prove_segment's.  Traces are device-resident (Montgomery, column-major) and must stay valid
+ * until the last pb_query_chips. */
+typedef struct { const pb_air_t* air; const uint32_t* d_trace; size_t log_n; size_t width; } pb_chip_t;
+typedef struct {
+    uint32_t main_root[8], perm_root[8], quotient_root[8];
+    uint32_t logup_alpha[4], logup_beta[4], alpha[4], zeta[4], gamma[4];
+    uint32_t n_fri_layers;
+    uint32_t fri_roots[32][8];
+    uint32_t fri_betas[32][4];
+    uint32_t final_poly[8][4];
+    uint32_t final_len;
+    uint32_t pow_witness;
+    uint32_t pow_bits, n_queries, n_chips, log_max;   /* log_max: log2 of the tallest LDE */
+} pb_chips_proof_t;                  /* all values canonical */
+/* h_cumsums: [n_chips][4] canonical (zero for chips without interactions) */
+int pb_prove_chips(pb_ctx_t* ctx, const pb_chip_t* chips, size_t n_chips, pb_chips_proof_t* proof, uint32_t* h_cumsums);
+/* n_opened Ext4 values; words per query of the layout
+ *   [ r | main rows of all chips | main path (log_max x 8) | perm rows of the chips with interactions | perm path (tallest such chip) |
+ *     quotient rows (8 per chip) | quotient path | per FRI layer i: pair (8), path ((log_max-1-i) x 8) ] */
+int pb_chips_sizes(const pb_chip_t* chips, size_t n_chips, size_t* n_opened, size_t* words_per_query);
+/* queries ([n_queries][words_per_query], may be NULL) and opened values ([n_opened][4], may be NULL) of the last pb_prove_chips */
+int pb_query_chips(pb_ctx_t* ctx, uint32_t* h_queries, size_t queries_capacity_words, uint32_t* h_ys, size_t ys_capacity_words);
+
 /* ---- one segment across G = 2^g GPUs, one process (and one pb_ctx) per GPU: SURVEY.md §8e ----
  * The trace is column-sharded on input (rank r holds columns pb_shard_columns(width, G, r)), the LDE and everything after it
  * is row-sharded (rank r holds rows [r*2N/G, (r+1)*2N/G) of the bit-reversed LDE for ALL columns); one all-to-all of folded

@@ -17,7 +17,7 @@ EXPORTS = [
     "pb_lde_batch", "pb_air_compile", "pb_air_free", "pb_air_is_jit", "pb_air_jit_compile_only", "pb_quotient", "pb_constraint_fold", "pb_merkle_commit",
     "pb_merkle_commit_rows8", "pb_poseidon2_permute", "pb_fri_fold", "pb_eval_at_point", "pb_deep_quotient", "pb_prove_segment", "pb_query_words", "pb_query_segment", "pb_last_openings", "pb_last_stage_ms",
     "pb_ctx_set_fri_params", "pb_air_set_interactions", "pb_air_perm_width", "pb_air_logup_compile_only", "pb_allgather_caps", "pb_bus_compile", "pb_bus_free", "pb_bus_apply",
-    "pb_shard_columns", "pb_lde_shard", "pb_prove_segment_sharded",
+    "pb_shard_columns", "pb_lde_shard", "pb_prove_segment_sharded", "pb_prove_chips", "pb_chips_sizes", "pb_query_chips",
     "pb_launch_count", "pb_leaf_kernel_profile", "_apc_tracegen", "_apc_apply_derived_expr", "_apc_apply_bus",
 ]
 
@@ -71,6 +71,23 @@ class SegmentProof(C.Structure):
         d["fri_betas"] = [list(self.fri_betas[i]) for i in range(n)]
         d["final_poly"] = [list(self.final_poly[i]) for i in range(self.final_len)]
         return d
+
+
+class Chip(C.Structure):
+    """pb_chip_t"""
+    _fields_ = [("air", C.c_void_p), ("d_trace", C.c_void_p), ("log_n", C.c_size_t), ("width", C.c_size_t)]
+
+
+class ChipsProof(C.Structure):
+    """pb_chips_proof_t (include/powdr_b200.h)"""
+    _fields_ = [("main_root", C.c_uint32 * 8), ("perm_root", C.c_uint32 * 8), ("quotient_root", C.c_uint32 * 8),
+                ("logup_alpha", C.c_uint32 * 4), ("logup_beta", C.c_uint32 * 4), ("alpha", C.c_uint32 * 4), ("zeta", C.c_uint32 * 4),
+                ("gamma", C.c_uint32 * 4), ("n_fri_layers", C.c_uint32), ("fri_roots", (C.c_uint32 * 8) * 32),
+                ("fri_betas", (C.c_uint32 * 4) * 32), ("final_poly", (C.c_uint32 * 4) * 8), ("final_len", C.c_uint32),
+                ("pow_witness", C.c_uint32), ("pow_bits", C.c_uint32), ("n_queries", C.c_uint32), ("n_chips", C.c_uint32), ("log_max", C.c_uint32)]
+    VEC = ("main_root", "perm_root", "quotient_root", "logup_alpha", "logup_beta", "alpha", "zeta", "gamma")
+    SCALAR = ("n_fri_layers", "final_len", "pow_witness", "pow_bits", "n_queries", "n_chips", "log_max")
+    as_dict = SegmentProof.as_dict
 
 
 STAGES = ("h2d", "lde", "merkle", "logup_gen", "logup_commit", "quotient", "qlde", "qmerkle", "open", "fri", "pow", "total")
@@ -305,6 +322,22 @@ class Context:
         ys = np.empty((width + 2 * perm_width + 8, 4), dtype=np.uint32)
         _chk(self.lib.pb_last_openings(self.h, ys.ctypes.data_as(C.c_void_p), C.c_size_t(ys.size)), "pb_last_openings")
         return out, ys
+
+    def prove_chips(self, chips, want_queries=True):
+        """chips: [(Air, d_trace_ptr, log_n, width)], device-resident Montgomery traces.  All chips of a segment under one transcript
+        (pb_prove_chips).  -> (proof dict, cumulative sums (K, 4), opened values (n_opened, 4), queries (n_queries, words) or None)"""
+        K = len(chips)
+        arr = (Chip * K)(*[Chip(a.h.value, int(p), int(ln), int(w)) for a, p, ln, w in chips])
+        proof = ChipsProof()
+        cums = np.zeros((K, 4), dtype=np.uint32)
+        _chk(self.lib.pb_prove_chips(self.h, arr, C.c_size_t(K), C.byref(proof), cums.ctypes.data_as(C.c_void_p)), "pb_prove_chips")
+        n_open, wpq = C.c_size_t(), C.c_size_t()
+        _chk(self.lib.pb_chips_sizes(arr, C.c_size_t(K), C.byref(n_open), C.byref(wpq)), "pb_chips_sizes")
+        ys = np.empty((n_open.value, 4), dtype=np.uint32)
+        q = np.empty((self.n_queries, wpq.value), dtype=np.uint32) if want_queries and self.n_queries else None
+        _chk(self.lib.pb_query_chips(self.h, q.ctypes.data_as(C.c_void_p) if q is not None else None, C.c_size_t(q.size if q is not None else 0),
+                                     ys.ctypes.data_as(C.c_void_p), C.c_size_t(ys.size)), "pb_query_chips")
+        return proof.as_dict(), cums, ys, q
 
     def last_stage_ms(self):
         ms = (C.c_float * len(STAGES))()

@@ -170,6 +170,15 @@ struct pb_bus {
     std::vector<unsigned> grid_y;
 };
 
+// one chip of a multi-chip segment (chips.inl): its matrices stay resident between pb_prove_chips and pb_query_chips
+struct McChip {
+    size_t log_n = 0, width = 0, wp = 0, n_chunks = 0, e_main = 0, e_perm = 0, e_q = 0;
+    const pb_air* air = nullptr;
+    const uint32_t* d_trace = nullptr;
+    DevBuf<uint32_t> lde, perm, perm_lde, qnat, qlde;
+    bb::E4 cumsum = {{0u, 0u, 0u, 0u}};
+};
+
 struct pb_ctx {
     int device = 0;
     cudaStream_t stream = nullptr;
@@ -199,6 +208,18 @@ struct pb_ctx {
         Challenger ch;                       // transcript state after the FRI commit phase
         std::vector<uint32_t> ys;            // opened values, Montgomery, [(width + 2 perm_width + 8)][4]
     } seg;
+    // multi-chip segment (chips.inl)
+    DevBuf<uint32_t> ws_mc_dig;              // digests of the shorter height groups until the tree reaches their level
+    struct {
+        bool valid = false, any_lu = false;
+        size_t K = 0, hmax = 0, hperm = 0;
+        uint32_t n_layers = 0;
+        size_t word_off[32] = {0}, tree_off[32] = {0};
+        Challenger ch;
+        std::vector<uint32_t> ys;
+        std::vector<McChip> chips;
+        DevBuf<uint32_t> tree_main, tree_perm, tree_q, ro[32];
+    } mc;
     cudaStream_t copy_stream = nullptr;   // H2D chunks of the host-input pipeline
     cudaStream_t lde_streams[8] = {nullptr};   // PB_LDE_STREAMS experiment
     cudaEvent_t lde_join[8] = {nullptr}, lde_fork = nullptr;
@@ -387,6 +408,9 @@ int pb_ctx_destroy(pb_ctx_t* ctx) {
     ctx->ws_lu_raw.release(); ctx->ws_lu_s.release(); ctx->ws_pow.release();
     ctx->ws_qraw.release(); ctx->ws_shard_send.release(); ctx->ws_shard_recv.release(); ctx->ws_shard_coef.release(); ctx->ws_gather.release(); ctx->ws_gather2.release();
     ctx->ws_qnat.release(); ctx->ws_qlde.release(); ctx->ws_f0.release(); ctx->ws_f1.release(); ctx->ws_state.release();
+    ctx->ws_mc_dig.release(); ctx->mc.tree_main.release(); ctx->mc.tree_perm.release(); ctx->mc.tree_q.release();
+    for (auto& b : ctx->mc.ro) b.release();
+    for (auto& w : ctx->mc.chips) { w.lde.release(); w.perm.release(); w.perm_lde.release(); w.qnat.release(); w.qlde.release(); }
     if (ctx->copy_stream) cudaStreamDestroy(ctx->copy_stream);
     for (int i = 0; i < 2; i++) { if (ctx->ev_copy[i]) cudaEventDestroy(ctx->ev_copy[i]); if (ctx->ev_free[i]) cudaEventDestroy(ctx->ev_free[i]); }
     for (auto& e : ctx->ev) if (e) cudaEventDestroy(e);
@@ -859,13 +883,16 @@ static int eval_at_point_m(pb_ctx* ctx, const uint32_t* d_mat, size_t log_n, siz
 // reduced opening over shift*H' (bit-reversed rows).  `cols[j]` is opened at point zs[grp[j]]; its gamma exponent is j (the order
 // in which the opened values are observed).  ys_m: host, [n_cols][4] Montgomery.  One kernel launch per point (the later ones
 // accumulate into d_out).  rows [row0, row0 + n_rows) of the domain only when n_rows != 0 (cols[] then point at that row block).
+// gamma_start (optional): gamma exponent of cols[0] as a power already computed (multi-chip prover: a chip's block starts at its
+// position in the observation order); accumulate: add to d_out instead of overwriting it.
 static int deep_quotient_groups_m(pb_ctx* ctx, const std::vector<const uint32_t*>& cols, const std::vector<uint32_t>& grp, const std::vector<bb::E4>& zs,
-                                  size_t log_m, uint32_t shift_m, bb::E4 gamma_m, const uint32_t* ys_m, uint32_t* d_out, size_t row0 = 0, size_t n_rows = 0) {
+                                  size_t log_m, uint32_t shift_m, bb::E4 gamma_m, const uint32_t* ys_m, uint32_t* d_out, size_t row0 = 0, size_t n_rows = 0,
+                                  const bb::E4* gamma_start = nullptr, bool accumulate = false) {
     const size_t n_cols = cols.size(), M = n_rows ? n_rows : (size_t)1 << log_m;
     if (n_cols == 0 || grp.size() != n_cols) return PB_ERR_INVALID_ARG;
     std::vector<uint4> gs(n_cols);
     std::vector<bb::E4> ysum(zs.size(), bb::E4{{0u, 0u, 0u, 0u}});
-    bb::E4 cur = {{bb::R1, 0u, 0u, 0u}};
+    bb::E4 cur = gamma_start ? *gamma_start : bb::E4{{bb::R1, 0u, 0u, 0u}};
     for (size_t j = 0; j < n_cols; j++) {
         uint32_t c[4];
         for (int l = 0; l < 4; l++) c[l] = h_from_m(cur.c[l]);
@@ -917,7 +944,7 @@ static int deep_quotient_groups_m(pb_ctx* ctx, const std::vector<const uint32_t*
     deep::deep_quotient_kernel<<<(unsigned)((M + 255) / 256), 256, 0, ctx->stream>>>(segs, M, (int)log_m, row0, shift_m, h_root_of_unity_m((int)log_m),
                                                                                     reinterpret_cast<const uint4*>(ctx->ws_gp.p), ysum[0], zs[0],
                                                                                     two ? ysum[1] : ysum[0], two ? zs[1] : zs[0], two ? 1 : 0,
-                                                                                    reinterpret_cast<uint4*>(d_out));
+                                                                                    reinterpret_cast<uint4*>(d_out), accumulate ? 1 : 0);
     LAUNCHED(ctx);
     CK(cudaGetLastError());
     return 0;
@@ -948,6 +975,7 @@ int pb_deep_quotient(pb_ctx_t* ctx, const uint32_t* const* d_mats, const size_t*
 }
 
 #include "segment.inl"
+#include "chips.inl"
 
 int pb_last_stage_ms(pb_ctx_t* ctx, float ms[PB_N_STAGES]) {
     if (!ctx || !ms) return PB_ERR_INVALID_ARG;

@@ -172,7 +172,7 @@ __device__ __forceinline__ void dq_mac(Acc96 (&acc)[4], uint32_t f, const uint4 
 
 __global__ void __launch_bounds__(256) deep_quotient_kernel(DeepSegs segs, size_t m, int log_m, size_t row0, uint32_t shift_m, uint32_t omega_m,
                                                             const uint4* __restrict__ gpow, bb::E4 ysum, bb::E4 zeta, bb::E4 ysum2, bb::E4 zeta2,
-                                                            int two_points, uint4* __restrict__ out) {
+                                                            int two_points, uint4* __restrict__ out, int accumulate) {
     __shared__ uint4 sg[DQ_CHUNK];
     const size_t r = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     const bool live = r < m;
@@ -256,6 +256,10 @@ __global__ void __launch_bounds__(256) deep_quotient_kernel(DeepSegs segs, size_
         for (int l = 0; l < 4; l++) a2.c[l] = bb::sub(acc96_mod(acc2[l]), ysum2.c[l]);
         bb::E4 d2 = {{bb::sub(x, zeta2.c[0]), bb::neg(zeta2.c[1]), bb::neg(zeta2.c[2]), bb::neg(zeta2.c[3])}};
         v = bb::e4_add(v, bb::e4_mul(a2, e4_inv(d2)));
+    }
+    if (accumulate) {
+        const uint4 o = out[r];
+        v.c[0] = bb::add(v.c[0], o.x); v.c[1] = bb::add(v.c[1], o.y); v.c[2] = bb::add(v.c[2], o.z); v.c[3] = bb::add(v.c[3], o.w);
     }
     out[r] = make_uint4(v.c[0], v.c[1], v.c[2], v.c[3]);
 }

@@ -20,6 +20,12 @@ __global__ void __launch_bounds__(256) fold_kernel(const uint4* __restrict__ in,
     out[j] = make_uint4(r.c[0], r.c[1], r.c[2], r.c[3]);
 }
 
+// f[i] += g[i] over n words (multi-chip FRI: the reduced-opening codeword of a shorter height joins the folded codeword)
+__global__ void __launch_bounds__(256) add_words_kernel(uint32_t* __restrict__ f, const uint32_t* __restrict__ g, size_t n) {
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) f[i] = bb::add(f[i], g[i]);
+}
+
 // FRI input codeword from the two committed quotient-chunk LDEs (8 base columns, column-major, height m):
 // f[r] = Q0[r] + gamma * Q1[r]
 __global__ void __launch_bounds__(256) combine_chunks_kernel(const uint32_t* __restrict__ qlde, size_t m, bb::E4 gamma, uint4* __restrict__ f) {
@@ -98,4 +104,36 @@ __global__ void __launch_bounds__(256) gather_queries_kernel(QueryDesc d, const 
     }
 }
 
+}  // namespace fri
+
+// ---------------- query gathering for the multi-chip prover: generic pieces, one launch per (commitment, matrix) / tree ----------------
+namespace fri {
+// out[q * wpq + off + c] = canonical(mat[c * m + (idx[q] >> shift)])
+__global__ void gather_rows_kernel(const uint32_t* __restrict__ mat, size_t m, uint32_t width, int shift, const uint32_t* __restrict__ idx, uint32_t* __restrict__ out,
+                                   size_t wpq, size_t off) {
+    const size_t r = idx[blockIdx.x] >> shift;
+    uint32_t* o = out + (size_t)blockIdx.x * wpq + off;
+    for (uint32_t c = threadIdx.x; c < width; c += blockDim.x) o[c] = bb::from_monty(mat[(size_t)c * m + r]);
+}
+__global__ void gather_path_kernel(const uint32_t* __restrict__ tree, int log_h, int shift, const uint32_t* __restrict__ idx, uint32_t* __restrict__ out, size_t wpq,
+                                   size_t off) {
+    copy_path(tree, log_h, idx[blockIdx.x] >> shift, out + (size_t)blockIdx.x * wpq + off);
+}
+__global__ void gather_index_kernel(const uint32_t* __restrict__ idx, uint32_t* __restrict__ out, size_t wpq) {
+    if (threadIdx.x == 0) out[(size_t)blockIdx.x * wpq] = idx[blockIdx.x];
+}
+struct FriDesc { const uint32_t* fri_words; const uint32_t* fri_trees; int log_m; int n_layers; size_t word_off[32]; size_t tree_off[32]; };
+__global__ void gather_fri_kernel(FriDesc d, const uint32_t* __restrict__ idx, uint32_t* __restrict__ out, size_t wpq, size_t off) {
+    const size_t r = idx[blockIdx.x];
+    uint32_t* o = out + (size_t)blockIdx.x * wpq + off;
+    for (int i = 0; i < d.n_layers; i++) {
+        const int log_h = d.log_m - 1 - i;
+        const size_t j = r >> (i + 1);
+        const uint32_t* row = d.fri_words + d.word_off[i] + 8 * j;
+        for (uint32_t e = threadIdx.x; e < 8; e += blockDim.x) o[e] = bb::from_monty(row[e]);
+        o += 8;
+        copy_path(d.fri_trees + d.tree_off[i], log_h, j, o);
+        o += 8 * log_h;
+    }
+}
 }  // namespace fri

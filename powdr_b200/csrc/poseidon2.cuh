@@ -268,6 +268,18 @@ __global__ void __launch_bounds__(256, 1) compress_layer_kernel(const uint4* __r
     next[2 * j + 1] = make_uint4(s[4], s[5], s[6], s[7]);
 }
 
+// mixed-height MMCS (Plonky3 MerkleTreeMmcs): a level whose size equals the height of further matrices gets the digest of their rows
+// injected: node[j] = compress(node[j], injected[j])
+__global__ void __launch_bounds__(256, 1) inject_layer_kernel(uint4* __restrict__ nodes, const uint4* __restrict__ injected, size_t n) {
+    size_t j = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= n) return;
+    uint4 a = nodes[2 * j], b = nodes[2 * j + 1], c = injected[2 * j], d = injected[2 * j + 1];
+    uint32_t s[16] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w, c.x, c.y, c.z, c.w, d.x, d.y, d.z, d.w};
+    permute(s);
+    nodes[2 * j] = make_uint4(s[0], s[1], s[2], s[3]);
+    nodes[2 * j + 1] = make_uint4(s[4], s[5], s[6], s[7]);
+}
+
 // the top of the tree in one CTA: layers of n, n/2, ..., 1 nodes laid out back to back starting at `layer`
 __global__ void __launch_bounds__(512) compress_tail_kernel(uint4* layer, uint32_t n) {
     uint4* prev = layer;
