@@ -225,6 +225,12 @@ int pb_lde_shard(pb_ctx_t* ctx, const uint32_t* d_trace, size_t log_n, size_t wi
 int pb_prove_segment_sharded(pb_ctx_t* ctx, const pb_air_t* air, const uint32_t* trace_cols, size_t log_n, size_t width, uint32_t flags,
                              const pb_comm_t* comm, pb_segment_proof_t* proof);
 
+/* The Fiat-Shamir transcript (DuplexChallenger over Poseidon2, width 16, rate 8) runs on the HOST: absorbing the opened values is a
+ * serial sponge (4363 dependent permutations for the keccak shape), so it uses an AVX-512 permutation with the whole state in one
+ * register when the CPU has it (scalar otherwise; PB_HOST_P2_SCALAR=1 forces scalar).  This entry applies that permutation `reps`
+ * times with the default constants, canonical words in and out, without a device: a known-answer / cross-check hook. */
+int pb_host_poseidon2_permute(uint32_t state[16], int reps, int force_scalar, int* used_avx512);
+
 /* per-stage device milliseconds of the last pb_prove_segment:
  * [h2d, lde, merkle, logup_gen, logup_commit, quotient, qlde, qmerkle, open, fri, pow, total] */
 #define PB_N_STAGES 12

@@ -1,6 +1,7 @@
 """Build the sm_100a shared library in-tree (powdr_b200/_lib/libpowdr_b200.so) with nvcc.
 
-One translation unit (csrc/capi.cu) -> one .so exporting the C ABI of include/powdr_b200.h.  Cross-compiles without a GPU.
+One CUDA translation unit (csrc/capi.cu) plus the host-only transcript permutation (csrc/transcript_host.cpp, g++) -> one .so
+exporting the C ABI of include/powdr_b200.h.  Cross-compiles without a GPU.
 """
 import os
 import subprocess
@@ -11,6 +12,7 @@ CSRC = os.path.join(HERE, "csrc")
 LIB_DIR = os.path.join(HERE, "_lib")
 LIB = os.path.join(LIB_DIR, "libpowdr_b200.so")
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
+CXX = os.environ.get("CXX", "/usr/bin/g++")
 FLAGS = ["-std=c++17", "-O3", "-ldl", "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo",
          "-Xcompiler", "-fPIC", "-shared", "-ccbin", "/usr/bin/g++"]
 
@@ -33,7 +35,9 @@ def build(force=False, verbose=False):
     if not force and not stale():
         return LIB
     os.makedirs(LIB_DIR, exist_ok=True)
-    cmd = [NVCC] + FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-o", LIB, os.path.join(CSRC, "capi.cu")]
+    host_obj = os.path.join(LIB_DIR, "transcript_host.o")
+    subprocess.check_call([CXX, "-std=c++17", "-O3", "-fPIC", "-c", os.path.join(CSRC, "transcript_host.cpp"), "-o", host_obj])
+    cmd = [NVCC] + FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-o", LIB, os.path.join(CSRC, "capi.cu"), host_obj]
     subprocess.check_call(cmd)
     return LIB
 

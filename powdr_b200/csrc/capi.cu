@@ -25,6 +25,7 @@
 #include "ntt_tma.cuh"
 #include "poseidon2.cuh"
 #include "tracegen.cuh"
+#include "transcript_host.h"
 
 #define CK(x)                                  \
     do {                                       \
@@ -41,46 +42,9 @@ inline uint32_t h_from_m(uint32_t m) { return bb::from_monty(m); }
 inline uint32_t h_root_of_unity_m(int log_n) { return bb::pow(h_to_m(bb::GEN), (uint64_t)(bb::P - 1) >> log_n); }
 inline bb::E4 h_e4_from_canon(const uint32_t v[4]) { bb::E4 r; for (int i = 0; i < 4; i++) r.c[i] = h_to_m(v[i]); return r; }
 
-struct P2Host {   // Montgomery constants for the host-side transcript permutation
-    uint32_t rc_ext[8][16], rc_int[13], diag[16];
-};
-
-void host_external_linear(uint32_t s[16]) {
-    // M4 = [[2,3,1,1],[1,2,3,1],[1,1,2,3],[3,1,1,2]] on each 4-chunk as an add chain, then add the column sums
-    for (int c = 0; c < 16; c += 4) {
-        const uint32_t x0 = s[c], x1 = s[c + 1], x2 = s[c + 2], x3 = s[c + 3];
-        const uint32_t t01 = bb::add(x0, x1), t23 = bb::add(x2, x3), t0123 = bb::add(t01, t23);
-        const uint32_t t01123 = bb::add(t0123, x1), t01233 = bb::add(t0123, x3);
-        s[c + 3] = bb::add(t01233, bb::dbl(x0));
-        s[c + 1] = bb::add(t01123, bb::dbl(x2));
-        s[c] = bb::add(t01123, t01);
-        s[c + 2] = bb::add(t01233, t23);
-    }
-    uint32_t q[4];
-    for (int i = 0; i < 4; i++) q[i] = bb::add(bb::add(s[i], s[4 + i]), bb::add(s[8 + i], s[12 + i]));
-    for (int i = 0; i < 16; i++) s[i] = bb::add(s[i], q[i & 3]);
-}
-inline uint32_t host_sbox(uint32_t x) {
-    uint32_t x2 = bb::mul(x, x), x3 = bb::mul(x2, x), x4 = bb::mul(x2, x2);
-    return bb::mul(x3, x4);
-}
-void host_permute(uint32_t s[16], const P2Host& k) {
-    host_external_linear(s);
-    for (int r = 0; r < 4; r++) {
-        for (int i = 0; i < 16; i++) s[i] = host_sbox(bb::add(s[i], k.rc_ext[r][i]));
-        host_external_linear(s);
-    }
-    for (int r = 0; r < 13; r++) {
-        s[0] = host_sbox(bb::add(s[0], k.rc_int[r]));
-        uint32_t sum = 0;
-        for (int i = 0; i < 16; i++) sum = bb::add(sum, s[i]);
-        for (int i = 0; i < 16; i++) s[i] = bb::add(sum, bb::mul(s[i], k.diag[i]));
-    }
-    for (int r = 4; r < 8; r++) {
-        for (int i = 0; i < 16; i++) s[i] = host_sbox(bb::add(s[i], k.rc_ext[r][i]));
-        host_external_linear(s);
-    }
-}
+// the transcript's permutation runs on the host (transcript_host.cpp: AVX-512 with a scalar fallback)
+using pbhost::P2Host;
+inline void host_permute(uint32_t s[16], const P2Host& k) { pbhost::permute(s, k); }
 
 // DuplexChallenger<BabyBear, Perm16, 16, 8> on Montgomery values
 struct Challenger {
@@ -416,6 +380,21 @@ int pb_ctx_destroy(pb_ctx_t* ctx) {
     for (auto& e : ctx->ev) if (e) cudaEventDestroy(e);
     for (int i = 0; i < pb_ctx::KPROF; i++) { if (ctx->kp_a[i]) cudaEventDestroy(ctx->kp_a[i]); if (ctx->kp_b[i]) cudaEventDestroy(ctx->kp_b[i]); }
     delete ctx;
+    return 0;
+}
+
+// the transcript's host-side permutation with the default (Plonky3) instance, canonical words in and out; needs no device
+int pb_host_poseidon2_permute(uint32_t state[16], int reps, int force_scalar, int* used_avx512) {
+    if (!state || reps < 0) return PB_ERR_INVALID_ARG;
+    P2Host k;
+    for (int r = 0; r < 8; r++) for (int i = 0; i < 16; i++) k.rc_ext[r][i] = h_to_m(PB_P2_RC_EXT[r][i]);
+    for (int r = 0; r < 13; r++) k.rc_int[r] = h_to_m(PB_P2_RC_INT[r]);
+    for (int i = 0; i < 16; i++) k.diag[i] = h_to_m(PB_P2_DIAG_M1[i]);
+    uint32_t s[16];
+    for (int i = 0; i < 16; i++) s[i] = h_to_m(state[i]);
+    for (int i = 0; i < reps; i++) { if (force_scalar) pbhost::permute_scalar(s, k); else pbhost::permute(s, k); }
+    for (int i = 0; i < 16; i++) state[i] = h_from_m(s[i]);
+    if (used_avx512) *used_avx512 = force_scalar ? 0 : pbhost::uses_avx512();
     return 0;
 }
 

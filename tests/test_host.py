@@ -318,3 +318,31 @@ def test_v1_metrics_json_is_consumed_by_the_reference_tooling(tmp_path):
     out = basic_metrics.extract_metrics(str(path))
     assert out["num_segments"] == 1 and out["powdr_ratio"] == 1.0 and out["powdr_rows"] == 1 << 20
     assert abs(out["app_proof_time_excluding_trace_ms"] - 571.5) < 1e-6 and out["app_proof_cols"] == 2022 + 3348
+
+
+def test_host_transcript_permutation_kat_and_simd_equals_scalar():
+    """the host side of the transcript (AVX-512 when the CPU has it) against the Plonky3 known answer, the scalar version, and the
+    oracle's permutation on random states"""
+    import ctypes as C
+    import powdr_b200
+    from oracle import orc
+    orc.build()
+    lib = powdr_b200.load_library()
+    used = C.c_int(-1)
+    st = (C.c_uint32 * 16)(*range(16))
+    assert lib.pb_host_poseidon2_permute(st, 1, 0, C.byref(used)) == 0
+    kat = [1906786279, 1737026427, 1959749225, 700325316]
+    assert list(st)[:4] == kat and st[15] == 304856115
+    st2 = (C.c_uint32 * 16)(*range(16))
+    assert lib.pb_host_poseidon2_permute(st2, 1, 1, None) == 0 and list(st2) == list(st)
+    rng = np.random.default_rng(5)
+    for reps in (1, 2, 7):
+        s = rng.integers(0, 2013265921, 16, dtype=np.uint32)
+        a, b = (C.c_uint32 * 16)(*s.tolist()), (C.c_uint32 * 16)(*s.tolist())
+        assert lib.pb_host_poseidon2_permute(a, reps, 0, None) == 0 and lib.pb_host_poseidon2_permute(b, reps, 1, None) == 0
+        exp = s.copy()
+        for _ in range(reps):
+            exp = np.asarray(orc.poseidon2_permute(exp), dtype=np.uint32)
+        assert list(a) == list(b) == exp.tolist()
+    assert lib.pb_host_poseidon2_permute(None, 1, 0, None) == -1
+    assert used.value in (0, 1)
