@@ -27,6 +27,7 @@ extern "C" {
 #define PB_ERR_BAD_BYTECODE (-4)
 #define PB_ERR_NO_DEVICE (-5)
 #define PB_ERR_COMM (-6)          /* a caller-supplied collective (pb_comm_t) reported failure */
+#define PB_ERR_INTERNAL (-7)      /* a self-check failed (the host replay of the device-driven FRI transcript disagreed): a bug */
 
 #define PB_BABYBEAR_P 2013265921u
 #define PB_DIGEST_WORDS 8

@@ -173,6 +173,7 @@ struct pb_ctx {
         std::vector<uint32_t> ys;            // opened values, Montgomery, [(width + 2 perm_width + 8)][4]
     } seg;
     // multi-chip segment (chips.inl)
+    DevBuf<uint32_t> ws_fri_ch, ws_fri_log;  // device challenger state and the (root, beta) log of the FRI commit phase
     DevBuf<uint32_t> ws_mc_dig;              // digests of the shorter height groups until the tree reaches their level
     struct {
         bool valid = false, any_lu = false;
@@ -295,20 +296,28 @@ int get_fold_table(pb_ctx* ctx, int log_len) {
     return 0;
 }
 
-// Merkle layers above the leaves: node-major, layer k+1 follows layer k
+// Merkle layers above the leaves: node-major, layer k+1 follows layer k.  Levels with more than MERKLE_COOP nodes are throughput
+// work: compress_block_kernel, one thread per permutation, up to 10 levels per launch.  Below that every level is ONE permutation
+// latency however few nodes it has (measured ~8.5 us per level one-thread-per-permutation, ~6 us with 16 lanes per permutation), so
+// they run on compress_coop_kernel: 128-node subtrees per CTA, then the last <= 128 nodes in one CTA.  Measured on B200
+// (profiles/README.md round 2c): a 2^12-row chip's FRI phase 1.07 -> 0.77 ms; with the threshold at 8192 nodes the 16-lane form
+// loses to the throughput form on the wider levels (keccak FRI phase 3.6 -> 4.6 ms), hence 1024.
+constexpr size_t MERKLE_COOP = 1024;     // nodes
+constexpr size_t LEAF_COOP = 1024;       // rows: leaf sponges of shorter matrices run 16 lanes per row as well
 int merkle_upper(pb_ctx* ctx, uint32_t* d_layers, size_t log_h) {
     size_t n = (size_t)1 << log_h;
     uint32_t* prev = d_layers;
     while (n > 1) {
-        if (n <= 1024) {
-            p2::compress_tail_kernel<<<1, 512, 0, ctx->stream>>>(reinterpret_cast<uint4*>(prev), (uint32_t)n);
-            LAUNCHED(ctx);
-            break;
-        }
-        // up to 10 levels per launch, leaving at least 1024 nodes for the single-CTA tail
         int kb = 0;
-        while (kb < 10 && (n >> (kb + 1)) >= 1024) kb++;
-        p2::compress_block_kernel<<<(unsigned)(n >> kb), 256, 0, ctx->stream>>>(reinterpret_cast<uint4*>(prev), n, kb);
+        if (n <= MERKLE_COOP) {
+            while (kb < 7 && ((size_t)1 << (kb + 1)) <= n) kb++;
+            const unsigned threads = 16u * (unsigned)std::max<size_t>(2, ((size_t)1 << kb) / 2);       // one group per first-level parent
+            p2::compress_coop_kernel<<<(unsigned)(n >> kb), threads, 0, ctx->stream>>>(prev, n, kb);
+        } else {
+            while (kb < 10 && (n >> (kb + 1)) >= MERKLE_COOP) kb++;
+            const unsigned threads = (unsigned)std::min<size_t>(256, std::max<size_t>(32, ((size_t)1 << kb) / 2));
+            p2::compress_block_kernel<<<(unsigned)(n >> kb), threads, 0, ctx->stream>>>(reinterpret_cast<uint4*>(prev), n, kb);
+        }
         LAUNCHED(ctx);
         for (int l = 0; l < kb; l++) { prev += 8 * n; n >>= 1; }
     }
@@ -372,6 +381,7 @@ int pb_ctx_destroy(pb_ctx_t* ctx) {
     ctx->ws_lu_raw.release(); ctx->ws_lu_s.release(); ctx->ws_pow.release();
     ctx->ws_qraw.release(); ctx->ws_shard_send.release(); ctx->ws_shard_recv.release(); ctx->ws_shard_coef.release(); ctx->ws_gather.release(); ctx->ws_gather2.release();
     ctx->ws_qnat.release(); ctx->ws_qlde.release(); ctx->ws_f0.release(); ctx->ws_f1.release(); ctx->ws_state.release();
+    ctx->ws_fri_ch.release(); ctx->ws_fri_log.release();
     ctx->ws_mc_dig.release(); ctx->mc.tree_main.release(); ctx->mc.tree_perm.release(); ctx->mc.tree_q.release();
     for (auto& b : ctx->mc.ro) b.release();
     for (auto& w : ctx->mc.chips) { w.lde.release(); w.perm.release(); w.perm_lde.release(); w.qnat.release(); w.qlde.release(); }
@@ -762,7 +772,10 @@ int pb_merkle_commit(pb_ctx_t* ctx, const uint32_t* const* d_mats, const size_t*
     CK(cudaMemcpyAsync(ctx->coltab.p, cols.data(), cols.size() * sizeof(void*), cudaMemcpyHostToDevice, ctx->stream));
     const int slot = ctx->kp_n < pb_ctx::KPROF ? ctx->kp_n : -1;
     if (slot >= 0) CK(cudaEventRecord(ctx->kp_a[slot], ctx->stream));
-    p2::leaf_hash_cols_kernel<<<(unsigned)((h + p2::LEAF_THREADS - 1) / p2::LEAF_THREADS), p2::LEAF_THREADS, 0, ctx->stream>>>(ctx->coltab.p, (uint32_t)cols.size(), h, d_layers);
+    if (h <= LEAF_COOP)
+        p2::leaf_hash_cols_coop_kernel<<<(unsigned)((16 * h + 255) / 256), 256, 0, ctx->stream>>>(ctx->coltab.p, (uint32_t)cols.size(), h, d_layers);
+    else
+        p2::leaf_hash_cols_kernel<<<(unsigned)((h + p2::LEAF_THREADS - 1) / p2::LEAF_THREADS), p2::LEAF_THREADS, 0, ctx->stream>>>(ctx->coltab.p, (uint32_t)cols.size(), h, d_layers);
     LAUNCHED(ctx);
     if (slot >= 0) {
         CK(cudaEventRecord(ctx->kp_b[slot], ctx->stream));
@@ -783,7 +796,10 @@ int pb_merkle_commit(pb_ctx_t* ctx, const uint32_t* const* d_mats, const size_t*
 int pb_merkle_commit_rows8(pb_ctx_t* ctx, const uint32_t* d_rows, size_t log_h, uint32_t* d_layers, uint32_t root_out[8]) {
     if (!ctx || !d_rows || !d_layers) return PB_ERR_INVALID_ARG;
     const size_t h = (size_t)1 << log_h;
-    p2::leaf_hash_rows8_kernel<<<(unsigned)((h + 255) / 256), 256, 0, ctx->stream>>>(reinterpret_cast<const uint4*>(d_rows), h, d_layers);
+    if (h <= LEAF_COOP)
+        p2::leaf_hash_rows8_coop_kernel<<<(unsigned)((16 * h + 255) / 256), 256, 0, ctx->stream>>>(d_rows, h, d_layers);
+    else
+        p2::leaf_hash_rows8_kernel<<<(unsigned)((h + 255) / 256), 256, 0, ctx->stream>>>(reinterpret_cast<const uint4*>(d_rows), h, d_layers);
     LAUNCHED(ctx);
     int rc = merkle_upper(ctx, d_layers, log_h);
     if (rc) return rc;
@@ -828,6 +844,67 @@ int pb_fri_fold(pb_ctx_t* ctx, const uint32_t* d_in, size_t log_len, uint32_t sh
     if (!ctx || !d_in || !d_out || !beta) return PB_ERR_INVALID_ARG;
     if (log_len < 1 || log_len > 27 || shift == 0 || shift >= bb::P) return PB_ERR_UNSUPPORTED;
     return fri_fold_m(ctx, d_in, log_len, h_to_m(shift), h_e4_from_canon(beta), d_out);
+}
+
+// FRI commit phase, device-driven: the codeword at ws_fri_words[0 .. 4 * 2^log_len0) is committed and folded down to length 2 without
+// a host round trip per layer (p2::fri_challenge_kernel keeps the duplex state on the device and hands the challenge to the fold
+// through memory).  Layer codewords / trees stay in ws_fri_words / ws_fri_trees at word_off / tree_off for the query phase.
+// inject (optional, [32]): inject[h] is added to the folded codeword when it reaches length 2^h (multi-chip segments).
+// Afterwards ONE read-back of (roots, challenges, final values) and the host replays the transcript: `ch` advances exactly as if
+// it had driven the phase, and any difference from what the device sampled is PB_ERR_INTERNAL.
+static int fri_commit_phase(pb_ctx* ctx, Challenger& ch, size_t log_len0, uint32_t* const* inject, size_t* word_off, size_t* tree_off,
+                            uint32_t* n_layers, uint32_t fri_roots[32][8], uint32_t fri_betas[32][4], uint32_t fin_m[8], cudaEvent_t after_last_kernel) {
+    cudaStream_t st = ctx->stream;
+    int rc;
+    if (ch.n_in != 0) return PB_ERR_INTERNAL;              // the phase starts right after a sampled challenge: no pending input
+    if ((rc = ctx->ws_fri_ch.ensure(16))) return rc;
+    if ((rc = ctx->ws_fri_log.ensure(32 * 12))) return rc;
+    if ((rc = get_fold_table(ctx, (int)log_len0))) return rc;
+    uint32_t* d_sponge = ctx->ws_fri_ch.p;
+    CK(cudaMemcpyAsync(d_sponge, ch.sponge, 64, cudaMemcpyHostToDevice, st));    // pageable source: staged before the call returns
+    uint32_t* f = ctx->ws_fri_words.p;
+    size_t log_len = log_len0, woff = 0, toff = 0;
+    uint32_t shift_m = h_to_m(bb::GEN), layer = 0;
+    const uint32_t two_inv = bb::inv(h_to_m(2));
+    while (log_len > 1) {
+        uint32_t* tree = ctx->ws_fri_trees.p + toff;
+        word_off[layer] = woff;
+        tree_off[layer] = toff;
+        if ((rc = pb_merkle_commit_rows8(ctx, f, log_len - 1, tree, nullptr))) return rc;
+        uint32_t* lg = ctx->ws_fri_log.p + 12 * layer;
+        p2::fri_challenge_kernel<<<1, 32, 0, st>>>(d_sponge, tree + 8 * (((size_t)2 << (log_len - 1)) - 2), lg);
+        uint32_t* g = f + ((size_t)4 << log_len);
+        const size_t half = (size_t)1 << (log_len - 1);
+        fri::fold_dev_beta_kernel<<<(unsigned)((half + 255) / 256), 256, 0, st>>>(reinterpret_cast<const uint4*>(f), reinterpret_cast<uint4*>(g), half, ctx->d_fold_tab,
+                                                                                lg + 8, bb::mul(two_inv, bb::inv(shift_m)), two_inv);
+        ctx->launches += 2;
+        woff += (size_t)4 << log_len;
+        toff += 8 * (((size_t)2 << (log_len - 1)) - 1);
+        f = g;
+        shift_m = bb::mul(shift_m, shift_m);
+        log_len--;
+        layer++;
+        if (inject && log_len > 1 && inject[log_len]) {
+            const size_t nw = (size_t)4 << log_len;
+            fri::add_words_kernel<<<(unsigned)((nw + 255) / 256), 256, 0, st>>>(f, inject[log_len], nw);
+            LAUNCHED(ctx);
+        }
+    }
+    CK(cudaGetLastError());
+    uint32_t log_h[32 * 12];
+    CK(cudaMemcpyAsync(fin_m, f, 32, cudaMemcpyDeviceToHost, st));
+    if (layer) CK(cudaMemcpyAsync(log_h, ctx->ws_fri_log.p, 48 * (size_t)layer, cudaMemcpyDeviceToHost, st));
+    if (after_last_kernel) CK(cudaEventRecord(after_last_kernel, st));
+    CK(cudaStreamSynchronize(st));
+    for (uint32_t l = 0; l < layer; l++) {
+        ch.observe(log_h + 12 * l, 8);
+        const bb::E4 beta = ch.sample_ext();
+        if (memcmp(beta.c, log_h + 12 * l + 8, 16) != 0) return PB_ERR_INTERNAL;
+        for (int i = 0; i < 8; i++) fri_roots[l][i] = h_from_m(log_h[12 * l + i]);
+        for (int i = 0; i < 4; i++) fri_betas[l][i] = h_from_m(beta.c[i]);
+    }
+    *n_layers = layer;
+    return 0;
 }
 
 // ---------------------------------------------------------------------------------------------------------------------

@@ -41,8 +41,11 @@ int mmcs_commit_dev(pb_ctx* ctx, const std::vector<McMat>& ms, DevBuf<uint32_t>&
         // (pageable source: staged before the call returns; the table itself is reused in stream order)
         uint32_t* dst = h == h0 ? tree.p : ctx->ws_mc_dig.p + dig_off[h];
         const size_t rows = (size_t)1 << h;
-        p2::leaf_hash_cols_kernel<<<(unsigned)((rows + p2::LEAF_THREADS - 1) / p2::LEAF_THREADS), p2::LEAF_THREADS, 0, ctx->stream>>>(ctx->coltab.p, (uint32_t)cols.size(),
-                                                                                                                                      rows, dst);
+        if (rows <= LEAF_COOP)
+            p2::leaf_hash_cols_coop_kernel<<<(unsigned)((16 * rows + 255) / 256), 256, 0, ctx->stream>>>(ctx->coltab.p, (uint32_t)cols.size(), rows, dst);
+        else
+            p2::leaf_hash_cols_kernel<<<(unsigned)((rows + p2::LEAF_THREADS - 1) / p2::LEAF_THREADS), p2::LEAF_THREADS, 0, ctx->stream>>>(ctx->coltab.p, (uint32_t)cols.size(),
+                                                                                                                                          rows, dst);
         LAUNCHED(ctx);
     }
     // levels down to the lowest injected height one by one, then the fused upper-tree launches
@@ -282,39 +285,13 @@ int pb_prove_chips(pb_ctx_t* ctx, const pb_chip_t* chips, size_t K, pb_chips_pro
     RC(ctx->ws_fri_words.ensure(8 * Mmax + 64));
     RC(ctx->ws_fri_trees.ensure(8 * (2 * Mmax)));
     CK(cudaMemcpyAsync(ctx->ws_fri_words.p, ctx->mc.ro[hmax].p, (size_t)16 << hmax, cudaMemcpyDeviceToDevice, st));
-    uint32_t* f = ctx->ws_fri_words.p;
-    size_t log_len = hmax, word_off = 0, tree_off = 0;
-    uint32_t shift_m = h_to_m(bb::GEN);
+    uint32_t* inject[32] = {nullptr};
+    for (size_t h = 2; h < hmax; h++) if (have_h[h]) inject[h] = ctx->mc.ro[h].p;
     uint32_t layer = 0;
-    while (log_len > 1) {
-        uint32_t* tree = ctx->ws_fri_trees.p + tree_off;
-        ctx->mc.word_off[layer] = word_off;
-        ctx->mc.tree_off[layer] = tree_off;
-        RC(pb_merkle_commit_rows8(ctx, f, log_len - 1, tree, nullptr));
-        RC(read_root(ctx, tree, log_len - 1, root_m));
-        for (int i = 0; i < 8; i++) proof->fri_roots[layer][i] = h_from_m(root_m[i]);
-        ch.observe(root_m, 8);
-        const bb::E4 beta = ch.sample_ext();
-        for (int i = 0; i < 4; i++) proof->fri_betas[layer][i] = h_from_m(beta.c[i]);
-        uint32_t* g = f + ((size_t)4 << log_len);
-        RC(fri_fold_m(ctx, f, log_len, shift_m, beta, g));
-        word_off += (size_t)4 << log_len;
-        tree_off += 8 * (((size_t)2 << (log_len - 1)) - 1);
-        f = g;
-        shift_m = bb::mul(shift_m, shift_m);
-        log_len--;
-        layer++;
-        if (log_len > 1 && have_h[log_len]) {
-            const size_t nw = (size_t)4 << log_len;
-            fri::add_words_kernel<<<(unsigned)((nw + 255) / 256), 256, 0, st>>>(f, ctx->mc.ro[log_len].p, nw);
-            LAUNCHED(ctx);
-        }
-    }
+    uint32_t fin[8];
+    RC(fri_commit_phase(ctx, ch, hmax, inject, ctx->mc.word_off, ctx->mc.tree_off, &layer, proof->fri_roots, proof->fri_betas, fin, nullptr));
     proof->n_fri_layers = layer;
     proof->final_len = 2;
-    uint32_t fin[8];
-    CK(cudaMemcpyAsync(fin, f, 32, cudaMemcpyDeviceToHost, st));
-    CK(cudaStreamSynchronize(st));
     for (uint32_t i = 0; i < 2; i++)
         for (int l = 0; l < 4; l++) proof->final_poly[i][l] = h_from_m(fin[4 * i + l]);
     ch.observe(fin, 4);

@@ -20,6 +20,21 @@ __global__ void __launch_bounds__(256) fold_kernel(const uint4* __restrict__ in,
     out[j] = make_uint4(r.c[0], r.c[1], r.c[2], r.c[3]);
 }
 
+// same fold with the challenge read from device memory (Montgomery Ext4, written by p2::fri_challenge_kernel); c = (2*shift)^-1
+__global__ void __launch_bounds__(256) fold_dev_beta_kernel(const uint4* __restrict__ in, uint4* __restrict__ out, size_t half,
+                                                            const uint32_t* __restrict__ inv_tw, const uint32_t* __restrict__ beta4, uint32_t c,
+                                                            uint32_t half_inv) {
+    size_t j = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= half) return;
+    const bb::E4 beta_c = {{bb::mul(__ldg(beta4), c), bb::mul(__ldg(beta4 + 1), c), bb::mul(__ldg(beta4 + 2), c), bb::mul(__ldg(beta4 + 3), c)}};
+    uint4 l = __ldg(in + 2 * j), h = __ldg(in + 2 * j + 1);
+    bb::E4 lo = {{l.x, l.y, l.z, l.w}}, hi = {{h.x, h.y, h.z, h.w}};
+    bb::E4 s = bb::e4_scale(bb::e4_add(lo, hi), half_inv);
+    bb::E4 d = bb::e4_scale(bb::e4_sub(lo, hi), __ldg(inv_tw + j));
+    bb::E4 r = bb::e4_add(s, bb::e4_mul(beta_c, d));
+    out[j] = make_uint4(r.c[0], r.c[1], r.c[2], r.c[3]);
+}
+
 // f[i] += g[i] over n words (multi-chip FRI: the reduced-opening codeword of a shorter height joins the folded codeword)
 __global__ void __launch_bounds__(256) add_words_kernel(uint32_t* __restrict__ f, const uint32_t* __restrict__ g, size_t n) {
     size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;

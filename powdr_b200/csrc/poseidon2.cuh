@@ -280,24 +280,6 @@ __global__ void __launch_bounds__(256, 1) inject_layer_kernel(uint4* __restrict_
     nodes[2 * j + 1] = make_uint4(s[4], s[5], s[6], s[7]);
 }
 
-// the top of the tree in one CTA: layers of n, n/2, ..., 1 nodes laid out back to back starting at `layer`
-__global__ void __launch_bounds__(512) compress_tail_kernel(uint4* layer, uint32_t n) {
-    uint4* prev = layer;
-    for (uint32_t m = n >> 1; m >= 1; m >>= 1) {
-        uint4* next = prev + 4 * (size_t)m;        // previous layer has 2m nodes = 4m uint4
-        for (uint32_t j = threadIdx.x; j < m; j += blockDim.x) {
-            uint4 a = prev[4 * j], b = prev[4 * j + 1], c = prev[4 * j + 2], d = prev[4 * j + 3];
-            uint32_t s[16] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w, c.x, c.y, c.z, c.w, d.x, d.y, d.z, d.w};
-            permute(s);
-            next[2 * j] = make_uint4(s[0], s[1], s[2], s[3]);
-            next[2 * j + 1] = make_uint4(s[4], s[5], s[6], s[7]);
-        }
-        __syncthreads();
-        prev = next;
-        if (m == 1) break;
-    }
-}
-
 // kb tree levels per launch: CTA b reduces nodes [b << kb, (b + 1) << kb) of the level at `level` (n nodes) to one node,
 // writing every intermediate level at its place in the node-major layer array (level l+1 follows level l).  A thread reads
 // back only what its own CTA wrote, so __syncthreads() orders the global traffic.  Cuts the launches of a 2^21-leaf tree
@@ -343,6 +325,124 @@ __global__ void __launch_bounds__(256, 1) grind_kernel(GrindState st, int pos, u
         if (k == pos) s[k] = bb::to_monty(w);
     permute(s);
     if ((bb::from_monty(s[7]) & mask) == 0) atomicMin(found, w);
+}
+
+// ---------------- 16 lanes per permutation: the latency-bound end of the path ----------------
+// One thread per permutation is the throughput shape, but a single permutation then takes ~8 us (5 k dependent-issue instructions
+// in one warp), and the top of every Merkle tree, every small FRI layer and the transcript itself are CHAINS of single
+// permutations: 210 dependent levels in the FRI commit phase of a 2^21 codeword.  Here lane i of a 16-lane group holds state
+// word i: the S-box layer is one x^7 per lane, the external layer is two in-group rotations + two xor-shuffles
+// (y_i = S + x_i + 2 x_(i+1) inside a 4-lane chunk, then the column sums), the internal layer a 4-step xor-shuffle sum plus one
+// Shoup product by the lane's diagonal entry.  ~4x shorter latency per permutation, ~4x more issue slots: used where a level has
+// at most a few thousand permutations.
+struct CoopConsts { uint32_t rc[8], dw, dwp; };
+__device__ __forceinline__ CoopConsts coop_load(int lane) {
+    CoopConsts k;
+#pragma unroll
+    for (int r = 0; r < 8; r++) k.rc[r] = c_p2.rc_ext_mp[r][lane];
+    k.dw = c_p2.diag_w[lane];
+    k.dwp = c_p2.diag_wp[lane];
+    return k;
+}
+__device__ __forceinline__ uint32_t coop_external(uint32_t x, int lane) {
+    const int base = lane & ~3;
+    const uint32_t x1 = __shfl_sync(0xffffffffu, x, base | ((lane + 1) & 3), 16);
+    const uint32_t t = bb::add(x, x1);
+    const uint32_t S = bb::add(t, __shfl_sync(0xffffffffu, t, base | ((lane + 2) & 3), 16));
+    const uint32_t y = bb::add(bb::add(S, x), bb::dbl(x1));
+    const uint32_t a = bb::add(y, __shfl_xor_sync(0xffffffffu, y, 4, 16));
+    const uint32_t q = bb::add(a, __shfl_xor_sync(0xffffffffu, a, 8, 16));
+    return bb::add(y, q);
+}
+// every lane of the warp must call this (full-mask shuffles); lane = threadIdx.x & 15
+__device__ __forceinline__ uint32_t permute_coop16(uint32_t x, int lane, const CoopConsts& k) {
+    x = coop_external(x, lane);
+#pragma unroll
+    for (int r = 0; r < 4; r++) x = coop_external(sbox_rc(x, k.rc[r]), lane);
+#pragma unroll 1
+    for (int r = 0; r < 13; r++) {
+        const uint32_t xs = sbox_rc(x, c_p2.rc_int_mp[r]);
+        x = lane == 0 ? xs : x;
+        uint32_t sum = x;
+#pragma unroll
+        for (int o = 8; o > 0; o >>= 1) sum = bb::add(sum, __shfl_xor_sync(0xffffffffu, sum, o, 16));
+        x = bb::add(sum, mul_const(x, k.dw, k.dwp));
+    }
+#pragma unroll
+    for (int r = 4; r < 8; r++) x = coop_external(sbox_rc(x, k.rc[r]), lane);
+    return x;
+}
+
+// kb tree levels, CTA b reduces nodes [b << kb, (b + 1) << kb) of the level at `level` (n nodes) to one node -- the 16-lane
+// counterpart of compress_block_kernel (grid 1, kb = log2 n: the whole top of a tree).  blockDim.x = 16 * groups.
+__global__ void __launch_bounds__(1024) compress_coop_kernel(uint32_t* level, size_t n, int kb) {
+    const int lane = threadIdx.x & 15;
+    const uint32_t grp = threadIdx.x >> 4, ngrp = blockDim.x >> 4;
+    const CoopConsts k = coop_load(lane);
+    uint32_t* lvl = level;
+    size_t nn = n, off = (size_t)blockIdx.x << kb;
+    uint32_t cnt = 1u << kb;
+    for (int l = 0; l < kb; l++) {
+        uint32_t* next = lvl + 8 * nn;
+        const uint32_t m = cnt >> 1;
+        const size_t q0 = off >> 1;
+        for (uint32_t j0 = 0; j0 < m; j0 += ngrp) {          // the same trip count for every thread: the shuffles need whole warps
+            const uint32_t j = j0 + grp;
+            const bool live = j < m;
+            uint32_t x = live ? lvl[16 * (q0 + j) + lane] : 0u;
+            x = permute_coop16(x, lane, k);
+            if (live && lane < 8) next[8 * (q0 + j) + lane] = x;
+        }
+        __syncthreads();
+        lvl = next;
+        nn >>= 1;
+        cnt = m;
+        off = q0;
+    }
+}
+
+// leaves of a row-major width-8 matrix, one 16-lane group per row (small FRI layers)
+__global__ void __launch_bounds__(256) leaf_hash_rows8_coop_kernel(const uint32_t* __restrict__ rows, size_t height, uint32_t* __restrict__ digests) {
+    const int lane = threadIdx.x & 15;
+    const size_t r = ((size_t)blockIdx.x * blockDim.x + threadIdx.x) >> 4;
+    const bool live = r < height;
+    const CoopConsts k = coop_load(lane);
+    uint32_t x = (live && lane < 8) ? __ldg(rows + 8 * r + lane) : 0u;
+    x = permute_coop16(x, lane, k);
+    if (live && lane < 8) digests[8 * r + lane] = x;
+}
+
+// leaf sponge over column-major matrices, one 16-lane group per row (short chips: the sponge is width/8 DEPENDENT permutations per row)
+__global__ void __launch_bounds__(256) leaf_hash_cols_coop_kernel(const uint32_t* const* __restrict__ cols, uint32_t n_cols, size_t height,
+                                                                  uint32_t* __restrict__ digests) {
+    const int lane = threadIdx.x & 15;
+    const size_t r = ((size_t)blockIdx.x * blockDim.x + threadIdx.x) >> 4;
+    const bool live = r < height;
+    const CoopConsts k = coop_load(lane);
+    uint32_t x = 0u;
+    for (uint32_t c0 = 0; c0 < n_cols; c0 += 8) {            // uniform trip count
+        const uint32_t c = c0 + lane;
+        if (live && lane < 8 && c < n_cols) x = __ldg(cols[c] + r);      // overwrite mode: a partial last block leaves the other words
+        x = permute_coop16(x, lane, k);
+    }
+    if (live && lane < 8) digests[8 * r + lane] = x;
+}
+
+// The FRI commit phase without a host round trip per layer: the duplex sponge lives in device memory, one 16-lane group absorbs
+// the layer's root (8 words, overwrite mode, exactly one permutation: the challenger has no pending input between layers) and the
+// folding challenge is output words 7..4.  Root and challenge are logged so that the host can replay the transcript afterwards
+// (it stays the authority: a mismatch is an internal error) and fill the proof.
+__global__ void __launch_bounds__(32) fri_challenge_kernel(uint32_t* sponge16, const uint32_t* __restrict__ root, uint32_t* __restrict__ log12) {
+    const int lane = threadIdx.x & 15;
+    const bool first = threadIdx.x < 16;
+    const CoopConsts k = coop_load(lane);
+    uint32_t x = lane < 8 ? root[lane] : sponge16[lane];
+    if (first && lane < 8) log12[lane] = x;
+    x = permute_coop16(x, lane, k);
+    if (first) {
+        sponge16[lane] = x;
+        if (lane >= 4 && lane < 8) log12[8 + (7 - lane)] = x;
+    }
 }
 
 // single permutation per thread on [n][16] states -- used by tests and the throughput micro-benchmark

@@ -351,36 +351,12 @@ int pb_prove_segment(pb_ctx_t* ctx, const pb_air_t* a, const uint32_t* trace, si
     }
     CK(cudaEventRecord(ctx->ev[9], st));
 
-    // ---- FRI commit phase ----
-    uint32_t* f = ctx->ws_fri_words.p;
-    size_t log_len = log_m, word_off = 0, tree_off = 0;
-    uint32_t shift_m = h_to_m(bb::GEN);
+    // ---- FRI commit phase (device-driven, one read-back at the end) ----
     uint32_t layer = 0;
-    while (log_len > log_blowup) {
-        uint32_t* tree = ctx->ws_fri_trees.p + tree_off;
-        ctx->seg.word_off[layer] = word_off;
-        ctx->seg.tree_off[layer] = tree_off;
-        RC(pb_merkle_commit_rows8(ctx, f, log_len - 1, tree, nullptr));
-        RC(read_root(ctx, tree, log_len - 1, root_m));
-        for (int i = 0; i < 8; i++) proof->fri_roots[layer][i] = h_from_m(root_m[i]);
-        ch.observe(root_m, 8);
-        bb::E4 beta = ch.sample_ext();
-        for (int i = 0; i < 4; i++) proof->fri_betas[layer][i] = h_from_m(beta.c[i]);
-        uint32_t* g = f + ((size_t)4 << log_len);
-        RC(fri_fold_m(ctx, f, log_len, shift_m, beta, g));
-        word_off += (size_t)4 << log_len;
-        tree_off += 8 * (((size_t)2 << (log_len - 1)) - 1);
-        f = g;
-        shift_m = bb::mul(shift_m, shift_m);
-        log_len--;
-        layer++;
-    }
+    uint32_t fin[8];
+    RC(fri_commit_phase(ctx, ch, log_m, nullptr, ctx->seg.word_off, ctx->seg.tree_off, &layer, proof->fri_roots, proof->fri_betas, fin, ctx->ev[10]));
     proof->n_fri_layers = layer;
-    proof->final_len = 1u << log_len;
-    uint32_t fin[8 * 4];
-    CK(cudaMemcpyAsync(fin, f, 16 * proof->final_len, cudaMemcpyDeviceToHost, st));
-    CK(cudaEventRecord(ctx->ev[10], st));
-    CK(cudaStreamSynchronize(st));
+    proof->final_len = 1u << log_blowup;
     for (uint32_t i = 0; i < proof->final_len; i++)
         for (int l = 0; l < 4; l++) proof->final_poly[i][l] = h_from_m(fin[4 * i + l]);
     ch.observe(fin, 4);                              // the final polynomial is one constant
