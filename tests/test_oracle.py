@@ -151,6 +151,23 @@ def test_oracle_kats(orc):
     assert orc.fri_fold(np.array(k["fold_in"], dtype=np.uint32), 31, k["fold_beta"]).tolist() == k["fold_out"]
 
 
+def test_two_adic_generators_are_plonky3s(orc):
+    """The subgroup generators the NTT / LDE / FRI domains are built from, against p3-baby-bear's TWO_ADIC_GENERATORS table
+    (recollected public constants: 0x1, 0x78000000, 0x67055c21, 0x5ee99486, 0xbb4c4e4 for 2^0..2^4, 0x67456167 for 2^8,
+    0x1a427a41 for 2^27): Plonky3 derives them as 31^((p-1)/2^k) like the restatement does, so the evaluation domains -- not only
+    the field -- coincide.  Taken from the oracle itself: the evaluations of the polynomial x over the subgroup."""
+    def root(bits):
+        e = np.zeros(1 << bits, dtype=np.uint32)
+        e[1] = 1
+        return int(orc.dft_naive(e, 1)[1])
+    known = {1: 0x78000000, 2: 0x67055c21, 3: 0x5ee99486, 4: 0x0bb4c4e4, 8: 0x67456167}
+    for bits, w in known.items():
+        assert root(bits) == w == pow(31, (P - 1) >> bits, P)
+        assert pow(w, 1 << bits, P) == 1 and pow(w, 1 << (bits - 1), P) == P - 1
+    assert pow(31, (P - 1) >> 27, P) == 0x1a427a41          # generator of the whole 2-adic subgroup
+    assert orc.GENERATOR == 31                               # the coset shift of every LDE is the field generator, as in Plonky3's PCS
+
+
 def test_poseidon2_is_a_permutation_with_full_diffusion(orc):
     a = orc.poseidon2_permute(np.zeros(16, dtype=np.uint32))
     e = np.zeros(16, dtype=np.uint32)
