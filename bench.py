@@ -407,6 +407,7 @@ def sharded_segment(a, ctx, air, dist, dev, stream, world, rank):
     full = torch.randint(0, P, (w, n), dtype=torch.int32, device=dev, generator=gen)
     single = ctx.prove_segment(air, full.data_ptr(), a.log_n, w, on_device=True)
     single_ms = ctx.last_stage_ms()["total"]
+    single_q = ctx.query_segment(a.log_n, w, air.perm_width)[0] if a.queries else None
     first, count = shard_columns(w, world, rank)
     mine = full[first:first + count].clone()
     del full
@@ -434,10 +435,16 @@ def sharded_segment(a, ctx, air, dist, dev, stream, world, rank):
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         return float(t.item()), pr
 
-    sec, proof = timed(lambda: ctx.prove_segment_sharded(air, mine.data_ptr() if count else 0, a.log_n, w, comm, on_device=True))
+    def step_dev():
+        # the same unit of work as the N = 1 step: proof AND the query openings (pb_query_segment_sharded: one more all-gather)
+        pr = ctx.prove_segment_sharded(air, mine.data_ptr() if count else 0, a.log_n, w, comm, on_device=True)
+        return pr, (ctx.query_segment_sharded(comm, a.log_n, w, air.perm_width) if a.queries else None)
+
+    sec, (proof, queries) = timed(step_dev)
     stages = ctx.last_stage_ms()
     calls, nbytes = comm.calls, comm.bytes
-    ok = torch.tensor([1 if proof == single else 0], dtype=torch.int32, device=dev)
+    same = proof == single and (queries is None or bool((queries == single_q).all()))
+    ok = torch.tensor([1 if same else 0], dtype=torch.int32, device=dev)
     dist.all_reduce(ok, op=dist.ReduceOp.MIN)
     out = {"value": sec, "unit": "s", "scaling": "strong", "single_gpu_s": single_ms / 1e3, "speedup": single_ms / 1e3 / sec,
            "proof_equals_single_gpu": bool(ok.item()), "stages_ms": stages,
@@ -448,10 +455,16 @@ def sharded_segment(a, ctx, air, dist, dev, stream, world, rank):
         if count:
             host.copy_(mine)
         torch.cuda.synchronize()
-        esec, eproof = timed(lambda: ctx.prove_segment_sharded(air, host.data_ptr() if count else 0, a.log_n, w, comm, on_device=False))
+        def step_host():
+            pr = ctx.prove_segment_sharded(air, host.data_ptr() if count else 0, a.log_n, w, comm, on_device=False)
+            if a.queries:
+                ctx.query_segment_sharded(comm, a.log_n, w, air.perm_width)
+            return pr
+
+        esec, eproof = timed(step_host)
         import ctypes
         from powdr_b200.capi import SegmentProof
-        out["e2e"] = {"value": esec, "unit": "s", "h2d_bytes_per_step": 4 * w * n, "d2h_bytes_per_step": ctypes.sizeof(SegmentProof) * world,
+        out["e2e"] = {"value": esec, "unit": "s", "h2d_bytes_per_step": 4 * w * n, "d2h_bytes_per_step": (ctypes.sizeof(SegmentProof) + (4 * int(single_q.size) if single_q is not None else 0)) * world,
                       "proof_equals_single_gpu": eproof == single,
                       "stages_ms": ctx.last_stage_ms()}
     return out
@@ -717,7 +730,10 @@ def run_pairing(a):
         torch.cuda.synchronize()
 
     def step():
-        return ctx.prove_segment_sharded(air, mine.data_ptr() if count else 0, a.log_n, w, comm, on_device=True)
+        pr = ctx.prove_segment_sharded(air, mine.data_ptr() if count else 0, a.log_n, w, comm, on_device=True)
+        if a.queries:
+            ctx.query_segment_sharded(comm, a.log_n, w, 0)       # the query openings belong to the unit of work, as at N = 1
+        return pr
 
     for _ in range(a.warmup):
         step()

@@ -220,11 +220,15 @@ int pb_shard_columns(size_t width, int world, int rank, size_t* first, size_t* c
 int pb_lde_shard(pb_ctx_t* ctx, const uint32_t* d_trace, size_t log_n, size_t width, uint32_t shift, int world, int blk, uint32_t* d_out);
 /* trace_cols: this rank's column block [count][2^log_n] (device if PB_TRACE_ON_DEVICE, else host); width: the whole trace's.
  * Bus interactions attached to the AIR are proved here too (the LogUp phase runs on row / column shards); the query
- * phase is not sharded.  FAILURE SEMANTICS: arguments and workspace sizes are checked before the first collective, but a rank that
+ * phase is pb_query_segment_sharded.  FAILURE SEMANTICS: arguments and workspace sizes are checked before the first collective, but a rank that
  * fails later (a CUDA error, a collective reporting failure) returns at once while its peers are still inside a collective -- the
  * caller's collectives must carry the abort (NCCL: a communicator timeout / ncclCommAbort on the failing rank's error path). */
 int pb_prove_segment_sharded(pb_ctx_t* ctx, const pb_air_t* air, const uint32_t* trace_cols, size_t log_n, size_t width, uint32_t flags,
                              const pb_comm_t* comm, pb_segment_proof_t* proof);
+/* query phase of the last pb_prove_segment_sharded, collective over the same ranks: the same indices, layout (pb_query_words) and
+ * words as pb_query_segment after pb_prove_segment on the gathered trace, on every rank.  A row and the bottom of its Merkle path come
+ * from the rank that holds that row block, the top log2(world) levels from the subtree roots kept at commit time; one all-gather. */
+int pb_query_segment_sharded(pb_ctx_t* ctx, const pb_comm_t* comm, uint32_t* h_out, size_t out_capacity_words);
 
 /* The Fiat-Shamir transcript (DuplexChallenger over Poseidon2, width 16, rate 8) runs on the HOST: absorbing the opened values is a
  * serial sponge (4363 dependent permutations for the keccak shape), so it uses an AVX-512 permutation with the whole state in one

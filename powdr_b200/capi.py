@@ -17,7 +17,7 @@ EXPORTS = [
     "pb_lde_batch", "pb_air_compile", "pb_air_free", "pb_air_is_jit", "pb_air_jit_compile_only", "pb_quotient", "pb_constraint_fold", "pb_merkle_commit",
     "pb_merkle_commit_rows8", "pb_poseidon2_permute", "pb_fri_fold", "pb_eval_at_point", "pb_deep_quotient", "pb_prove_segment", "pb_query_words", "pb_query_segment", "pb_last_openings", "pb_last_stage_ms",
     "pb_ctx_set_fri_params", "pb_air_set_interactions", "pb_air_perm_width", "pb_air_logup_compile_only", "pb_allgather_caps", "pb_bus_compile", "pb_bus_free", "pb_bus_apply",
-    "pb_shard_columns", "pb_lde_shard", "pb_prove_segment_sharded", "pb_prove_chips", "pb_chips_sizes", "pb_query_chips", "pb_host_poseidon2_permute",
+    "pb_shard_columns", "pb_lde_shard", "pb_prove_segment_sharded", "pb_query_segment_sharded", "pb_prove_chips", "pb_chips_sizes", "pb_query_chips", "pb_host_poseidon2_permute",
     "pb_launch_count", "pb_leaf_kernel_profile", "_apc_tracegen", "_apc_apply_derived_expr", "_apc_apply_bus",
 ]
 
@@ -311,6 +311,14 @@ class Context:
         _chk(self.lib.pb_prove_segment_sharded(self.h, air.h, C.c_void_p(trace_cols_ptr or 0), C.c_size_t(log_n), C.c_size_t(width),
                                                C.c_uint32(1 if on_device else 0), C.byref(comm.c), C.byref(proof)), "pb_prove_segment_sharded")
         return proof.as_dict()
+
+    def query_segment_sharded(self, comm, log_n, width, perm_width=0):
+        """query openings of the last prove_segment_sharded (collective: every rank calls it, every rank gets the whole set)"""
+        wpq = C.c_size_t()
+        _chk(self.lib.pb_query_words(C.c_size_t(log_n), C.c_size_t(width), C.c_size_t(perm_width), C.byref(wpq)), "pb_query_words")
+        out = np.empty((self.n_queries, wpq.value), dtype=np.uint32)
+        _chk(self.lib.pb_query_segment_sharded(self.h, C.byref(comm.c), out.ctypes.data_as(C.c_void_p), C.c_size_t(out.size)), "pb_query_segment_sharded")
+        return out
 
     def query_segment(self, log_n, width, perm_width=0):
         """-> (n_queries, words_per_query) uint32 array of openings for the last prove_segment (n_queries from set_fri_params),

@@ -172,8 +172,21 @@ struct pb_ctx {
         Challenger ch;                       // transcript state after the FRI commit phase
         std::vector<uint32_t> ys;            // opened values, Montgomery, [(width + 2 perm_width + 8)][4]
     } seg;
-    // multi-chip segment (chips.inl)
     DevBuf<uint32_t> ws_fri_ch, ws_fri_log;  // device challenger state and the (root, beta) log of the FRI commit phase
+    // what pb_query_segment_sharded needs from the last pb_prove_segment_sharded: this rank's row blocks and subtrees stay resident
+    // (ws_lde / ws_perm_lde / ws_qlde, ws_layers*), the FRI layers in ws_fri_words / ws_fri_trees, every tree's G subtree roots here
+    struct {
+        bool valid = false;
+        size_t log_n = 0, width = 0, perm_width = 0;
+        int G = 0, g = 0, rank = 0;
+        uint32_t n_layers = 0;
+        bool layer_sharded[33] = {false};
+        size_t word_off[33] = {0}, tree_off[33] = {0};
+        uint32_t roots_main[16][8], roots_perm[16][8], roots_q[16][8], roots_fri[32][16][8];   // Montgomery
+        Challenger ch;
+    } sh;
+    DevBuf<uint32_t> ws_sh_q, ws_sh_qall;    // this rank's share of the query openings, and all ranks' shares
+    // multi-chip segment (chips.inl)
     DevBuf<uint32_t> ws_mc_dig;              // digests of the shorter height groups until the tree reaches their level
     struct {
         bool valid = false, any_lu = false;
@@ -381,7 +394,7 @@ int pb_ctx_destroy(pb_ctx_t* ctx) {
     ctx->ws_lu_raw.release(); ctx->ws_lu_s.release(); ctx->ws_pow.release();
     ctx->ws_qraw.release(); ctx->ws_shard_send.release(); ctx->ws_shard_recv.release(); ctx->ws_shard_coef.release(); ctx->ws_gather.release(); ctx->ws_gather2.release();
     ctx->ws_qnat.release(); ctx->ws_qlde.release(); ctx->ws_f0.release(); ctx->ws_f1.release(); ctx->ws_state.release();
-    ctx->ws_fri_ch.release(); ctx->ws_fri_log.release();
+    ctx->ws_fri_ch.release(); ctx->ws_fri_log.release(); ctx->ws_sh_q.release(); ctx->ws_sh_qall.release();
     ctx->ws_mc_dig.release(); ctx->mc.tree_main.release(); ctx->mc.tree_perm.release(); ctx->mc.tree_q.release();
     for (auto& b : ctx->mc.ro) b.release();
     for (auto& w : ctx->mc.chips) { w.lde.release(); w.perm.release(); w.perm_lde.release(); w.qnat.release(); w.qlde.release(); }

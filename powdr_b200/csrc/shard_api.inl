@@ -191,7 +191,7 @@ inline void host_compress(const P2Host& k, const uint32_t l[8], const uint32_t r
 }
 
 // all ranks' subtree roots (device, Montgomery) -> the root of the whole tree (host, Montgomery)
-int combine_roots(pb_ctx* ctx, const pb_comm_t* comm, const uint32_t* d_my_root, uint32_t root_m[8]) {
+int combine_roots(pb_ctx* ctx, const pb_comm_t* comm, const uint32_t* d_my_root, uint32_t root_m[8], uint32_t (*sub_roots)[8] = nullptr) {
     int rc = ctx->ws_gather.ensure(8 * (size_t)comm->world);
     if (rc) return rc;
     if (!(comm->flags & PB_COMM_STREAM_ORDERED)) CK(cudaStreamSynchronize(ctx->stream));
@@ -200,6 +200,7 @@ int combine_roots(pb_ctx* ctx, const pb_comm_t* comm, const uint32_t* d_my_root,
     uint32_t nodes[16][8];
     CK(cudaMemcpyAsync(nodes, ctx->ws_gather.p, 32 * (size_t)comm->world, cudaMemcpyDeviceToHost, ctx->stream));
     CK(cudaStreamSynchronize(ctx->stream));
+    if (sub_roots) memcpy(sub_roots, nodes, 32 * (size_t)comm->world);        // the query phase opens paths through this top tree
     for (int n = comm->world; n > 1; n >>= 1)
         for (int i = 0; i < n / 2; i++) {
             uint32_t t[8];
@@ -259,6 +260,7 @@ int pb_prove_segment_sharded(pb_ctx_t* ctx, const pb_air_t* a, const uint32_t* t
     proof->perm_width = (uint32_t)(a->has_lu ? a->lu.perm_width() : 0);
     cudaStream_t st = ctx->stream;
     ctx->seg.valid = false;
+    ctx->sh.valid = false;
 #define RC(x) do { rc = (x); if (rc) return rc; } while (0)
 #define COMM(fn, send, recv, bytes) do { if (!(comm->flags & PB_COMM_STREAM_ORDERED)) CK(cudaStreamSynchronize(st)); if (comm->fn(comm->user, (send), (recv), (bytes))) return PB_ERR_COMM; } while (0)
     CK(cudaEventRecord(ctx->ev[0], st));
@@ -307,7 +309,7 @@ int pb_prove_segment_sharded(pb_ctx_t* ctx, const pb_air_t* a, const uint32_t* t
         RC(pb_merkle_commit(ctx, mats1, &width, 1, log_ms, ctx->ws_layers.p, nullptr));
     }
     CK(cudaEventRecord(ctx->ev[3], st));
-    RC(combine_roots(ctx, comm, root_ptr(ctx->ws_layers.p, log_ms), root_m));
+    RC(combine_roots(ctx, comm, root_ptr(ctx->ws_layers.p, log_ms), root_m, ctx->sh.roots_main));
     for (int i = 0; i < 8; i++) proof->trace_root[i] = h_from_m(root_m[i]);
     ch.observe(root_m, 8);
 
@@ -374,7 +376,7 @@ int pb_prove_segment_sharded(pb_ctx_t* ctx, const pb_air_t* a, const uint32_t* t
             const uint32_t* matsp[1] = {ctx->ws_perm_lde.p};
             RC(pb_merkle_commit(ctx, matsp, &wp, 1, log_ms, ctx->ws_layers_p.p, nullptr));
         }
-        RC(combine_roots(ctx, comm, root_ptr(ctx->ws_layers_p.p, log_ms), root_m));
+        RC(combine_roots(ctx, comm, root_ptr(ctx->ws_layers_p.p, log_ms), root_m, ctx->sh.roots_perm));
         for (int i = 0; i < 8; i++) proof->perm_root[i] = h_from_m(root_m[i]);
         ch.observe(root_m, 8);
         ch.observe(cumsum.c, 4);
@@ -439,7 +441,7 @@ int pb_prove_segment_sharded(pb_ctx_t* ctx, const pb_air_t* a, const uint32_t* t
         RC(pb_merkle_commit(ctx, mats2, w2, 2, log_ms, ctx->ws_layers_q.p, nullptr));
     }
     CK(cudaEventRecord(ctx->ev[6], st));
-    RC(combine_roots(ctx, comm, root_ptr(ctx->ws_layers_q.p, log_ms), root_m));
+    RC(combine_roots(ctx, comm, root_ptr(ctx->ws_layers_q.p, log_ms), root_m, ctx->sh.roots_q));
     for (int i = 0; i < 8; i++) proof->quotient_root[i] = h_from_m(root_m[i]);
     ch.observe(root_m, 8);
     const bb::E4 zeta = ch.sample_ext();
@@ -477,9 +479,31 @@ int pb_prove_segment_sharded(pb_ctx_t* ctx, const pb_air_t* a, const uint32_t* t
     const bb::E4 gamma = ch.sample_ext();
     for (int i = 0; i < 4; i++) proof->gamma[i] = h_from_m(gamma.c[i]);
 
-    // ---- reduced opening on my rows ----
-    uint32_t* f = ctx->ws_f0.p;
-    uint32_t* f_next = ctx->ws_f1.p;
+    // ---- reduced opening on my rows: layer 0 of the FRI codewords, which all stay resident (my part of every sharded layer, the whole
+    //      codeword of the replicated ones) together with the layer trees -- the query phase opens them ----
+    size_t SMALL = 14;
+    if (const char* e = getenv("PB_SHARD_FRI_SMALL")) SMALL = std::min<size_t>(24, std::max<size_t>(2, (size_t)atol(e)));
+    {
+        // offsets of every layer's codeword and tree in ws_fri_words / ws_fri_trees (a layer is sharded while log_len - g >= SMALL)
+        size_t woff = 0, toff = 0, ll = log_m;
+        uint32_t li = 0;
+        bool shd = true;
+        while (ll > 1) {
+            if (shd && ll - (size_t)s.g < SMALL) shd = false;
+            ctx->sh.layer_sharded[li] = shd;
+            ctx->sh.word_off[li] = woff;
+            ctx->sh.tree_off[li] = toff;
+            const size_t log_rows = shd ? ll - 1 - (size_t)s.g : ll - 1;
+            woff += (size_t)8 << log_rows;
+            toff += 8 * (((size_t)2 << log_rows) - 1);
+            ll--;
+            li++;
+        }
+        ctx->sh.word_off[li] = woff;                     // the final values (2 Ext4) follow the last layer
+        RC(ctx->ws_fri_words.ensure(woff + 64));
+        RC(ctx->ws_fri_trees.ensure(toff + 64));
+    }
+    uint32_t* f = ctx->ws_fri_words.p;
     {
         std::vector<const uint32_t*> cols(n_open);
         std::vector<uint32_t> grp(n_open, 0u);
@@ -495,27 +519,27 @@ int pb_prove_segment_sharded(pb_ctx_t* ctx, const pb_air_t* a, const uint32_t* t
     CK(cudaEventRecord(ctx->ev[8], st));
 
     // ---- FRI commit phase: fold partners are adjacent, so a row block folds locally; per layer only the subtree root travels.
-    //      Below 2^SMALL entries per rank the codeword is gathered once and the remaining layers run replicated. ----
+    //      Below 2^SMALL entries per rank the codeword is gathered once and the remaining layers run replicated: every sharded layer
+    //      costs one (latency-bound) root exchange, a replicated layer of 2^k entries costs microseconds. ----
     uint32_t layer = 0;
     bool sharded = true;
-    RC(ctx->ws_fri_trees.ensure(8 * (2 * N)));
     size_t log_len = log_m;
     uint32_t shift_m = h_to_m(bb::GEN);
-    // every sharded layer costs one (latency-bound) root exchange, a replicated layer of 2^k entries costs microseconds: switch early
-    size_t SMALL = 14;
-    if (const char* e = getenv("PB_SHARD_FRI_SMALL")) SMALL = std::min<size_t>(24, std::max<size_t>(2, (size_t)atol(e)));
     while (log_len > 1) {
-        if (sharded && log_len - (size_t)s.g < SMALL) {
+        if (sharded && !ctx->sh.layer_sharded[layer]) {
+            // my part of this layer's codeword sits where the last fold wrote it; the gathered whole codeword takes this layer's slot
             const size_t loc = (size_t)1 << (log_len - s.g);
-            COMM(all_gather, f, f_next, 16 * loc);
-            std::swap(f, f_next);
+            RC(ctx->ws_f0.ensure(4 * loc));
+            CK(cudaMemcpyAsync(ctx->ws_f0.p, f, 16 * loc, cudaMemcpyDeviceToDevice, st));
+            COMM(all_gather, ctx->ws_f0.p, f, 16 * loc);
             sharded = false;
         }
-        uint32_t* tree = ctx->ws_fri_trees.p;
+        uint32_t* tree = ctx->ws_fri_trees.p + ctx->sh.tree_off[layer];
+        uint32_t* f_next = ctx->ws_fri_words.p + ctx->sh.word_off[layer + 1];      // (the slot after the last layer holds the final values)
         if (sharded) {
             const size_t log_rows = log_len - 1 - (size_t)s.g, loc_out = (size_t)1 << log_rows;
             RC(pb_merkle_commit_rows8(ctx, f, log_rows, tree, nullptr));
-            RC(combine_roots(ctx, comm, root_ptr(tree, log_rows), root_m));
+            RC(combine_roots(ctx, comm, root_ptr(tree, log_rows), root_m, ctx->sh.roots_fri[layer]));
             for (int i = 0; i < 8; i++) proof->fri_roots[layer][i] = h_from_m(root_m[i]);
             ch.observe(root_m, 8);
             const bb::E4 beta = ch.sample_ext();
@@ -530,7 +554,7 @@ int pb_prove_segment_sharded(pb_ctx_t* ctx, const pb_air_t* a, const uint32_t* t
             for (int i = 0; i < 4; i++) proof->fri_betas[layer][i] = h_from_m(beta.c[i]);
             RC(fri_fold_m(ctx, f, log_len, shift_m, beta, f_next));
         }
-        std::swap(f, f_next);
+        f = f_next;
         shift_m = bb::mul(shift_m, shift_m);
         log_len--;
         layer++;
@@ -549,9 +573,15 @@ int pb_prove_segment_sharded(pb_ctx_t* ctx, const pb_air_t* a, const uint32_t* t
         uint32_t w = 0;
         RC(grind(ctx, ch, ctx->pow_bits, &w));
         proof->pow_witness = w;
+        const uint32_t w_m = h_to_m(w);
+        ch.observe(&w_m, 1);
+        (void)ch.sample();
     }
     CK(cudaEventRecord(ctx->ev[9], st));
     CK(cudaStreamSynchronize(st));
+    ctx->sh.valid = true;
+    ctx->sh.log_n = log_n; ctx->sh.width = width; ctx->sh.perm_width = wp; ctx->sh.G = G; ctx->sh.g = s.g; ctx->sh.rank = rho; ctx->sh.n_layers = layer;
+    ctx->sh.ch = ch;
     // stage clocks in the layout of pb_last_stage_ms (no LogUp phase here)
     float t[8];
     for (int i = 0; i < 6; i++) cudaEventElapsedTime(&t[i], ctx->ev[i], ctx->ev[i + 1]);
@@ -567,5 +597,171 @@ int pb_prove_segment_sharded(pb_ctx_t* ctx, const pb_air_t* a, const uint32_t* t
     cudaEventElapsedTime(&ctx->stage_ms[11], ctx->ev[0], ctx->ev[9]);
 #undef COMM
 #undef RC
+    return 0;
+}
+
+// ---- query phase of the sharded prover ---------------------------------------------------------------------------------
+// Same indices and the same output as pb_query_segment after pb_prove_segment on the gathered trace.  Row r of a committed matrix
+// lives on rank r >> log2(Ms) together with the bottom log2(Ms) levels of its Merkle path (that rank's subtree); the top g levels run
+// through the G subtree roots every rank kept from the commit.  Each rank gathers what it owns into a zeroed [n_queries][words]
+// buffer, ONE all-gather brings the shares together (every word has exactly one owner, so the shares add up), the host fills in the
+// top-of-tree siblings.
+namespace shard {
+
+struct QueryDesc {
+    const uint32_t *lde, *plde, *qlde, *tree_t, *tree_p, *tree_q, *fri_words, *fri_trees;
+    size_t ms;                       // rows per rank of the LDE matrices
+    uint32_t width, perm_width;
+    int log_m, log_ms, g, rank, n_layers;
+    size_t word_off[32], tree_off[32];
+    uint32_t sharded_mask;           // bit i: FRI layer i is sharded
+};
+
+// levels [0, n_local) of the path of leaf `idx_local` in a local subtree (layers node-major); canonical words
+__device__ __forceinline__ void copy_local_path(const uint32_t* tree, int log_h, size_t idx_local, uint32_t* out) {
+    for (int k = 0; k < log_h; k++) {
+        const size_t level_off = ((size_t)2 << log_h) - ((size_t)2 << (log_h - k));
+        const uint32_t* node = tree + 8 * (level_off + ((idx_local >> k) ^ 1));
+        for (int e = threadIdx.x; e < 8; e += blockDim.x) out[8 * k + e] = bb::from_monty(node[e]);
+    }
+}
+
+__global__ void __launch_bounds__(256) gather_share_kernel(QueryDesc d, const uint32_t* __restrict__ indices, uint32_t* __restrict__ out, size_t wpq) {
+    const size_t r = indices[blockIdx.x];
+    uint32_t* o = out + (size_t)blockIdx.x * wpq;
+    const bool own = (int)(r >> d.log_ms) == d.rank;
+    const size_t rl = r & (d.ms - 1);
+    if (d.rank == 0 && threadIdx.x == 0) o[0] = (uint32_t)r;
+    o += 1;
+    if (own) {
+        for (uint32_t c = threadIdx.x; c < d.width; c += blockDim.x) o[c] = bb::from_monty(d.lde[(size_t)c * d.ms + rl]);
+        copy_local_path(d.tree_t, d.log_ms, rl, o + d.width);
+    }
+    o += d.width + 8 * d.log_m;
+    if (d.perm_width) {
+        if (own) {
+            for (uint32_t c = threadIdx.x; c < d.perm_width; c += blockDim.x) o[c] = bb::from_monty(d.plde[(size_t)c * d.ms + rl]);
+            copy_local_path(d.tree_p, d.log_ms, rl, o + d.perm_width);
+        }
+        o += d.perm_width + 8 * d.log_m;
+    }
+    if (own) {
+        for (uint32_t c = threadIdx.x; c < 8; c += blockDim.x) o[c] = bb::from_monty(d.qlde[(size_t)c * d.ms + rl]);
+        copy_local_path(d.tree_q, d.log_ms, rl, o + 8);
+    }
+    o += 8 + 8 * d.log_m;
+    for (int i = 0; i < d.n_layers; i++) {
+        const int log_h = d.log_m - 1 - i;                 // rows of the layer's tree (pairs)
+        const size_t j = r >> (i + 1);
+        if ((d.sharded_mask >> i) & 1u) {
+            const int log_loc = log_h - d.g;
+            if ((int)(j >> log_loc) == d.rank) {
+                const size_t jl = j & (((size_t)1 << log_loc) - 1);
+                const uint32_t* row = d.fri_words + d.word_off[i] + 8 * jl;
+                for (uint32_t e = threadIdx.x; e < 8; e += blockDim.x) o[e] = bb::from_monty(row[e]);
+                copy_local_path(d.fri_trees + d.tree_off[i], log_loc, jl, o + 8);
+            }
+        } else if (d.rank == 0) {
+            const uint32_t* row = d.fri_words + d.word_off[i] + 8 * j;
+            for (uint32_t e = threadIdx.x; e < 8; e += blockDim.x) o[e] = bb::from_monty(row[e]);
+            copy_local_path(d.fri_trees + d.tree_off[i], log_h, j, o + 8);
+        }
+        o += 8 + 8 * log_h;
+    }
+}
+
+// out[i] = sum over ranks of all[rank * n + i]  (one non-zero term per word)
+__global__ void __launch_bounds__(256) sum_shares_kernel(const uint32_t* __restrict__ all, int G, size_t n, uint32_t* __restrict__ out) {
+    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    uint32_t v = 0;
+    for (int b = 0; b < G; b++) v += all[(size_t)b * n + i];
+    out[i] = v;
+}
+
+}  // namespace shard
+
+namespace {
+// siblings along the path of leaf `blk` in the tree over the G subtree roots, bottom-up, canonical words: out[g][8]
+void top_path(const P2Host& k, const uint32_t (*roots)[8], int G, int blk, uint32_t* out) {
+    uint32_t nodes[16][8];
+    memcpy(nodes, roots, 32 * (size_t)G);
+    int lvl = 0;
+    for (int n = G; n > 1; n >>= 1, lvl++) {
+        const int sib = (blk >> lvl) ^ 1;
+        for (int e = 0; e < 8; e++) out[8 * lvl + e] = h_from_m(nodes[sib][e]);
+        for (int i = 0; i < n / 2; i++) {
+            uint32_t t[8];
+            host_compress(k, nodes[2 * i], nodes[2 * i + 1], t);
+            memcpy(nodes[i], t, 32);
+        }
+    }
+}
+}  // namespace
+
+int pb_query_segment_sharded(pb_ctx_t* ctx, const pb_comm_t* comm, uint32_t* h_out, size_t out_capacity_words) {
+    if (!ctx || !comm || !comm->all_gather || !h_out) return PB_ERR_INVALID_ARG;
+    if (!ctx->sh.valid || comm->world != ctx->sh.G || comm->rank != ctx->sh.rank) return PB_ERR_INVALID_ARG;
+    const size_t nq = ctx->n_queries;
+    if (nq == 0) return 0;
+    const size_t log_n = ctx->sh.log_n, log_m = log_n + 1, width = ctx->sh.width, wp = ctx->sh.perm_width;
+    const int G = ctx->sh.G, g = ctx->sh.g, rho = ctx->sh.rank;
+    const size_t log_ms = log_m - (size_t)g, Ms = (size_t)1 << log_ms;
+    const size_t wpq = query_words(log_n, width, wp);
+    if (out_capacity_words < wpq * nq) return PB_ERR_INVALID_ARG;
+    int rc;
+    cudaStream_t st = ctx->stream;
+    std::vector<uint32_t> idx(nq);
+    Challenger ch = ctx->sh.ch;
+    for (size_t q = 0; q < nq; q++) idx[q] = h_from_m(ch.sample()) & (uint32_t)(((size_t)1 << log_m) - 1);
+    if ((rc = ctx->ws_qidx.ensure(nq))) return rc;
+    if ((rc = ctx->ws_sh_q.ensure(wpq * nq))) return rc;
+    if ((rc = ctx->ws_sh_qall.ensure((size_t)G * wpq * nq))) return rc;
+    if ((rc = ctx->ws_qout.ensure(wpq * nq))) return rc;
+    CK(cudaMemcpyAsync(ctx->ws_qidx.p, idx.data(), 4 * nq, cudaMemcpyHostToDevice, st));
+    CK(cudaMemsetAsync(ctx->ws_sh_q.p, 0, 4 * wpq * nq, st));
+    shard::QueryDesc d;
+    d.lde = ctx->ws_lde.p; d.plde = ctx->ws_perm_lde.p; d.qlde = ctx->ws_qlde.p;
+    d.tree_t = ctx->ws_layers.p; d.tree_p = ctx->ws_layers_p.p; d.tree_q = ctx->ws_layers_q.p;
+    d.fri_words = ctx->ws_fri_words.p; d.fri_trees = ctx->ws_fri_trees.p;
+    d.ms = Ms; d.width = (uint32_t)width; d.perm_width = (uint32_t)wp;
+    d.log_m = (int)log_m; d.log_ms = (int)log_ms; d.g = g; d.rank = rho; d.n_layers = (int)ctx->sh.n_layers;
+    d.sharded_mask = 0;
+    for (int i = 0; i < 32; i++) {
+        d.word_off[i] = ctx->sh.word_off[i];
+        d.tree_off[i] = ctx->sh.tree_off[i];
+        if (i < (int)ctx->sh.n_layers && ctx->sh.layer_sharded[i]) d.sharded_mask |= 1u << i;
+    }
+    shard::gather_share_kernel<<<(unsigned)nq, 256, 0, st>>>(d, ctx->ws_qidx.p, ctx->ws_sh_q.p, wpq);
+    LAUNCHED(ctx);
+    CK(cudaGetLastError());
+    if (!(comm->flags & PB_COMM_STREAM_ORDERED)) CK(cudaStreamSynchronize(st));
+    if (comm->all_gather(comm->user, ctx->ws_sh_q.p, ctx->ws_sh_qall.p, 4 * wpq * nq)) return PB_ERR_COMM;
+    shard::sum_shares_kernel<<<(unsigned)((wpq * nq + 255) / 256), 256, 0, st>>>(ctx->ws_sh_qall.p, G, wpq * nq, ctx->ws_qout.p);
+    LAUNCHED(ctx);
+    CK(cudaMemcpyAsync(h_out, ctx->ws_qout.p, 4 * wpq * nq, cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
+    // the top g levels of every path: through the subtree roots gathered at commit time
+    for (size_t q = 0; q < nq; q++) {
+        uint32_t* o = h_out + q * wpq + 1;
+        const size_t r = idx[q];
+        const int blk = (int)(r >> log_ms);
+        top_path(ctx->p2, ctx->sh.roots_main, G, blk, o + width + 8 * log_ms);
+        o += width + 8 * log_m;
+        if (wp) {
+            top_path(ctx->p2, ctx->sh.roots_perm, G, blk, o + wp + 8 * log_ms);
+            o += wp + 8 * log_m;
+        }
+        top_path(ctx->p2, ctx->sh.roots_q, G, blk, o + 8 + 8 * log_ms);
+        o += 8 + 8 * log_m;
+        for (uint32_t i = 0; i < ctx->sh.n_layers; i++) {
+            const size_t log_h = log_m - 1 - i, j = r >> (i + 1);
+            if (ctx->sh.layer_sharded[i]) {
+                const size_t log_loc = log_h - (size_t)g;
+                top_path(ctx->p2, ctx->sh.roots_fri[i], G, (int)(j >> log_loc), o + 8 + 8 * log_loc);
+            }
+            o += 8 + 8 * log_h;
+        }
+    }
     return 0;
 }
