@@ -283,6 +283,10 @@ def test_entry_points_reject_null_arguments_before_touching_the_device():
     assert lib.pb_air_set_interactions(z, z, z, n0, z, n0, z, n0) == INVALID
     assert lib.pb_allgather_caps(z, z, z, z) == INVALID
     assert lib.pb_ctx_set_fri_params(z, C.c_uint32(8), C.c_uint32(4)) == INVALID
+    assert lib.pb_prove_chips(z, z, C.c_size_t(1), z, z) == INVALID
+    assert lib.pb_chips_sizes(z, C.c_size_t(1), z, z) == INVALID
+    assert lib.pb_query_chips(z, z, n0, z, n0) == INVALID
+    assert lib.pb_query_segment_sharded(z, z, z, n0) == INVALID
 
 
 def test_v1_metrics_json_is_consumed_by_the_reference_tooling(tmp_path):

@@ -147,13 +147,37 @@ def _sharded_worker(rank, world, port, ret):
         for m in range(n_blk):
             block[c, _bitrev(m, log_blk)] = ev[m]
     # 4. subtree root, all-gather, top of the tree
-    my_root = orc.merkle_commit([block])[-1][0]
+    layers = orc.merkle_commit([block])                 # my subtree: layers[k][j] = node j of level k
+    my_root = layers[-1][0]
     roots = [torch.zeros(8, dtype=torch.int64) for _ in range(world)]
     dist.all_gather(roots, torch.from_numpy(my_root.astype(np.int64)))
-    nodes = [r.numpy().astype(np.uint32) for r in roots]
+    sub_roots = [r.numpy().astype(np.uint32) for r in roots]
+    nodes = list(sub_roots)
     while len(nodes) > 1:
         nodes = [orc.compress(nodes[2 * i], nodes[2 * i + 1]) for i in range(len(nodes) // 2)]
-    ret[rank] = (block, nodes[0])
+    # 5. query phase (pb_query_segment_sharded): the owner of a row block contributes the row and the bottom of its path into a zeroed
+    #    share, one all-gather, the shares add up; the top log2(world) siblings come from the gathered subtree roots
+    log_ms = log_blk
+    log_m = log_n + 1
+    idx = [int(x) for x in np.random.default_rng(5).integers(0, 2 * n, size=6)]      # same indices on every rank
+    words = width + 8 * log_m
+    share = np.zeros((len(idx), words), dtype=np.int64)
+    for qi, r in enumerate(idx):
+        if r >> log_ms == rank:
+            rl = r & (n_blk - 1)
+            share[qi, :width] = block[:, rl]
+            for k in range(log_ms):
+                share[qi, width + 8 * k: width + 8 * k + 8] = layers[k][(rl >> k) ^ 1]
+    shares = [torch.zeros((len(idx), words), dtype=torch.int64) for _ in range(world)]
+    dist.all_gather(shares, torch.from_numpy(share))
+    q = sum(t.numpy() for t in shares)
+    for qi, r in enumerate(idx):
+        top, lvl, blk = list(sub_roots), 0, r >> log_ms
+        while len(top) > 1:
+            q[qi, width + 8 * (log_ms + lvl): width + 8 * (log_ms + lvl) + 8] = top[(blk >> lvl) ^ 1]
+            top = [orc.compress(top[2 * i], top[2 * i + 1]) for i in range(len(top) // 2)]
+            lvl += 1
+    ret[rank] = (block, nodes[0], idx, q.astype(np.uint32))
     dist.barrier()
     dist.destroy_process_group()
 
@@ -178,7 +202,14 @@ def test_sharded_commit_data_flow_gloo(world):
     lde = orc.lde_batch(trace, 1, orc.GENERATOR)
     ms = lde.shape[1] // world
     root = orc.merkle_commit([lde])[-1][0]
+    full = orc.merkle_commit([lde])
+    log_m = len(full) - 1
     for r in range(world):
-        block, top = ret[r]
+        block, top, idx, q = ret[r]
         assert (block == lde[:, r * ms:(r + 1) * ms]).all(), "rank %d: row block is not the sub-coset evaluation" % r
         assert (top == root).all(), "rank %d: combined root differs from the single-process commitment" % r
+        # the assembled openings are the single-process ones: row, then the sibling at every level of the whole tree
+        for qi, i in enumerate(idx):
+            assert (q[qi, :5] == lde[:, i]).all()
+            for k in range(log_m):
+                assert (q[qi, 5 + 8 * k: 5 + 8 * k + 8] == full[k][(i >> k) ^ 1]).all(), (r, i, k)
