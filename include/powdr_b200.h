@@ -151,6 +151,8 @@ int pb_prove_segment(pb_ctx_t* ctx, const pb_air_t* air, const uint32_t* trace, 
  *     when perm_width = 0) | quotient row (8) | quotient path (log_m x 8) | per FRI layer i: opened pair row (8), path ((log_m-1-i) x 8) ]
  * pb_last_openings: the opened values, [(width + 2*perm_width + 8)][4] canonical:
  *   main at zeta | perm at zeta | perm at zeta*w | quotient chunks at zeta. */
+/* ONE proof state per context: pb_prove_segment, pb_prove_segment_sharded and pb_prove_chips share workspaces, so each of them invalidates
+ * the query state of any earlier proof of the context (a later pb_query_* / pb_last_openings for it returns PB_ERR_INVALID_ARG). */
 int pb_query_words(size_t log_n, size_t width, size_t perm_width, size_t* words_per_query);
 int pb_query_segment(pb_ctx_t* ctx, uint32_t* h_out, size_t out_capacity_words);
 int pb_last_openings(pb_ctx_t* ctx, uint32_t* h_ys, size_t capacity_words);

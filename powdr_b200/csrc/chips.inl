@@ -91,7 +91,8 @@ int pb_chips_sizes(const pb_chip_t* chips, size_t K, size_t* n_opened, size_t* w
 }
 
 int pb_prove_chips(pb_ctx_t* ctx, const pb_chip_t* chips, size_t K, pb_chips_proof_t* proof, uint32_t* h_cumsums) {
-    if (ctx) ctx->mc.valid = false;                    // a failure below must not leave a stale proof state queryable
+    if (ctx) ctx->mc.valid = ctx->seg.valid = ctx->sh.valid = false;      // a failure below must not leave a stale proof state queryable; the
+                                                                          // single-chip provers share the FRI workspaces with this one
     if (!ctx || !chips || !K || !proof || !h_cumsums) return PB_ERR_INVALID_ARG;
     for (size_t c = 0; c < K; c++)
         if (!chips[c].air || !chips[c].d_trace || chips[c].log_n < 1 || chips[c].log_n > 24 || chips[c].width == 0 || chips[c].width != chips[c].air->width)

@@ -133,6 +133,8 @@ int pb_prove_segment(pb_ctx_t* ctx, const pb_air_t* a, const uint32_t* trace, si
     int rc;
     memset(proof, 0, sizeof *proof);
     ctx->seg.valid = false;                           // a failure below must not leave a stale proof state queryable
+    ctx->sh.valid = false;                            // the sharded and the multi-chip prover share workspaces with this one
+    ctx->mc.valid = false;
     proof->pow_bits = ctx->pow_bits;
     proof->n_queries = ctx->n_queries;
     proof->perm_width = (uint32_t)wp;
@@ -424,9 +426,9 @@ int pb_query_segment(pb_ctx_t* ctx, uint32_t* h_out, size_t out_capacity_words) 
     return 0;
 }
 
-// opened values of the last pb_prove_segment, canonical, [(width + 2*perm_width + 8)][4]
+// opened values of the last pb_prove_segment / pb_prove_segment_sharded, canonical, [(width + 2*perm_width + 8)][4]
 int pb_last_openings(pb_ctx_t* ctx, uint32_t* h_ys, size_t capacity_words) {
-    if (!ctx || !h_ys || !ctx->seg.valid || capacity_words < ctx->seg.ys.size()) return PB_ERR_INVALID_ARG;
+    if (!ctx || !h_ys || (!ctx->seg.valid && !ctx->sh.valid) || capacity_words < ctx->seg.ys.size()) return PB_ERR_INVALID_ARG;
     for (size_t i = 0; i < ctx->seg.ys.size(); i++) h_ys[i] = h_from_m(ctx->seg.ys[i]);
     return 0;
 }

@@ -261,6 +261,7 @@ int pb_prove_segment_sharded(pb_ctx_t* ctx, const pb_air_t* a, const uint32_t* t
     cudaStream_t st = ctx->stream;
     ctx->seg.valid = false;
     ctx->sh.valid = false;
+    ctx->mc.valid = false;
 #define RC(x) do { rc = (x); if (rc) return rc; } while (0)
 #define COMM(fn, send, recv, bytes) do { if (!(comm->flags & PB_COMM_STREAM_ORDERED)) CK(cudaStreamSynchronize(st)); if (comm->fn(comm->user, (send), (recv), (bytes))) return PB_ERR_COMM; } while (0)
     CK(cudaEventRecord(ctx->ev[0], st));
