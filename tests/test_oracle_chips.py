@@ -74,3 +74,34 @@ def test_tampering_is_rejected(orc):
     assert v(qq=q3) == 9
     p2 = dict(proof); p2["final_poly"] = [proof["final_poly"][0], [(proof["final_poly"][1][0] + 1) % P] + proof["final_poly"][1][1:]]
     assert v(p2) == 15
+
+
+def test_random_chip_mixes_verify_and_bind_every_opened_value(orc):
+    """hypothesis: 2-4 chips of random heights / widths / interaction counts under one transcript -- the verifier accepts the honest
+    proof and rejects it after ANY single opened value, cumulative sum or query word is changed"""
+    from hypothesis import given, settings, strategies as st
+
+    chip = st.tuples(st.integers(3, 6), st.integers(4, 12), st.integers(0, 3), st.integers(0, 4))
+
+    @settings(max_examples=8, deadline=None)
+    @given(st.lists(chip, min_size=2, max_size=4), st.integers(0, 2**31), st.data())
+    def run(spec, seed, data):
+        spec = [(ln, w, nc if (nc or ni) else 1, ni) for ln, w, nc, ni in spec]       # every chip needs at least one column user
+        chips = _chips(spec, seed=seed)
+        proof, cs, ys, q = orc.prove_chips(chips, n_queries=3, pow_bits=2)
+        assert orc.verify_chips(chips, proof, cs, ys, q, check_constraints=False) == 0
+        y2 = ys.copy()
+        i, l = data.draw(st.integers(0, ys.shape[0] - 1)), data.draw(st.integers(0, 3))
+        y2[i, l] = (int(y2[i, l]) + 1) % P
+        assert orc.verify_chips(chips, proof, cs, y2, q, check_constraints=False) != 0
+        q2 = q.copy()
+        qi, w = data.draw(st.integers(0, q.shape[0] - 1)), data.draw(st.integers(1, q.shape[1] - 1))
+        q2[qi, w] = (int(q2[qi, w]) + 1) % P
+        assert orc.verify_chips(chips, proof, cs, ys, q2, check_constraints=False) != 0
+        if cs.any():
+            c2 = cs.copy()
+            k = int(np.flatnonzero(cs.any(axis=1))[0])
+            c2[k, 0] = (int(c2[k, 0]) + 1) % P
+            assert orc.verify_chips(chips, proof, c2, ys, q, check_constraints=False) != 0
+
+    run()
