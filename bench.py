@@ -57,8 +57,10 @@ def parse():
 
 
 def workload_name(a):
-    return ("guest-keccak APC shape: 2^%d rows x %d cols, %d constraints deg<=3, %d bus interactions (LogUp), log_blowup 1, "
-            "%d queries, %d PoW bits (synthetic AIR + uniform trace)" % (a.log_n, a.width, a.constraints, a.interactions, a.queries, a.pow_bits))
+    shape = (a.log_n, a.width, a.constraints, a.interactions)
+    name = {(20, 2022, 187, 1734): "guest-keccak APC shape", (16, 12035, 3770, 9539): "guest-sha256 largest-APC shape"}.get(shape, "custom APC shape")
+    return ("%s: 2^%d rows x %d cols, %d constraints deg<=3, %d bus interactions (LogUp), log_blowup 1, "
+            "%d queries, %d PoW bits (synthetic AIR + uniform trace)" % (name, a.log_n, a.width, a.constraints, a.interactions, a.queries, a.pow_bits))
 
 
 def machine_for(a):
