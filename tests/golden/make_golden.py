@@ -13,6 +13,8 @@ reference-derived fixtures and the oracle for the generated vectors):  python te
   oracle_kat.json                  known-answer vectors produced BY THE ORACLE (Poseidon2, sponge, compress, challenger,
                                    small LDE / fold) -- regression pins for oracle and GPU alike
   segment_2p8_w12.json             a whole-segment proof produced by the oracle
+  segment_logup_2p7.json           the same with bus interactions (LogUp phase, transcript v2): proof + digests of the opened values / queries
+  chips_mixed.json                 three chips of different heights under one transcript (orc_prove_chips): proof, cumulative sums, digests
 """
 import glob
 import gzip
@@ -90,6 +92,37 @@ def main():
     trace = rand_field(np.random.default_rng(g["trace_seed"]), (mach.width, 1 << g["log_n"]))
     g["proof"], _ = orc.prove_segment(trace, bc, spans)
     dump("segment_2p8_w12.json", g)
+
+    import hashlib
+    sha = lambda a: hashlib.sha256(np.ascontiguousarray(a, dtype=np.uint32).tobytes()).hexdigest()
+    g = {"width": 14, "n_constraints": 4, "n_interactions": 9, "quadratic_every": 4, "seed": 21, "bus_seed": 22, "trace_seed": 777, "log_n": 7,
+         "n_queries": 8, "pow_bits": 4}
+    base = M.synthetic_machine(g["width"], g["n_constraints"], seed=g["seed"])
+    mach = M.SymbolicMachine(base.constraints, M.synthetic_bus(base, g["n_interactions"], g["bus_seed"], g["quadratic_every"]))
+    bc, spans = M.compile_constraints(mach)
+    trace = rand_field(np.random.default_rng(g["trace_seed"]), (mach.width, 1 << g["log_n"]))
+    proof, ys, q, _ = orc.prove(trace, bc, spans, M.compile_bus(mach, 1), n_queries=g["n_queries"], pow_bits=g["pow_bits"])
+    g.update(proof=proof, ys_sha256=sha(ys), queries_sha256=sha(q))
+    dump("segment_logup_2p7.json", g)
+
+    g = {"spec": [[6, 12, 3, 7], [4, 9, 2, 0], [3, 10, 0, 3]], "seed": 5, "n_queries": 6, "pow_bits": 5}
+    chips = chips_for(g["spec"], g["seed"])
+    proof, cs, ys, q = orc.prove_chips(chips, n_queries=g["n_queries"], pow_bits=g["pow_bits"])
+    g.update(proof=proof, cumsums=cs.tolist(), ys_sha256=sha(ys), queries_sha256=sha(q))
+    dump("chips_mixed.json", g)
+
+
+def chips_for(spec, seed):
+    """[(log_n, width, n_constraints, n_interactions)] -> [(trace, bytecode, spans, bus)]; shared with tests/test_oracle_chips.py"""
+    rng = np.random.default_rng(seed)
+    out = []
+    for i, (log_n, width, ncons, nints) in enumerate(spec):
+        base = M.synthetic_machine(width, ncons, seed=100 + i) if ncons else None
+        bus_json = M.synthetic_bus(width, nints, seed=200 + i, quadratic_every=5) if nints else []
+        mach = M.SymbolicMachine(base.constraints if base else [], bus_json)
+        bc, spans = M.compile_constraints(mach)
+        out.append((rand_field(rng, (mach.width, 1 << log_n)), bc, spans, M.compile_bus(mach, 1) if nints else None))
+    return out
 
 
 if __name__ == "__main__":

@@ -105,3 +105,31 @@ def test_random_chip_mixes_verify_and_bind_every_opened_value(orc):
             assert orc.verify_chips(chips, proof, c2, ys, q, check_constraints=False) != 0
 
     run()
+
+
+def test_committed_fixtures_are_reproduced(orc):
+    """tests/golden/segment_logup_2p7.json and chips_mixed.json (written by tests/golden/make_golden.py): regression pins of transcript
+    v2 with the LogUp phase and of the multi-chip transcript -- proof fields exactly, opened values / query openings by digest"""
+    import hashlib
+    import json
+    import os
+    import sys
+    from powdr_b200 import machine as M
+    golden = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+    sys.path.insert(0, golden)
+    from make_golden import chips_for
+    sha = lambda a: hashlib.sha256(np.ascontiguousarray(a, dtype=np.uint32).tobytes()).hexdigest()
+    g = json.load(open(os.path.join(golden, "segment_logup_2p7.json")))
+    base = M.synthetic_machine(g["width"], g["n_constraints"], seed=g["seed"])
+    mach = M.SymbolicMachine(base.constraints, M.synthetic_bus(base, g["n_interactions"], g["bus_seed"], g["quadratic_every"]))
+    bc, spans = M.compile_constraints(mach)
+    trace = rand_field(np.random.default_rng(g["trace_seed"]), (mach.width, 1 << g["log_n"]))
+    for fast in ([False, True] if orc.fast_available() else [False]):
+        proof, ys, q, _ = orc.prove(trace, bc, spans, M.compile_bus(mach, 1), n_queries=g["n_queries"], pow_bits=g["pow_bits"], fast=fast)
+        assert proof == g["proof"] and sha(ys) == g["ys_sha256"] and sha(q) == g["queries_sha256"]
+    g = json.load(open(os.path.join(golden, "chips_mixed.json")))
+    chips = chips_for([tuple(x) for x in g["spec"]], g["seed"])
+    for fast in ([False, True] if orc.fast_available() else [False]):
+        proof, cs, ys, q = orc.prove_chips(chips, n_queries=g["n_queries"], pow_bits=g["pow_bits"], fast=fast)
+        assert proof == g["proof"] and cs.tolist() == g["cumsums"] and sha(ys) == g["ys_sha256"] and sha(q) == g["queries_sha256"]
+    assert orc.verify_chips(chips, proof, cs, ys, q, check_constraints=False) == 0
