@@ -264,6 +264,41 @@ def compile_bus(machine, height):
     return ints, spans, bc
 
 
+def compile_substitutions(opcodes, subs, id_to_index, opcode_to_air=None):
+    """The (`OriginalAir`, `Subst`) tables of stage 0 from an APC's instruction list and its per-instruction substitutions, the way
+    `PowdrTraceGeneratorGpu::try_generate_witness` assembles them (/root/reference/openvm/src/powdr_extension/trace_generator/cuda/mod.rs:268-326):
+    instructions with substitutions are grouped by the original AIR their opcode executes on; an AIR's group index is its
+    `air_index`, an instruction's position inside its group is the `row` of its cells in that AIR's block of rows per APC call
+    (`row_block_size` = group size), `col` = `original_poly_index`, `apc_col` = index of `apc_poly_id` among the machine's columns.
+
+    opcodes: one opcode per instruction (`block.blocks[*].instructions[*][0]` of the reference's APC JSON, SURVEY App. A);
+    subs: per instruction [(original_poly_index, apc_poly_id)]; id_to_index: apc poly id -> column index (SymbolicMachine.id_to_index);
+    opcode_to_air: opcode -> AIR key (`original_airs.opcode_to_air`, an OpenVM table that is not in the reference tree; default: one
+    AIR per opcode).  Rust groups with a HashMap, so the AIR order is arbitrary there; here it is the order of first appearance.
+    -> (airs [(air_key, row_block_size, min_width)], substs [(air_index, col, row, apc_col)])"""
+    assert len(opcodes) == len(subs)
+    air_of = opcode_to_air or (lambda op: op)
+    groups, order = {}, []
+    for op, ss in zip(opcodes, subs):
+        if not ss:
+            continue                                    # an instruction without substitutions contributes no rows (cuda/mod.rs:277-281)
+        key = air_of(op)
+        if key not in groups:
+            groups[key] = []
+            order.append(key)
+        groups[key].append(ss)
+    airs, substs = [], []
+    for air_index, key in enumerate(order):
+        rows = groups[key]
+        width = 0
+        for row, ss in enumerate(rows):
+            for orig, apc_id in ss:
+                substs.append((air_index, int(orig), row, id_to_index[int(apc_id)]))
+                width = max(width, int(orig) + 1)
+        airs.append((key, len(rows), width))
+    return airs, substs
+
+
 def synthetic_machine(width, n_constraints, seed=0):
     """Synthetic AIR with the pinned post-optimisation SHAPE of an APC (width, constraint count, degree <= 3;
     SURVEY.md §8d): column i belongs to constraint i % C; a constraint is the sum, over consecutive triples (x, y, z) of its

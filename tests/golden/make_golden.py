@@ -14,6 +14,9 @@ reference-derived fixtures and the oracle for the generated vectors):  python te
                                    small LDE / fold) -- regression pins for oracle and GPU alike
   segment_2p8_w12.json             a whole-segment proof produced by the oracle
   segment_logup_2p7.json           the same with bus interactions (LogUp phase, transcript v2): proof + digests of the opened values / queries
+  stage0_subs.json.gz              instruction opcodes + per-instruction substitution tables (`block`, `subs` sections) of
+                                   single_div_nondet, wasm_register_reuse and keccak_apc_pre_opt (677 instructions, 27 521 cells): the
+                                   REAL stage-0 gather pattern (the machines of the big fixture are not committed: 28 627 constraints)
   chips_mixed.json                 three chips of different heights under one transcript (orc_prove_chips): proof, cumulative sums, digests
 """
 import glob
@@ -65,6 +68,18 @@ def main():
             stats[name] = {"columns": mach.width, "constraints": len(mach.constraints), "bus_interactions": len(mach.bus_interactions),
                            "degree_hist": hist}
         dump("fixture_stats.json", stats)
+        st0 = {}
+        for name in ("single_div_nondet", "wasm_register_reuse", "keccak_apc_pre_opt"):
+            doc = json.load(gzip.open(os.path.join(REF, "autoprecompiles/tests/%s.json.gz" % name), "rt"))
+            mach = M.SymbolicMachine(doc["machine"]["constraints"], doc["machine"]["bus_interactions"], doc["machine"]["derived_columns"])
+            assert mach.column_ids == list(range(mach.width)), name           # pre-opt machines: contiguous poly ids, all used
+            ops = [ins[0] for b in doc["block"]["blocks"] for ins in b["instructions"]]
+            subs = [[[s_["original_poly_index"], s_["apc_poly_id"]] for s_ in ss] for ss in doc["subs"]]
+            assert len(ops) == len(subs)
+            st0[name] = {"n_columns": mach.width, "opcodes": ops, "subs": subs}
+        with gzip.GzipFile(os.path.join(HERE, "stage0_subs.json.gz"), "wb", mtime=0) as f:
+            f.write(json.dumps(st0, separators=(",", ":")).encode())
+        print("wrote stage0_subs.json.gz", os.path.getsize(os.path.join(HERE, "stage0_subs.json.gz")), "bytes")
     rng = np.random.default_rng(2024)
     kat = {}
     kat["perm_zero"] = orc.poseidon2_permute(np.zeros(16, dtype=np.uint32)).tolist()

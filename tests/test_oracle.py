@@ -467,3 +467,42 @@ def test_size_independent_properties_of_the_oracle(orc):
     lde_is_linear()
     fold_is_affine_in_beta()
     merkle_root_binds_every_element()
+
+
+# ---- stage 0 with the REAL substitution tables of the reference fixtures (tests/golden/stage0_subs.json.gz) ----
+def _stage0_fixture(name):
+    import gzip
+    with gzip.open(os.path.join(GOLDEN, "stage0_subs.json.gz"), "rt") as f:
+        return json.load(f)[name]
+
+
+def stage0_tables(name):
+    """(n_columns, airs [(key, row_block_size, width)], substs) of a fixture, via the host mirror of cuda/mod.rs:268-326"""
+    from powdr_b200 import machine as M
+    fx = _stage0_fixture(name)
+    airs, substs = M.compile_substitutions(fx["opcodes"], fx["subs"], {i: i for i in range(fx["n_columns"])})
+    return fx, airs, substs
+
+
+@pytest.mark.parametrize("name,n_instr,n_cols,n_airs", [("single_div_nondet", 1, 59, 1), ("wasm_register_reuse", 2, 64, 2),
+                                                         ("keccak_apc_pre_opt", 677, 27521, 10)])
+def test_substitution_tables_of_the_reference_fixtures(orc, name, n_instr, n_cols, n_airs):
+    """sizes pinned by SURVEY App. A (keccak: 677 instructions, 27 521 columns); every APC column is gathered from exactly one original
+    cell; an AIR's row block is as long as the number of its instructions in the block; the CPU mirror of `_apc_tracegen` then
+    reproduces a direct numpy statement of the gather on synthetic original traces"""
+    fx, airs, substs = stage0_tables(name)
+    assert len(fx["opcodes"]) == n_instr and fx["n_columns"] == n_cols and len(airs) == n_airs
+    assert sorted(s[3] for s in substs) == list(range(n_cols))
+    assert len({(a, c, r) for a, c, r, _ in substs}) == len(substs)
+    assert sum(rbs for _, rbs, _ in airs) == sum(1 for ss in fx["subs"] if ss)
+    for ai, (_, rbs, width) in enumerate(airs):
+        mine = [s for s in substs if s[0] == ai]
+        assert max(s[2] for s in mine) == rbs - 1 and max(s[1] for s in mine) == width - 1
+    num_calls, H = 5, 8
+    rng = np.random.default_rng(n_cols)
+    traces = [rand_field(rng, (width, rbs * H)) for _, rbs, width in airs]
+    out = orc.apc_tracegen(H, n_cols, [(t, rbs) for t, (_, rbs, _) in zip(traces, airs)], substs, num_calls)
+    for ai, col, row, apc_col in substs[:: max(1, len(substs) // 500)]:
+        rbs = airs[ai][1]
+        assert (out[apc_col, :num_calls] == traces[ai][col, row: rbs * num_calls: rbs]).all()
+        assert not out[apc_col, num_calls:].any()
