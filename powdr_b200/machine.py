@@ -264,6 +264,25 @@ def compile_bus(machine, height):
     return ints, spans, bc
 
 
+# OpenVM RV32IM opcode classes (first global opcode, number of opcodes, executing AIR) -- RECOLLECTED from the `#[opcode_offset = ..]`
+# attributes of openvm's rv32im transpiler crate (not in the reference tree).  What the tree does confirm: in the keccak fixture the
+# opcodes of one class agree on the original AIR's width (0x200-0x204: 36 columns, 0x205/0x206: 53, 0x210/0x213: 41, 0x221: 26,
+# 0x231: 18) and `single_div_nondet` is opcode 0x254 (tests/test_oracle.py::test_rv32_opcode_classes_agree_with_the_fixture_widths).
+RV32_OPCODE_CLASSES = [
+    (0x200, 5, "BaseAlu"), (0x205, 3, "Shift"), (0x208, 2, "LessThan"), (0x210, 6, "LoadStore"), (0x216, 2, "LoadSignExtend"),
+    (0x220, 2, "BranchEqual"), (0x225, 4, "BranchLessThan"), (0x230, 2, "JalLui"), (0x235, 1, "Jalr"), (0x240, 1, "Auipc"),
+    (0x250, 1, "Mul"), (0x251, 3, "MulH"), (0x254, 4, "DivRem"),
+]
+
+
+def rv32_air_of_opcode(op):
+    """opcode -> AIR key by opcode class (the role of `original_airs.opcode_to_air`); unknown opcodes are their own AIR"""
+    for first, count, name in RV32_OPCODE_CLASSES:
+        if first <= op < first + count:
+            return name
+    return op
+
+
 def compile_substitutions(opcodes, subs, id_to_index, opcode_to_air=None):
     """The (`OriginalAir`, `Subst`) tables of stage 0 from an APC's instruction list and its per-instruction substitutions, the way
     `PowdrTraceGeneratorGpu::try_generate_witness` assembles them (/root/reference/openvm/src/powdr_extension/trace_generator/cuda/mod.rs:268-326):

@@ -480,12 +480,25 @@ def stage0_tables(name):
     """(n_columns, airs [(key, row_block_size, width)], substs) of a fixture, via the host mirror of cuda/mod.rs:268-326"""
     from powdr_b200 import machine as M
     fx = _stage0_fixture(name)
-    airs, substs = M.compile_substitutions(fx["opcodes"], fx["subs"], {i: i for i in range(fx["n_columns"])})
+    airs, substs = M.compile_substitutions(fx["opcodes"], fx["subs"], {i: i for i in range(fx["n_columns"])}, M.rv32_air_of_opcode)
     return fx, airs, substs
 
 
+def test_rv32_opcode_classes_agree_with_the_fixture_widths():
+    """the recollected opcode classes against what the tree pins: all instructions that the class table sends to one AIR use the same
+    number of original columns (an AIR has ONE width), different classes differ, and the nondeterministic-division fixture is a DivRem
+    instruction"""
+    from powdr_b200 import machine as M
+    fx = _stage0_fixture("keccak_apc_pre_opt")
+    widths = {}
+    for op, ss in zip(fx["opcodes"], fx["subs"]):
+        widths.setdefault(M.rv32_air_of_opcode(op), set()).add((len(ss), max(o for o, _ in ss) + 1))
+    assert widths == {"BaseAlu": {(36, 36)}, "Shift": {(53, 53)}, "LoadStore": {(41, 41)}, "BranchEqual": {(26, 26)}, "JalLui": {(18, 18)}}
+    assert M.rv32_air_of_opcode(_stage0_fixture("single_div_nondet")["opcodes"][0]) == "DivRem"
+
+
 @pytest.mark.parametrize("name,n_instr,n_cols,n_airs", [("single_div_nondet", 1, 59, 1), ("wasm_register_reuse", 2, 64, 2),
-                                                         ("keccak_apc_pre_opt", 677, 27521, 10)])
+                                                         ("keccak_apc_pre_opt", 677, 27521, 5)])
 def test_substitution_tables_of_the_reference_fixtures(orc, name, n_instr, n_cols, n_airs):
     """sizes pinned by SURVEY App. A (keccak: 677 instructions, 27 521 columns); every APC column is gathered from exactly one original
     cell; an AIR's row block is as long as the number of its instructions in the block; the CPU mirror of `_apc_tracegen` then
