@@ -107,35 +107,3 @@ def test_argument_checks(ctx):
     assert lib.pb_prove_chips(ctx.h, arr, C.c_size_t(0), C.byref(proof), cs) == -1
     assert lib.pb_query_chips(ctx.h, None, C.c_size_t(0), None, C.c_size_t(0)) == -1          # nothing proved since the failure above
 
-
-def test_committed_fixtures_on_the_gpu(ctx):
-    """the GPU against the committed golden fixtures directly (no oracle call): the LogUp segment transcript and the multi-chip
-    transcript of tests/golden/ (regenerated by tests/golden/make_golden.py, reproduced on the CPU by tests/test_oracle_chips.py)"""
-    import hashlib
-    import json
-    import os
-    import sys
-    from powdr_b200 import machine as M
-    golden = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
-    sys.path.insert(0, golden)
-    from make_golden import chips_for
-    sha = lambda a: hashlib.sha256(np.ascontiguousarray(a, dtype=np.uint32).tobytes()).hexdigest()
-    g = json.load(open(os.path.join(golden, "segment_logup_2p7.json")))
-    assert (g["n_queries"], g["pow_bits"]) == (8, 4)                 # the parity contexts' FRI parameters (conftest.py)
-    base = M.synthetic_machine(g["width"], g["n_constraints"], seed=g["seed"])
-    mach = M.SymbolicMachine(base.constraints, M.synthetic_bus(base, g["n_interactions"], g["bus_seed"], g["quadratic_every"]))
-    bc, spans = M.compile_constraints(mach)
-    trace = rand_field(np.random.default_rng(g["trace_seed"]), (mach.width, 1 << g["log_n"]))
-    air = ctx.air(bc, spans, mach.width, M.compile_bus(mach, 1))
-    d = ctx.to_device(trace)
-    proof = ctx.prove_segment(air, d.ptr, g["log_n"], mach.width, on_device=True)
-    q, ys = ctx.query_segment(g["log_n"], mach.width, air.perm_width)
-    assert proof == g["proof"] and sha(ys) == g["ys_sha256"] and sha(q) == g["queries_sha256"]
-    g = json.load(open(os.path.join(golden, "chips_mixed.json")))
-    chips = chips_for([tuple(x) for x in g["spec"]], g["seed"])
-    ctx.set_fri_params(g["n_queries"], g["pow_bits"])
-    try:
-        proof, cs, ys, q = _gpu_prove(ctx, chips)
-    finally:
-        ctx.set_fri_params(8, 4)
-    assert proof == g["proof"] and cs.tolist() == g["cumsums"] and sha(ys) == g["ys_sha256"] and sha(q) == g["queries_sha256"]
