@@ -256,6 +256,28 @@ def test_bench_reference_arm_prints_one_contract_line():
     assert d["cpu_baseline"]["kind"] == "port" and d["e2e"]["h2d_bytes_per_step"] == 0 and d["e2e"]["value"] == d["value"]
 
 
+def test_bench_reference_arm_under_torchrun_prints_once_from_rank_0():
+    """the driver launches the reference arm like the native one at N > 1 (torchrun, one process per GPU): rank 0 alone times and prints,
+    the other ranks exit 0 without work, no process group is needed"""
+    import json
+    import socket
+    import subprocess
+    import sys
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    port = s.getsockname()[1]
+    s.close()
+    r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr", "127.0.0.1",
+                        "--master-port", str(port), os.path.join(ROOT, "bench.py"), "--impl", "reference", "--gpus", "2", "--steps", "1", "--warmup", "0",
+                        "--log-n", "10", "--width", "24", "--constraints", "5", "--interactions", "9", "--queries", "10", "--pow-bits", "6"],
+                       capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0, r.stderr[-2000:]
+    lines = [ln for ln in r.stdout.splitlines() if ln.startswith("{")]
+    assert len(lines) == 1
+    d = json.loads(lines[0])
+    assert d["impl"] == "reference" and d["n_gpus"] == 2 and d["value"] > 0 and d["cpu_baseline"]["kind"] == "port"
+
+
 def test_entry_points_reject_null_arguments_before_touching_the_device():
     """error behaviour of the boundary (cuda_abi.rs convention: an int comes back, nothing aborts): every compute entry point
     returns PB_ERR_INVALID_ARG for null handles / pointers -- checked here without a GPU"""
