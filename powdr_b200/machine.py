@@ -264,6 +264,25 @@ def compile_bus(machine, height):
     return ints, spans, bc
 
 
+def periphery_from_bus_map(bus_map):
+    """The periphery bus ids and table sizes stage 0's histogram kernel needs (`self.periphery.bus_ids.*`, `tuple_range_checker_chip.sizes`,
+    /root/reference/openvm/src/powdr_extension/trace_generator/cuda/mod.rs:359-372) out of the `bus_map` section of the reference's APC
+    JSON export (`BusMap<OpenVmBusType>`): {"bus_ids": {"3": {"Other": "VariableRangeChecker"}, "6": {"Other":
+    "BitwiseLookup"}, "7": {"Other": {"TupleRangeChecker": [256, 2048]}}, ...}}.
+    -> dict(var_bus, bitwise_bus, tuple2_bus, tuple2_sizes); a missing periphery bus maps to None."""
+    out = {"var_bus": None, "bitwise_bus": None, "tuple2_bus": None, "tuple2_sizes": None}
+    for bus_id, kind in (bus_map or {}).get("bus_ids", {}).items():
+        other = kind.get("Other") if isinstance(kind, dict) else None
+        if other == "VariableRangeChecker":
+            out["var_bus"] = int(bus_id)
+        elif other == "BitwiseLookup":
+            out["bitwise_bus"] = int(bus_id)
+        elif isinstance(other, dict) and "TupleRangeChecker" in other:
+            out["tuple2_bus"] = int(bus_id)
+            out["tuple2_sizes"] = tuple(int(x) for x in other["TupleRangeChecker"])
+    return out
+
+
 # OpenVM RV32IM opcode classes (first global opcode, number of opcodes, executing AIR) -- RECOLLECTED from the `#[opcode_offset = ..]`
 # attributes of openvm's rv32im transpiler crate (not in the reference tree).  What the tree does confirm: in the keccak fixture the
 # opcodes of one class agree on the original AIR's width (0x200-0x204: 36 columns, 0x205/0x206: 53, 0x210/0x213: 41, 0x221: 26,

@@ -62,6 +62,18 @@ def test_derived_and_bus_compilers_follow_reference_layout():
     assert bbc[spans[2][0]:spans[2][0] + spans[2][1]] == [1, 17]
 
 
+def test_periphery_bus_ids_come_from_the_fixture_bus_map():
+    """the bus ids / tuple-checker sizes the histogram kernel is called with (cuda/mod.rs:359-372) read from the `bus_map` of the reference
+    fixtures; they are also the defaults of `Context.bus_compile` / `_apc_apply_bus` callers here"""
+    import json
+    from powdr_b200 import machine as M
+    a = json.load(open(os.path.join(GOLDEN, "single_div_nondet.machine.json")))
+    assert M.periphery_from_bus_map(a["bus_map"]) == {"var_bus": 3, "bitwise_bus": 6, "tuple2_bus": 7, "tuple2_sizes": (256, 2048)}
+    b = json.load(open(os.path.join(GOLDEN, "wasm_register_reuse.machine.json")))
+    assert M.periphery_from_bus_map(b["bus_map"])["tuple2_sizes"] == (256, 4096)
+    assert M.periphery_from_bus_map(None)["var_bus"] is None
+
+
 def test_stack_depth_of_fixtures_fits_reference_capacity():
     from powdr_b200 import machine as M
     mach = M.SymbolicMachine.from_json_file(os.path.join(GOLDEN, "single_div_nondet.machine.json"))
