@@ -437,21 +437,35 @@ def sharded_segment(a, ctx, air, dist, dev, stream, world, rank):
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         return float(t.item()), pr
 
+    q_state = {"on": bool(a.queries), "error": None}
+
+    def sharded_queries():
+        # a library error here is symmetric across ranks (same arguments, same state): record it once and keep the proof-only line
+        if not q_state["on"]:
+            return None
+        try:
+            return ctx.query_segment_sharded(comm, a.log_n, w, air.perm_width)
+        except Exception as e:      # noqa: BLE001
+            q_state["on"], q_state["error"] = False, repr(e)
+            return None
+
     def step_dev():
         # the same unit of work as the N = 1 step: proof AND the query openings (pb_query_segment_sharded: one more all-gather)
         pr = ctx.prove_segment_sharded(air, mine.data_ptr() if count else 0, a.log_n, w, comm, on_device=True)
-        return pr, (ctx.query_segment_sharded(comm, a.log_n, w, air.perm_width) if a.queries else None)
+        return pr, sharded_queries()
 
     sec, (proof, queries) = timed(step_dev)
     stages = ctx.last_stage_ms()
     calls, nbytes = comm.calls, comm.bytes
-    same = proof == single and (queries is None or bool((queries == single_q).all()))
+    same = proof == single and (queries is None or bool((queries == single_q).all())) and q_state["error"] is None
     ok = torch.tensor([1 if same else 0], dtype=torch.int32, device=dev)
     dist.all_reduce(ok, op=dist.ReduceOp.MIN)
     out = {"value": sec, "unit": "s", "scaling": "strong", "single_gpu_s": single_ms / 1e3, "speedup": single_ms / 1e3 / sec,
            "proof_equals_single_gpu": bool(ok.item()), "stages_ms": stages,
            "collectives_per_segment": calls // max(1, a.steps + max(2, min(3, a.warmup))),
            "collective_bytes_per_rank_per_segment": nbytes // max(1, a.steps + max(2, min(3, a.warmup)))}
+    if q_state["error"]:
+        out["query_phase_error"] = q_state["error"]
     if not a.no_e2e:
         host = torch.empty((max(1, count), n), dtype=torch.int32, pin_memory=True)
         if count:
@@ -459,8 +473,7 @@ def sharded_segment(a, ctx, air, dist, dev, stream, world, rank):
         torch.cuda.synchronize()
         def step_host():
             pr = ctx.prove_segment_sharded(air, host.data_ptr() if count else 0, a.log_n, w, comm, on_device=False)
-            if a.queries:
-                ctx.query_segment_sharded(comm, a.log_n, w, air.perm_width)
+            sharded_queries()
             return pr
 
         esec, eproof = timed(step_host)
