@@ -384,3 +384,13 @@ def test_host_transcript_permutation_kat_and_simd_equals_scalar():
         assert list(a) == list(b) == exp.tolist()
     assert lib.pb_host_poseidon2_permute(None, 1, 0, None) == -1
     assert used.value in (0, 1)
+
+
+def test_host_transcript_generic_diagonal_branch(tmp_path):
+    """tests/host_transcript_check.cpp: AVX-512 vs scalar host permutation with a non-default internal diagonal, 50 k chained permutations"""
+    import subprocess
+    exe = str(tmp_path / "htc")
+    subprocess.check_call(["g++", "-std=c++17", "-O2", "-o", exe, os.path.join(ROOT, "tests", "host_transcript_check.cpp"),
+                           os.path.join(ROOT, "powdr_b200", "csrc", "transcript_host.cpp")])
+    r = subprocess.run([exe], capture_output=True, text=True, timeout=120)
+    assert r.returncode == 0 and "bad=0" in r.stdout, r.stdout + r.stderr
